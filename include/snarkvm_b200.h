@@ -1,0 +1,124 @@
+/*
+ * snarkvm_b200 — C ABI of the B200 (sm_100a) proving backend for snarkVM's two hot paths:
+ *   VariableBase::msm over BLS12-377 G1 and the radix-2 EvaluationDomain NTT over Fr.
+ *
+ * PART 1 is the drop-in boundary: the three symbols the reference's Rust FFI binds
+ * (declared at /root/reference/algorithms/cuda/src/lib.rs:42-69, defined by the reference at
+ * algorithms/cuda/cuda/snarkvm_api.cu:52-84).  Same names, argument order, data layouts and
+ * error convention, so `snarkvm-algorithms-cuda` links against this library unchanged
+ * (see INTEGRATION.md).
+ *
+ * PART 2 is the extended, device-resident API (pointers already in HBM) used by the
+ * host mirror, bench.py and multi-GPU sharding.
+ *
+ * Data layouts (identical to the reference's in-memory Rust types):
+ *   Fr element   : 32 B, 4 x u64 little-endian limbs, Montgomery form  (fields/src/fp_256.rs:52)
+ *   MSM scalar   : 32 B, canonical integer < r, NOT Montgomery         (BigInteger256; snarkvm.cu:275 mont=false)
+ *   G1 affine    : x[48] y[48] (Montgomery Fq) infinity[1] pad -> 104-byte stride
+ *                  (curves/src/templates/short_weierstrass_jacobian/affine.rs:41-46; lib.rs:161)
+ *   G1 projective: X[48] Y[48] Z[48] Jacobian, infinity <=> Z == 0     (projective.rs:36-60)
+ */
+#ifndef SNARKVM_B200_H
+#define SNARKVM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SNARKVM_API __attribute__((visibility("default")))
+#else
+#define SNARKVM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * PART 1 — drop-in replacements for the reference FFI
+ * ---------------------------------------------------------------------------------------- */
+
+/* #[repr(C)] enums of algorithms/cuda/src/lib.rs:22-40 */
+typedef enum { SNARKVM_NTT_NN = 0, SNARKVM_NTT_NR = 1, SNARKVM_NTT_RN = 2, SNARKVM_NTT_RR = 3 } snarkvm_ntt_order_t;
+typedef enum { SNARKVM_NTT_FORWARD = 0, SNARKVM_NTT_INVERSE = 1 } snarkvm_ntt_direction_t;
+typedef enum { SNARKVM_NTT_STANDARD = 0, SNARKVM_NTT_COSET = 1 } snarkvm_ntt_type_t;
+
+/* `cuda::Error` of sppark::cuda_error!() (lib.rs:19), returned BY VALUE.  The Rust side reads
+ * .code (lib.rs:93,141,164; 0 = success, otherwise a cudaError_t) and frees .message, which is
+ * therefore malloc()ed or NULL (shape evidenced at algorithms/cuda/cuda/snarkvm.cu:279). */
+typedef struct {
+    int code;
+    char* message;
+} snarkvm_error_t;
+
+/* Replaces `snarkvm_ntt` (lib.rs:43-49 ; snarkvm_api.cu:53-62 ; called from
+ * algorithms/src/fft/domain.rs:375-388, 404-417, 425-438).  In-place transform of 2^lg_domain_size
+ * Fr elements in HOST memory.  Only NN order is implemented (the only order any reference caller
+ * passes); other orders return cudaErrorNotSupported, which makes the Rust caller fall back to CPU.
+ * On failure `inout` is left untouched. */
+SNARKVM_API snarkvm_error_t snarkvm_ntt(void* inout, uint32_t lg_domain_size, snarkvm_ntt_order_t ntt_order,
+                            snarkvm_ntt_direction_t ntt_direction, snarkvm_ntt_type_t ntt_type);
+
+/* Replaces `snarkvm_polymul` (lib.rs:51-60 ; snarkvm_api.cu:64-75 ; called from
+ * algorithms/src/fft/polynomial/multiplier.rs:79-95).  out[2^lg] = iNTT( prod NTT(pad(poly_i)) * prod eval_j ).
+ * polynomials: const Fr* [pcount] with lengths plens[] (<= 2^lg); evaluations: const Fr* [ecount] in natural
+ * order with elens[] == 2^lg.  0 operands: success, out untouched. */
+SNARKVM_API snarkvm_error_t snarkvm_polymul(void* out, size_t pcount, const void* polynomials, const void* plens, size_t ecount,
+                                const void* evaluations, const void* elens, uint32_t lg_domain_size);
+
+/* Replaces `snarkvm_msm` (lib.rs:62-68 ; snarkvm_api.cu:77-83 ; called from
+ * algorithms/src/msm/variable_base/mod.rs:33-42).  out (144 B) = sum scalars[i] * points[i], i < npoints.
+ * The result is written NORMALISED (Z = Montgomery one, or (0, R, 0) for infinity), i.e. the bytes of
+ * `reference_result.to_affine().to_projective()`. */
+SNARKVM_API snarkvm_error_t snarkvm_msm(void* out, const void* points_with_infinity, size_t npoints, const void* scalars,
+                            size_t ffi_affine_sz);
+
+/* ------------------------------------------------------------------------------------------
+ * PART 2 — extended API.  `d_` pointers are device pointers on the CURRENT device; `stream` is a
+ * cudaStream_t (NULL = legacy default stream).  All functions return 0 or a cudaError_t.
+ * ---------------------------------------------------------------------------------------- */
+
+SNARKVM_API const char* snarkvm_b200_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+SNARKVM_API uint64_t snarkvm_b200_launch_count(void);
+
+/* In-place NN transform of 2^lg Fr elements resident in HBM.  d_scratch: 2^lg elements or NULL. */
+SNARKVM_API int snarkvm_b200_ntt_device(void* d_inout, uint32_t lg, int ntt_order, int ntt_direction, int ntt_type,
+                            void* d_scratch, void* stream);
+
+/* Device-resident polymul: d_out[2^lg]; polys/evals are HOST arrays of device pointers. */
+SNARKVM_API int snarkvm_b200_polymul_device(void* d_out, size_t pcount, const void* const* d_polys, const size_t* plens,
+                                size_t ecount, const void* const* d_evals, const size_t* elens, uint32_t lg,
+                                void* stream);
+
+/* Window/bucket plan the MSM will use for npoints (signed c-bit digits). */
+SNARKVM_API int snarkvm_b200_msm_plan(size_t npoints, int* c, int* nwin, uint32_t* cap);
+
+/* Full MSM with bases and scalars resident in HBM; out144 is HOST memory (normalised projective). */
+SNARKVM_API int snarkvm_b200_msm_device(void* out144, const void* d_points, size_t npoints, const void* d_scalars,
+                            size_t stride, void* stream);
+
+/* MSM pieces for multi-GPU sharding: per-window sums as XYZZ points (192 B each) in HBM ... */
+SNARKVM_API int snarkvm_b200_msm_window_sums_device(void* d_window_sums /* nwin * 192 B */, const void* d_points, size_t npoints,
+                                        const void* d_scalars, size_t stride, void* stream);
+/* ... summed across ranks after an all-gather: d_out[i] = sum_r d_in[r][i] ... */
+SNARKVM_API int snarkvm_b200_xyzz_sum_ranks_device(void* d_out, const void* d_in, int nranks, int count, void* stream);
+/* ... and folded on the host: out144 = sum_w 2^(c*w) * window_sums[w]  (h_window_sums in HOST memory). */
+SNARKVM_API int snarkvm_b200_msm_finish(void* out144, const void* h_window_sums, int nwin, int c);
+
+/* KZG10::commit core (algorithms/src/polycommit/kzg10/mod.rs:98-156): Montgomery coefficients ->
+ * canonical (to_bigint, :455-474) -> MSM against resident powers.  out144 is HOST memory. */
+SNARKVM_API int snarkvm_b200_kzg_commit_device(void* out144, const void* d_powers, size_t stride, const void* d_coeffs_mont,
+                                   size_t ncoeffs, void* stream);
+
+/* Fr Montgomery <-> canonical, n elements in HBM (to_bigint / from_bigint, fields/src/fp_256.rs:362-413). */
+SNARKVM_API int snarkvm_b200_fr_from_mont_device(void* d_out, const void* d_in, size_t n, void* stream);
+SNARKVM_API int snarkvm_b200_fr_to_mont_device(void* d_out, const void* d_in, size_t n, void* stream);
+
+/* Deterministic synthetic bases P_i = h(seed, i) * G written in the reference affine layout. */
+SNARKVM_API int snarkvm_b200_generate_bases_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNARKVM_B200_H */

@@ -182,3 +182,13 @@ def batch_affine_add(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     out = np.zeros_like(a)
     lib().oracle_batch_affine_add(_p(out), _p(a), _p(b), ctypes.c_size_t(a.shape[0]))
     return out
+
+
+def fr_dot_canonical(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Σ a_i·b_i mod r on canonical uint64 [n, 4] arrays → canonical uint64[4]."""
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+    assert a.shape == b.shape
+    out = np.zeros(4, dtype=np.uint64)
+    lib().oracle_fr_dot_canonical(_p(out), _p(a), _p(b), ctypes.c_size_t(a.shape[0]))
+    return out

@@ -693,6 +693,24 @@ API void oracle_fq_from_mont(uint64_t *out, const uint64_t *in, size_t n) {
     for (size_t i = 0; i < n; i++) fq_mul((fq_t *)(out + 6 * i), (const fq_t *)(in + 6 * i), &one);
 }
 
+
+/* Σ a_i·b_i mod r for canonical (non-Montgomery) 4-limb inputs; result canonical.  Used by the
+ * full-size MSM property test: Σ s_i·(k_i·G) = (Σ s_i·k_i)·G. */
+API void oracle_fr_dot_canonical(uint64_t *out, const uint64_t *a, const uint64_t *b, size_t n) {
+    fr_t total = {{0, 0, 0, 0}};
+#pragma omp parallel
+    {
+        fr_t local = {{0, 0, 0, 0}};
+#pragma omp for schedule(static)
+        for (size_t i = 0; i < n; i++) { fr_t t; fr_mul(&t, (const fr_t *)(a + 4 * i), (const fr_t *)(b + 4 * i)); fr_add(&local, &local, &t); }
+#pragma omp critical
+        fr_add(&total, &total, &local);
+    }
+    fr_t r2; memcpy(r2.l, FR_R2, 32);
+    fr_mul(&total, &total, &r2);            /* (Σ a·b·R^{-1})·R2·R^{-1} = Σ a·b */
+    memcpy(out, total.l, 32);
+}
+
 /* Same contract as snarkvm_ntt (algorithms/cuda/src/lib.rs:42-49): in place, NN order only.
  * direction 0 = Forward, 1 = Inverse ; type 0 = Standard, 1 = Coset. */
 API int oracle_ntt(uint64_t *inout, uint32_t lg, int order, int direction, int type) {

@@ -1,0 +1,283 @@
+// C ABI (include/snarkvm_b200.h): the three drop-in symbols of the reference FFI
+// (/root/reference/algorithms/cuda/src/lib.rs:42-69) plus the device-resident extended API.
+// Error contract: never throw or abort across the boundary; return a
+// cudaError_t code; leave outputs untouched on failure so the Rust caller can fall back.
+#include "../../include/snarkvm_b200.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "host_ec.hpp"
+#include "msm.cuh"
+#include "ntt.cuh"
+
+using namespace b200;
+
+namespace {
+
+snarkvm_error_t make_error(int code) {
+    snarkvm_error_t e;
+    e.code = code;
+    e.message = nullptr;
+    if (code != 0) {
+        const char* s = cudaGetErrorString((cudaError_t)code);
+        if (s) { size_t n = strlen(s) + 1; e.message = (char*)malloc(n); if (e.message) memcpy(e.message, s, n); }
+    }
+    return e;
+}
+
+// One non-blocking stream per (host thread, device): the FFI is entered concurrently from many
+// rayon workers (sonic_pc/mod.rs:186-245), so calls must not serialise on the default stream.
+struct ThreadCtx {
+    cudaStream_t stream[64] = {};
+    bool have[64] = {};
+    ~ThreadCtx() {}
+};
+thread_local ThreadCtx t_ctx;
+std::once_flag g_pool_once[64];
+
+int thread_stream(cudaStream_t* out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    dev &= 63;
+    std::call_once(g_pool_once[dev], [dev] {
+        // keep freed scratch in the stream-ordered pool instead of returning it to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    });
+    if (!t_ctx.have[dev]) {
+        e = cudaStreamCreateWithFlags(&t_ctx.stream[dev], cudaStreamNonBlocking);
+        if (e != cudaSuccess) return (int)e;
+        t_ctx.have[dev] = true;
+    }
+    *out = t_ctx.stream[dev];
+    return 0;
+}
+
+void write_infinity(void* out144) {
+    host::Xyzz inf = host::xyzz_inf();
+    host::xyzz_to_normalised_projective(inf, (uint64_t*)out144);
+}
+
+int msm_device_impl(void* out144, const void* d_points, size_t npoints, const void* d_scalars, size_t stride,
+                    cudaStream_t stream) {
+    if (npoints == 0) { write_infinity(out144); return 0; }
+    if (stride < 104 || (stride & 7)) return (int)cudaErrorInvalidValue;
+    MsmPlan plan = msm_make_plan(npoints);
+    uint32_t* d_sums = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&d_sums, (size_t)plan.nwin * 192, stream);
+    if (e != cudaSuccess) return (int)e;
+    int rc = msm_window_sums_device(d_sums, plan, d_points, stride, d_scalars, npoints, stream);
+    std::vector<host::Xyzz> sums((size_t)plan.nwin);
+    if (rc == 0) rc = (int)cudaMemcpyAsync(sums.data(), d_sums, (size_t)plan.nwin * 192, cudaMemcpyDeviceToHost, stream);
+    cudaFreeAsync(d_sums, stream);
+    if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
+    if (rc != 0) return rc;
+    host::Xyzz total = host::horner_windows(sums.data(), plan.nwin, plan.c);
+    host::xyzz_to_normalised_projective(total, (uint64_t*)out144);
+    return 0;
+}
+
+int polymul_device_impl(void* d_out, size_t pcount, const void* const* d_polys, const size_t* plens, size_t ecount,
+                        const void* const* d_evals, const size_t* elens, uint32_t lg, cudaStream_t stream) {
+    const size_t n = (size_t)1 << lg, bytes = n * 32;
+    if (pcount + ecount == 0) return 0;
+    for (size_t i = 0; i < pcount; i++) if (plens[i] > n) return (int)cudaErrorInvalidValue;
+    for (size_t i = 0; i < ecount; i++) if (elens[i] != n) return (int)cudaErrorInvalidValue;   // polynomial.cuh:95
+    void *tmp = nullptr, *scratch = nullptr;
+    cudaError_t e;
+    if ((e = cudaMallocAsync(&tmp, bytes, stream)) != cudaSuccess) return (int)e;
+    if ((e = cudaMallocAsync(&scratch, bytes, stream)) != cudaSuccess) { cudaFreeAsync(tmp, stream); return (int)e; }
+    int rc = 0;
+    bool have = false;
+    for (size_t i = 0; i < pcount && rc == 0; i++) {
+        void* dst = have ? tmp : d_out;
+        rc = (int)cudaMemsetAsync(dst, 0, bytes, stream);
+        if (rc == 0 && plens[i]) rc = (int)cudaMemcpyAsync(dst, d_polys[i], plens[i] * 32, cudaMemcpyDeviceToDevice, stream);
+        if (rc == 0) rc = ntt_device(dst, lg, NTT_FORWARD, NTT_STANDARD, scratch, stream);
+        if (rc == 0 && have) rc = fr_pointwise_mul_device(d_out, tmp, n, stream);
+        have = true;
+    }
+    for (size_t i = 0; i < ecount && rc == 0; i++) {
+        if (have) rc = fr_pointwise_mul_device(d_out, d_evals[i], n, stream);
+        else rc = (int)cudaMemcpyAsync(d_out, d_evals[i], bytes, cudaMemcpyDeviceToDevice, stream);
+        have = true;
+    }
+    if (rc == 0) rc = ntt_device(d_out, lg, NTT_INVERSE, NTT_STANDARD, scratch, stream);
+    cudaFreeAsync(tmp, stream);
+    cudaFreeAsync(scratch, stream);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* snarkvm_b200_version(void) { return "snarkvm_b200 0.1 (sm_100a)"; }
+uint64_t snarkvm_b200_launch_count(void) { return launch_count(); }
+
+// ----------------------------------------------------------------------------------------
+// PART 1 — drop-in symbols
+// ----------------------------------------------------------------------------------------
+snarkvm_error_t snarkvm_ntt(void* inout, uint32_t lg, snarkvm_ntt_order_t order, snarkvm_ntt_direction_t dir,
+                            snarkvm_ntt_type_t type) {
+    if (order != SNARKVM_NTT_NN) return make_error((int)cudaErrorNotSupported);
+    if (lg > NTT_MAX_LG || !inout) return make_error((int)cudaErrorInvalidValue);
+    cudaStream_t stream;
+    int rc = thread_stream(&stream);
+    if (rc) return make_error(rc);
+    const size_t bytes = ((size_t)1 << lg) * 32;
+    void *d = nullptr, *scratch = nullptr;
+    rc = (int)cudaMallocAsync(&d, bytes, stream);
+    if (rc == 0) rc = (int)cudaMallocAsync(&scratch, bytes, stream);
+    if (rc == 0) rc = (int)cudaMemcpyAsync(d, inout, bytes, cudaMemcpyHostToDevice, stream);
+    if (rc == 0) rc = ntt_device(d, lg, (int)dir, (int)type, scratch, stream);
+    if (rc == 0) rc = (int)cudaStreamSynchronize(stream);          // only copy back on success (snarkvm.cu:178-183)
+    if (rc == 0) rc = (int)cudaMemcpyAsync(inout, d, bytes, cudaMemcpyDeviceToHost, stream);
+    if (d) cudaFreeAsync(d, stream);
+    if (scratch) cudaFreeAsync(scratch, stream);
+    int rs = (int)cudaStreamSynchronize(stream);
+    return make_error(rc ? rc : rs);
+}
+
+snarkvm_error_t snarkvm_polymul(void* out, size_t pcount, const void* polynomials, const void* plens_v, size_t ecount,
+                                const void* evaluations, const void* elens_v, uint32_t lg) {
+    if (pcount + ecount == 0) return make_error(0);                 // snarkvm.cu:195-197
+    if (lg > NTT_MAX_LG || !out) return make_error((int)cudaErrorInvalidValue);
+    const void* const* polys = (const void* const*)polynomials;
+    const void* const* evals = (const void* const*)evaluations;
+    const size_t* plens = (const size_t*)plens_v;
+    const size_t* elens = (const size_t*)elens_v;
+    const size_t n = (size_t)1 << lg, bytes = n * 32;
+    for (size_t i = 0; i < pcount; i++) if (plens[i] > n) return make_error((int)cudaErrorInvalidValue);
+    for (size_t i = 0; i < ecount; i++) if (elens[i] != n) return make_error((int)cudaErrorInvalidValue);
+    cudaStream_t stream;
+    int rc = thread_stream(&stream);
+    if (rc) return make_error(rc);
+    std::vector<void*> dbuf(pcount + ecount, nullptr);
+    std::vector<const void*> dp(pcount), de(ecount);
+    void* d_out = nullptr;
+    rc = (int)cudaMallocAsync(&d_out, bytes, stream);
+    for (size_t i = 0; i < pcount && rc == 0; i++) {
+        size_t b = plens[i] ? plens[i] * 32 : 32;
+        rc = (int)cudaMallocAsync(&dbuf[i], b, stream);
+        if (rc == 0 && plens[i]) rc = (int)cudaMemcpyAsync(dbuf[i], polys[i], plens[i] * 32, cudaMemcpyHostToDevice, stream);
+        dp[i] = dbuf[i];
+    }
+    for (size_t i = 0; i < ecount && rc == 0; i++) {
+        rc = (int)cudaMallocAsync(&dbuf[pcount + i], bytes, stream);
+        if (rc == 0) rc = (int)cudaMemcpyAsync(dbuf[pcount + i], evals[i], bytes, cudaMemcpyHostToDevice, stream);
+        de[i] = dbuf[pcount + i];
+    }
+    if (rc == 0) rc = polymul_device_impl(d_out, pcount, dp.data(), plens, ecount, de.data(), elens, lg, stream);
+    if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
+    if (rc == 0) rc = (int)cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, stream);
+    for (void* p : dbuf) if (p) cudaFreeAsync(p, stream);
+    if (d_out) cudaFreeAsync(d_out, stream);
+    int rs = (int)cudaStreamSynchronize(stream);
+    return make_error(rc ? rc : rs);
+}
+
+snarkvm_error_t snarkvm_msm(void* out, const void* points, size_t npoints, const void* scalars, size_t ffi_affine_sz) {
+    if (!out) return make_error((int)cudaErrorInvalidValue);
+    if (npoints == 0) { write_infinity(out); return make_error(0); }
+    if (!points || !scalars || ffi_affine_sz < 104 || (ffi_affine_sz & 7)) return make_error((int)cudaErrorInvalidValue);
+    cudaStream_t stream;
+    int rc = thread_stream(&stream);
+    if (rc) return make_error(rc);
+    void *d_points = nullptr, *d_scalars = nullptr;
+    rc = (int)cudaMallocAsync(&d_points, npoints * ffi_affine_sz, stream);
+    if (rc == 0) rc = (int)cudaMallocAsync(&d_scalars, npoints * 32, stream);
+    if (rc == 0) rc = (int)cudaMemcpyAsync(d_scalars, scalars, npoints * 32, cudaMemcpyHostToDevice, stream);
+    if (rc == 0) rc = (int)cudaMemcpyAsync(d_points, points, npoints * ffi_affine_sz, cudaMemcpyHostToDevice, stream);
+    uint64_t result[18];
+    if (rc == 0) rc = msm_device_impl(result, d_points, npoints, d_scalars, ffi_affine_sz, stream);
+    if (d_points) cudaFreeAsync(d_points, stream);
+    if (d_scalars) cudaFreeAsync(d_scalars, stream);
+    int rs = (int)cudaStreamSynchronize(stream);
+    if (rc == 0 && rs == 0) memcpy(out, result, 144);
+    return make_error(rc ? rc : rs);
+}
+
+// ----------------------------------------------------------------------------------------
+// PART 2 — extended device-resident API
+// ----------------------------------------------------------------------------------------
+int snarkvm_b200_ntt_device(void* d_inout, uint32_t lg, int order, int dir, int type, void* d_scratch, void* stream) {
+    if (order != SNARKVM_NTT_NN) return (int)cudaErrorNotSupported;
+    return ntt_device(d_inout, lg, dir, type, d_scratch, (cudaStream_t)stream);
+}
+
+int snarkvm_b200_polymul_device(void* d_out, size_t pcount, const void* const* d_polys, const size_t* plens, size_t ecount,
+                                const void* const* d_evals, const size_t* elens, uint32_t lg, void* stream) {
+    if (lg > NTT_MAX_LG) return (int)cudaErrorInvalidValue;
+    return polymul_device_impl(d_out, pcount, d_polys, plens, ecount, d_evals, elens, lg, (cudaStream_t)stream);
+}
+
+int snarkvm_b200_msm_plan(size_t npoints, int* c, int* nwin, uint32_t* cap) {
+    MsmPlan p = msm_make_plan(npoints);
+    if (c) *c = p.c;
+    if (nwin) *nwin = p.nwin;
+    if (cap) *cap = p.cap;
+    return 0;
+}
+
+int snarkvm_b200_msm_device(void* out144, const void* d_points, size_t npoints, const void* d_scalars, size_t stride,
+                            void* stream) {
+    if (!out144) return (int)cudaErrorInvalidValue;
+    return msm_device_impl(out144, d_points, npoints, d_scalars, stride, (cudaStream_t)stream);
+}
+
+int snarkvm_b200_msm_window_sums_device(void* d_window_sums, const void* d_points, size_t npoints, const void* d_scalars,
+                                        size_t stride, void* stream) {
+    if (stride < 104 || (stride & 7) || npoints == 0) return (int)cudaErrorInvalidValue;
+    MsmPlan plan = msm_make_plan(npoints);
+    return msm_window_sums_device((uint32_t*)d_window_sums, plan, d_points, stride, d_scalars, npoints, (cudaStream_t)stream);
+}
+
+int snarkvm_b200_xyzz_sum_ranks_device(void* d_out, const void* d_in, int nranks, int count, void* stream) {
+    if (nranks < 1 || count < 1) return (int)cudaErrorInvalidValue;
+    return xyzz_sum_ranks_device((uint32_t*)d_out, (const uint32_t*)d_in, nranks, count, (cudaStream_t)stream);
+}
+
+int snarkvm_b200_msm_finish(void* out144, const void* h_window_sums, int nwin, int c) {
+    if (!out144 || !h_window_sums || nwin < 1 || c < 0) return (int)cudaErrorInvalidValue;
+    std::vector<host::Xyzz> sums((size_t)nwin);
+    memcpy(sums.data(), h_window_sums, (size_t)nwin * 192);
+    host::Xyzz total = host::horner_windows(sums.data(), nwin, c);
+    host::xyzz_to_normalised_projective(total, (uint64_t*)out144);
+    return 0;
+}
+
+int snarkvm_b200_kzg_commit_device(void* out144, const void* d_powers, size_t stride, const void* d_coeffs_mont,
+                                   size_t ncoeffs, void* stream_v) {
+    if (!out144) return (int)cudaErrorInvalidValue;
+    if (ncoeffs == 0) { write_infinity(out144); return 0; }
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    void* d_plain = nullptr;
+    int rc = (int)cudaMallocAsync(&d_plain, ncoeffs * 32, stream);
+    if (rc == 0) rc = fr_from_mont_device(d_plain, d_coeffs_mont, ncoeffs, stream);
+    if (rc == 0) rc = msm_device_impl(out144, d_powers, ncoeffs, d_plain, stride, stream);
+    if (d_plain) cudaFreeAsync(d_plain, stream);
+    return rc;
+}
+
+int snarkvm_b200_fr_from_mont_device(void* d_out, const void* d_in, size_t n, void* stream) {
+    return fr_from_mont_device(d_out, d_in, n, (cudaStream_t)stream);
+}
+int snarkvm_b200_fr_to_mont_device(void* d_out, const void* d_in, size_t n, void* stream) {
+    return fr_to_mont_device(d_out, d_in, n, (cudaStream_t)stream);
+}
+
+int snarkvm_b200_generate_bases_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, void* stream) {
+    return msm_generate_bases_device(d_points, npoints, stride, seed, (cudaStream_t)stream);
+}
+
+}  // extern "C"

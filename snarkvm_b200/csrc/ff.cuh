@@ -1,0 +1,271 @@
+// Montgomery prime-field arithmetic on 32-bit limbs for sm_100a.
+//
+// Device restatement of the arithmetic of the reference's
+//   Fp256<FrParameters>  (fields/src/fp_256.rs:52, mul :754-817, add/sub :730-750)
+//   Fp384<FqParameters>  (fields/src/fp_384.rs:52, mul :771-899)
+// Values are the SAME numbers as the reference keeps in memory: little-endian
+// limbs of (v · 2^{32N}) mod p, always fully reduced (< p), so a device value
+// stored to HBM is byte-identical to the Rust `Fp256.0.0` / `Fp384.0.0` image.
+//
+// Multiplication is a word-serial interleaved Montgomery product built from
+// two carry chains per row ("even" columns and "odd" columns) so that every
+// 32x32->64 product lands in an aligned register pair and ptxas can fuse the
+// mad.lo.cc / madc.hi.cc pairs into IMAD.WIDE.U32(.X) on the fma pipe.
+// No tensor cores: this is integer modular arithmetic (BASELINE.json north_star).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------
+// PTX carry-chain primitives.  Each is one instruction; the CC flag carries
+// between consecutive statements (asm volatile keeps their order).
+// ---------------------------------------------------------------------------
+#define FF_DEV __device__ __forceinline__
+
+FF_DEV uint32_t ptx_add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FF_DEV uint32_t ptx_addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FF_DEV uint32_t ptx_addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FF_DEV uint32_t ptx_sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FF_DEV uint32_t ptx_subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FF_DEV uint32_t ptx_subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FF_DEV uint32_t ptx_mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FF_DEV uint32_t ptx_mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FF_DEV uint32_t ptx_mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+FF_DEV uint32_t ptx_madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+FF_DEV uint32_t ptx_madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+FF_DEV uint32_t ptx_madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+
+// ---------------------------------------------------------------------------
+// Row helpers.  A running value V is held as two N-limb arrays:
+//     V = sum e[k]·2^{32k}  +  sum o[k]·2^{32(k+1)}
+// ("o" is offset by one limb).  Products x[j]·y with even j feed e, odd j feed o.
+// ---------------------------------------------------------------------------
+template <int N>
+FF_DEV void row_mul(uint32_t (&acc)[N], const uint32_t* x, uint32_t y) {
+    // acc = sum_{j even} x[j]·y·2^{32j}   (x already points at the first column)
+#pragma unroll
+    for (int j = 0; j < N; j += 2) { acc[j] = ptx_mul_lo(x[j], y); acc[j + 1] = ptx_mul_hi(x[j], y); }
+}
+template <int N>
+FF_DEV void row_mad(uint32_t (&acc)[N], const uint32_t* x, uint32_t y) {
+    // acc += sum_{j even} x[j]·y·2^{32j}; leaves the carry-out in CC
+    acc[0] = ptx_mad_lo_cc(x[0], y, acc[0]);
+    acc[1] = ptx_madc_hi_cc(x[0], y, acc[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) { acc[j] = ptx_madc_lo_cc(x[j], y, acc[j]); acc[j + 1] = ptx_madc_hi_cc(x[j], y, acc[j + 1]); }
+}
+template <int N>
+FF_DEV void row_mad_shift(uint32_t (&dst)[N], const uint32_t (&src)[N], const uint32_t* x, uint32_t y) {
+    // dst[k] = src[k+2] + (sum_{j even} x[j]·y·2^{32j})[k] + carry-in (CC); top two limbs have no src.
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) { dst[j] = ptx_madc_lo_cc(x[j], y, src[j + 2]); dst[j + 1] = ptx_madc_hi_cc(x[j], y, src[j + 3]); }
+    dst[N - 2] = ptx_madc_lo_cc(x[N - 2], y, 0u);
+    dst[N - 1] = ptx_madc_hi(x[N - 2], y, 0u);
+}
+
+// One word-serial step:  V <- (V_prev/2^32 + a·bi + m·p)  with m chosen so the low limb vanishes.
+// On entry (ee, oo) hold V_prev BEFORE its pending one-limb right shift (ee[0] == 0).
+// On exit  (oo', ee') := (new even array, new odd array) — the roles swap because of the shift,
+// so the caller alternates the argument order.
+template <int N, class P>
+FF_DEV void mont_step(uint32_t (&ev)[N], uint32_t (&od)[N], const uint32_t (&a)[N], uint32_t bi, bool first) {
+    // `ev` is the array that is limb-aligned with V after the shift (it was the odd array before);
+    // `od` was the even array before the shift: od[1] lands on limb 0, od[2..] become the new odd array.
+    if (first) {
+        row_mul<N>(od, &a[1], bi);
+        row_mul<N>(ev, &a[0], bi);
+    } else {
+        ev[0] = ptx_add_cc(ev[0], od[1]);
+        uint32_t nod[N];
+        row_mad_shift<N>(nod, od, &a[1], bi);          // consumes the carry of the add above
+#pragma unroll
+        for (int k = 0; k < N; k++) od[k] = nod[k];
+        row_mad<N>(ev, &a[0], bi);
+        od[N - 1] = ptx_addc(od[N - 1], 0u);
+    }
+    // Montgomery reduction row: m = -ev[0] / p mod 2^32
+    uint32_t m = ev[0] * P::INV32;
+    uint32_t pm[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) pm[k] = P::mod(k);
+    row_mad<N>(od, &pm[1], m);                          // odd columns of p (pm[N] is never read: j < N-1)
+    row_mad<N>(ev, &pm[0], m);
+    od[N - 1] = ptx_addc(od[N - 1], 0u);
+}
+
+// ---------------------------------------------------------------------------
+// Field element
+// ---------------------------------------------------------------------------
+template <class P>
+struct Fp {
+    static constexpr int N = P::N;
+    uint32_t v[N];
+
+    FF_DEV static Fp zero() { Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = 0u; return r; }
+    FF_DEV static Fp one() { Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::r1(i); return r; }
+    FF_DEV static Fp r2() { Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::r2(i); return r; }
+
+    FF_DEV bool is_zero() const { uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) t |= v[i]; return t == 0; }
+    FF_DEV bool operator==(const Fp& o) const { uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) t |= v[i] ^ o.v[i]; return t == 0; }
+    FF_DEV bool operator!=(const Fp& o) const { return !(*this == o); }
+
+    // r = (x >= p) ? x - p : x      (x < 2p)
+    FF_DEV void final_sub() {
+        uint32_t t[N];
+        t[0] = ptx_sub_cc(v[0], P::mod(0));
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = ptx_subc_cc(v[i], P::mod(i));
+        uint32_t borrow = ptx_subc(0u, 0u);            // 0xffffffff if x < p
+        if (borrow == 0u) {
+#pragma unroll
+            for (int i = 0; i < N; i++) v[i] = t[i];
+        }
+    }
+
+    FF_DEV friend Fp operator+(const Fp& a, const Fp& b) {
+        Fp r;
+        r.v[0] = ptx_add_cc(a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = ptx_addc_cc(a.v[i], b.v[i]);
+        r.v[N - 1] = ptx_addc(a.v[N - 1], b.v[N - 1]);  // moduli leave ≥3 spare bits: no carry out
+        r.final_sub();
+        return r;
+    }
+    FF_DEV friend Fp operator-(const Fp& a, const Fp& b) {
+        Fp r;
+        r.v[0] = ptx_sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) r.v[i] = ptx_subc_cc(a.v[i], b.v[i]);
+        uint32_t borrow = ptx_subc(0u, 0u);
+        if (borrow) {
+            r.v[0] = ptx_add_cc(r.v[0], P::mod(0));
+#pragma unroll
+            for (int i = 1; i < N - 1; i++) r.v[i] = ptx_addc_cc(r.v[i], P::mod(i));
+            r.v[N - 1] = ptx_addc(r.v[N - 1], P::mod(N - 1));
+        }
+        return r;
+    }
+    FF_DEV Fp neg() const { return is_zero() ? *this : (zero() - *this); }
+    FF_DEV Fp dbl() const { return *this + *this; }
+
+    FF_DEV friend Fp operator*(const Fp& a, const Fp& b) {
+        uint32_t e[N], o[N];
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            mont_step<N, P>(e, o, a.v, b.v[i], i == 0);
+            mont_step<N, P>(o, e, a.v, b.v[i + 1], false);
+        }
+        // pending shift + merge: result[k] = e'[k] + o'[k+1]  where (e', o') = (e, o) roles after N steps
+        Fp r;
+        r.v[0] = ptx_add_cc(e[0], o[1]);
+#pragma unroll
+        for (int k = 1; k < N - 1; k++) r.v[k] = ptx_addc_cc(e[k], o[k + 1]);
+        r.v[N - 1] = ptx_addc(e[N - 1], 0u);
+        r.final_sub();
+        return r;
+    }
+    FF_DEV Fp sqr() const { return (*this) * (*this); }
+
+    // a^e for a fixed public exponent given as 32-bit limbs (MSB-first square-and-multiply)
+    template <int L>
+    FF_DEV Fp pow_const(const uint32_t (&e)[L]) const {
+        Fp acc = one();
+        bool started = false;
+        for (int i = L - 1; i >= 0; i--) {
+            for (int b = 31; b >= 0; b--) {
+                if (started) acc = acc.sqr();
+                if ((e[i] >> b) & 1u) { acc = started ? acc * (*this) : *this; started = true; }
+            }
+        }
+        return acc;
+    }
+    // Fermat inverse a^{p-2}; returns zero for zero (callers that need the reference's Option test is_zero first).
+    FF_DEV Fp inverse() const {
+        uint32_t e[N];
+        uint32_t borrow = 2u;                           // e = p - 2
+#pragma unroll
+        for (int i = 0; i < N; i++) { uint32_t m = P::mod(i); e[i] = m - borrow; borrow = (m < borrow) ? 1u : 0u; }
+        return pow_const<N>(e);
+    }
+
+    // x/2 mod p (works on Montgomery images too: (x/2)·R = (x·R)/2)
+    FF_DEV Fp half() const {
+        uint32_t t[N + 1];
+        if (v[0] & 1u) {
+            t[0] = ptx_add_cc(v[0], P::mod(0));
+#pragma unroll
+            for (int i = 1; i < N; i++) t[i] = ptx_addc_cc(v[i], P::mod(i));
+            t[N] = ptx_addc(0u, 0u);
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; i++) t[i] = v[i];
+            t[N] = 0u;
+        }
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = __funnelshift_r(t[i], t[i + 1], 1);
+        return r;
+    }
+
+    FF_DEV Fp to_mont() const { return (*this) * r2(); }
+    FF_DEV Fp from_mont() const { Fp o = zero(); o.v[0] = 1u; return (*this) * o; }
+
+    // 128-bit vector global memory access (coalesced across a warp when elements are contiguous)
+    FF_DEV static Fp load(const void* p) {
+        Fp r; const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+        for (int i = 0; i < N / 4; i++) { uint4 t = q[i]; r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w; }
+        return r;
+    }
+    FF_DEV static Fp load_ldg(const void* p) {
+        Fp r; const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+        for (int i = 0; i < N / 4; i++) { uint4 t = __ldg(q + i); r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w; }
+        return r;
+    }
+    FF_DEV void store(void* p) const {
+        uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+        for (int i = 0; i < N / 4; i++) q[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// BLS12-377 parameters (numbers from curves/src/bls12_377/fr.rs:109-192, fq.rs:85-176,
+// re-expressed as 32-bit limbs; cross-checked in tests against oracle/bls12_377.py).
+// ---------------------------------------------------------------------------
+#define FF_TABLE(name, ...) \
+    __host__ __device__ static constexpr uint32_t name(int i) { constexpr uint32_t t[N] = {__VA_ARGS__}; return t[i]; }
+
+struct FrParams {
+    static constexpr int N = 8;
+    static constexpr uint32_t INV32 = 0xffffffffu;     // -r^{-1} mod 2^32 (low word of INV, fr.rs:137)
+    FF_TABLE(mod, 0x00000001u, 0x0a118000u, 0xd0000001u, 0x59aa76feu, 0x5c37b001u, 0x60b44d1eu, 0x9a2ca556u, 0x12ab655eu)
+    FF_TABLE(r1,  0xfffffff3u, 0x7d1c7fffu, 0x6ffffff2u, 0x7257f50fu, 0x512c0feeu, 0x16d81575u, 0x2bbb9a9du, 0x0d4bda32u)
+    FF_TABLE(r2,  0xb861857bu, 0x25d577bau, 0x8860591fu, 0xcc2c27b5u, 0xe5dc8593u, 0xa7cc008fu, 0xeff1c939u, 0x011fdae7u)
+};
+struct FqParams {
+    static constexpr int N = 12;
+    static constexpr uint32_t INV32 = 0xffffffffu;     // -q^{-1} mod 2^32 (low word of INV, fq.rs:111)
+    FF_TABLE(mod, 0x00000001u, 0x8508c000u, 0x30000000u, 0x170b5d44u, 0xba094800u, 0x1ef3622fu, 0x00f5138fu, 0x1a22d9f3u, 0x6ca1493bu, 0xc63b05c0u, 0x17c510eau, 0x01ae3a46u)
+    FF_TABLE(r1,  0xffffff68u, 0x02cdffffu, 0x7fffffb1u, 0x51409f83u, 0x8a7d3ff2u, 0x9f7db3a9u, 0x6e7c6305u, 0x7b4e97b7u, 0x803c84e8u, 0x4cf495bfu, 0xe2fdf49au, 0x008d6661u)
+    FF_TABLE(r2,  0x9400cd22u, 0xb786686cu, 0xb00431b1u, 0x0329fcaau, 0x62d6b46du, 0x22a5f111u, 0x827dc3acu, 0xbfdf7d03u, 0x41790bf9u, 0x837e92f0u, 0x1e914b88u, 0x006dfccbu)
+};
+#undef FF_TABLE
+
+using Fr = Fp<FrParams>;
+using Fq = Fp<FqParams>;
+
+}  // namespace b200

@@ -1,0 +1,289 @@
+// See msm.cuh for the map from reference functions to kernels.
+#include "msm.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cub/device/device_scan.cuh>
+
+#include "ec.cuh"
+
+namespace b200 {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t launch_count() { return g_launches.load(); }
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n); }
+
+#define CUDA_TRY(x)                                   \
+    do {                                              \
+        cudaError_t e_ = (x);                         \
+        if (e_ != cudaSuccess) { rc = (int)e_; goto done; } \
+    } while (0)
+
+static int ceil_log2(size_t x) { int l = 0; size_t v = x > 1 ? x - 1 : 0; while (v) { l++; v >>= 1; } return l; }
+
+MsmPlan msm_make_plan(size_t npoints) {
+    MsmPlan p;
+    int lg = ceil_log2(npoints < 2 ? 2 : npoints);
+    // Work model (Fq mults): n·W·10 for the mixed adds + W·2^(c-1)·~30 for the bucket reduction.
+    int c = lg <= 8 ? 4 : lg <= 12 ? lg - 4 : lg <= 16 ? lg - 3 : lg <= 20 ? 14 : lg <= 22 ? 15 : 16;
+    if (const char* e = getenv("SNARKVM_B200_MSM_C")) { int v = atoi(e); if (v >= 2 && v <= 24) c = v; }
+    p.c = c;
+    p.nwin = 253 / c + 1;
+    p.nbuckets = 1u << (c - 1);
+    // Aim for ≥ ~300k work items so 148 SMs × (2 × 256-thread CTAs) see several waves, but keep
+    // items long enough (≥ 16 points) that the per-item overhead stays in the noise.
+    size_t total = npoints * (size_t)p.nwin;
+    size_t cap = total / 300000 + 1;
+    if (cap < 16) cap = 16;
+    if (const char* e = getenv("SNARKVM_B200_MSM_CAP")) { long v = atol(e); if (v >= 1) cap = (size_t)v; }
+    p.cap = (uint32_t)cap;
+    return p;
+}
+
+// ---------------------------------------------------------------------------
+// Signed-digit recoding of a canonical 253-bit scalar (8 little-endian u32 words).
+// digit_w ∈ [-2^(c-1), 2^(c-1)]; returns magnitude and sign for window w given the
+// running carry (sequential over w).
+// ---------------------------------------------------------------------------
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ scalars, size_t n, int c, int nwin,
+                                                uint32_t nbuckets, uint32_t* __restrict__ counters /* hist or cursors */,
+                                                uint32_t* __restrict__ sorted) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    {
+        const uint4* q = reinterpret_cast<const uint4*>(scalars + 8 * i);
+        uint4 a = __ldg(q), b = __ldg(q + 1);
+        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    }
+    const uint32_t half = 1u << (c - 1);
+    uint32_t carry = 0;
+    for (int w = 0; w < nwin; w++) {
+        int bit = w * c;
+        // dynamic register-array indexing would spill: select the two words with a small switch-free scan
+        int wi = bit >> 5, sh = bit & 31;
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { if (k == wi) lo = s[k]; if (k == wi + 1) hi = s[k]; }
+        uint32_t raw = (__funnelshift_r(lo, hi, sh) & ((1u << c) - 1u)) + carry;
+        uint32_t neg = raw > half ? 1u : 0u;
+        uint32_t mag = neg ? (1u << c) - raw : raw;
+        carry = neg;
+        if (mag != 0u) {
+            uint32_t slot = (uint32_t)w * nbuckets + (mag - 1u);
+            if (SCATTER) {
+                uint32_t pos = atomicAdd(&counters[slot], 1u);
+                sorted[pos] = (uint32_t)i | (neg << 31);
+            } else {
+                atomicAdd(&counters[slot], 1u);
+            }
+        }
+    }
+}
+
+__global__ void k_items_per_bucket(const uint32_t* __restrict__ hist, uint32_t* __restrict__ items, uint32_t total_buckets, uint32_t cap) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total_buckets) items[i] = (hist[i] + cap - 1u) / cap;
+}
+
+// One thread per work item (a run of ≤ cap sorted entries of one bucket): XYZZ mixed additions
+// of gathered affine bases.  partial[item] receives the item's sum.
+__global__ void __launch_bounds__(256) k_bucket_accumulate(const uint8_t* __restrict__ points, size_t stride,
+                                                            const uint32_t* __restrict__ sorted,
+                                                            const uint32_t* __restrict__ bucket_start /* [TB+1] */,
+                                                            const uint32_t* __restrict__ item_start /* [TB+1] */,
+                                                            uint32_t total_buckets, uint32_t cap, uint32_t* __restrict__ partial) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t total_items = item_start[total_buckets];
+    if (t >= total_items) return;
+    // upper_bound(item_start, t) - 1 : the bucket whose item range contains t
+    uint32_t lo = 0, hi = total_buckets;          // invariant: item_start[lo] <= t < item_start[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (item_start[mid] <= t) lo = mid; else hi = mid;
+    }
+    uint32_t wb = lo;
+    uint32_t seg = t - item_start[wb];
+    uint32_t b0 = bucket_start[wb], b1 = bucket_start[wb + 1];
+    uint32_t s0 = b0 + seg * cap;
+    uint32_t s1 = s0 + cap < b1 ? s0 + cap : b1;
+
+    XYZZ acc = XYZZ::infinity();
+    // software pipeline: fetch entry k+1 while adding entry k
+    uint32_t e = sorted[s0];
+    AffinePoint p = load_affine(points, stride, e & 0x7fffffffu);
+    for (uint32_t k = s0; k < s1; k++) {
+        uint32_t e_cur = e;
+        AffinePoint p_cur = p;
+        if (k + 1 < s1) { e = sorted[k + 1]; p = load_affine(points, stride, e & 0x7fffffffu); }
+        acc.add_affine(p_cur, (e_cur >> 31) != 0u);
+    }
+    acc.store(partial + (size_t)t * XYZZ_WORDS);
+}
+
+// Σ of a bucket's item partials
+FF_DEV XYZZ bucket_sum(const uint32_t* __restrict__ partial, const uint32_t* __restrict__ item_start, uint32_t wb) {
+    uint32_t i0 = item_start[wb], i1 = item_start[wb + 1];
+    XYZZ s = XYZZ::infinity();
+    for (uint32_t i = i0; i < i1; i++) {
+        if (i == i0) s = XYZZ::load(partial + (size_t)i * XYZZ_WORDS);
+        else s.add(XYZZ::load(partial + (size_t)i * XYZZ_WORDS));
+    }
+    return s;
+}
+
+// Thread j of window w owns bucket values [lo, hi] = [j·K + 1, (j+1)·K]:
+//   running = Σ S_b ; acc = Σ (b − lo + 1)·S_b   (top-down running sum, batched.rs:356-361)
+//   out = acc + (lo − 1)·running = Σ b·S_b over the chunk.
+__global__ void __launch_bounds__(128) k_bucket_reduce(const uint32_t* __restrict__ partial, const uint32_t* __restrict__ item_start,
+                                                        uint32_t nbuckets, uint32_t chunk, uint32_t chunks_per_window,
+                                                        uint32_t nwin, uint32_t* __restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= chunks_per_window * nwin) return;
+    uint32_t w = t / chunks_per_window, j = t % chunks_per_window;
+    uint32_t lo = j * chunk, hi = lo + chunk;                 // 0-based bucket indices [lo, hi)
+    XYZZ running = XYZZ::infinity(), acc = XYZZ::infinity();
+    for (uint32_t b = hi; b-- > lo;) {
+        XYZZ s = bucket_sum(partial, item_start, w * nbuckets + b);
+        running.add(s);
+        acc.add(running);
+    }
+    if (lo != 0u) acc.add(running.mul_u32(lo));               // bucket value of index lo is lo+1 ⇒ (lo+1−1)·running
+    acc.store(out + (size_t)t * XYZZ_WORDS);
+}
+
+// out[j] = Σ in[j·group .. min((j+1)·group, per_row)) for each of `rows` independent rows.
+__global__ void __launch_bounds__(128) k_group_sum(const uint32_t* __restrict__ in, uint32_t per_row, uint32_t group,
+                                                    uint32_t out_per_row, uint32_t rows, uint32_t* __restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= out_per_row * rows) return;
+    uint32_t r = t / out_per_row, j = t % out_per_row;
+    uint32_t i0 = j * group, i1 = i0 + group < per_row ? i0 + group : per_row;
+    XYZZ s = XYZZ::infinity();
+    for (uint32_t i = i0; i < i1; i++) s.add(XYZZ::load(in + ((size_t)r * per_row + i) * XYZZ_WORDS));
+    s.store(out + (size_t)t * XYZZ_WORDS);
+}
+
+__global__ void k_xyzz_sum_ranks(const uint32_t* __restrict__ in, int nranks, int count, uint32_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    XYZZ s = XYZZ::load(in + (size_t)i * XYZZ_WORDS);
+    for (int r = 1; r < nranks; r++) s.add(XYZZ::load(in + ((size_t)r * count + i) * XYZZ_WORDS));
+    s.store(out + (size_t)i * XYZZ_WORDS);
+}
+
+int xyzz_sum_ranks_device(uint32_t* d_out, const uint32_t* d_in, int nranks, int count, cudaStream_t stream) {
+    k_xyzz_sum_ranks<<<(count + 31) / 32, 32, 0, stream>>>(d_in, nranks, count, d_out);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const void* d_points, size_t stride,
+                           const void* d_scalars, size_t npoints, cudaStream_t stream) {
+    int rc = 0;
+    const uint32_t TB = (uint32_t)plan.nwin * plan.nbuckets;      // total buckets
+    const size_t max_entries = npoints * (size_t)plan.nwin;
+    const size_t max_items = (size_t)TB + max_entries / plan.cap + 1;
+    if (npoints == 0 || npoints >= (1ull << 31) || max_entries >= (1ull << 32)) return (int)cudaErrorInvalidValue;
+
+    uint32_t *hist = nullptr, *bucket_start = nullptr, *cursors = nullptr, *items = nullptr, *item_start = nullptr;
+    uint32_t *sorted = nullptr, *partial = nullptr, *red_a = nullptr, *red_b = nullptr;
+    void* cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    const uint32_t chunk = plan.nbuckets < 32u ? plan.nbuckets : 32u;
+    const uint32_t chunks_per_window = plan.nbuckets / chunk;
+
+    CUDA_TRY(cudaMallocAsync(&hist, (size_t)(TB + 1) * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&bucket_start, (size_t)(TB + 1) * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&cursors, (size_t)(TB + 1) * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&items, (size_t)(TB + 1) * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&item_start, (size_t)(TB + 1) * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&sorted, max_entries * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&partial, max_items * XYZZ_WORDS * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&red_a, (size_t)plan.nwin * chunks_per_window * XYZZ_WORDS * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&red_b, (size_t)plan.nwin * (chunks_per_window / 32 + 1) * XYZZ_WORDS * 4, stream));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, hist, bucket_start, (int)(TB + 1), stream));
+    CUDA_TRY(cudaMallocAsync(&cub_tmp, cub_bytes ? cub_bytes : 16, stream));
+
+    CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)(TB + 1) * 4, stream));
+    CUDA_TRY(cudaMemsetAsync(items, 0, (size_t)(TB + 1) * 4, stream));
+    {
+        const unsigned grid = (unsigned)((npoints + 255) / 256);
+        k_digits<false><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, hist, nullptr);
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, hist, bucket_start, (int)(TB + 1), stream));
+        CUDA_TRY(cudaMemcpyAsync(cursors, bucket_start, (size_t)(TB + 1) * 4, cudaMemcpyDeviceToDevice, stream));
+        k_digits<true><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, cursors, sorted);
+        k_items_per_bucket<<<(TB + 255) / 256, 256, 0, stream>>>(hist, items, TB, plan.cap);
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(TB + 1), stream));
+        const unsigned agrid = (unsigned)((max_items + 255) / 256);
+        k_bucket_accumulate<<<agrid, 256, 0, stream>>>((const uint8_t*)d_points, stride, sorted, bucket_start, item_start, TB, plan.cap, partial);
+        const uint32_t nthreads = chunks_per_window * (uint32_t)plan.nwin;
+        k_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, stream>>>(partial, item_start, plan.nbuckets, chunk, chunks_per_window, (uint32_t)plan.nwin, red_a);
+        count_launch(7);
+        // tree over the per-chunk sums: groups of 32 until one point per window remains
+        uint32_t per_row = chunks_per_window;
+        const uint32_t* src = red_a;
+        uint32_t* bufs[2] = {red_b, red_a};
+        int which = 0;
+        while (per_row > 1) {
+            uint32_t out_per_row = (per_row + 31) / 32;
+            uint32_t* target = out_per_row == 1 ? d_window_sums : bufs[which];
+            uint32_t nt = out_per_row * (uint32_t)plan.nwin;
+            k_group_sum<<<(nt + 127) / 128, 128, 0, stream>>>(src, per_row, 32, out_per_row, (uint32_t)plan.nwin, target);
+            count_launch();
+            src = target; which ^= 1; per_row = out_per_row;
+        }
+        if (chunks_per_window == 1)
+            CUDA_TRY(cudaMemcpyAsync(d_window_sums, red_a, (size_t)plan.nwin * XYZZ_WORDS * 4, cudaMemcpyDeviceToDevice, stream));
+        CUDA_TRY(cudaGetLastError());
+    }
+done:
+    cudaFreeAsync(hist, stream); cudaFreeAsync(bucket_start, stream); cudaFreeAsync(cursors, stream);
+    cudaFreeAsync(items, stream); cudaFreeAsync(item_start, stream); cudaFreeAsync(sorted, stream);
+    cudaFreeAsync(partial, stream); cudaFreeAsync(red_a, stream); cudaFreeAsync(red_b, stream); cudaFreeAsync(cub_tmp, stream);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// Synthetic bases: P_i = h(seed, i)·G
+// ---------------------------------------------------------------------------
+FF_DEV uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__constant__ uint32_t G1_GEN_X[12] = {0xec301b95u, 0x1042a645u, 0xc1060f28u, 0x5a990780u, 0xa9007a5bu, 0x684a8ab3u,
+                                      0x257ba63fu, 0x1c35a184u, 0xfea8e32eu, 0xb2b2abd2u, 0x23fb2017u, 0x017df3a2u};   // g1.rs:225-236 (Montgomery)
+__constant__ uint32_t G1_GEN_Y[12] = {0xe2801ab9u, 0xbc5a1ae8u, 0xcbfe13b0u, 0xd4f3c861u, 0x4e949f13u, 0xecdd5ffcu,
+                                      0x7503667du, 0x8f87199bu, 0x7dc4fe1cu, 0x0f0b1b83u, 0x053eaabeu, 0x004bcc7eu};   // g1.rs:242-253
+
+__global__ void __launch_bounds__(128) k_generate_bases(uint8_t* points, size_t n, size_t stride, uint64_t seed) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = splitmix64(seed ^ splitmix64((uint64_t)i));
+    if (k == 0) k = 1;
+    AffinePoint g;
+#pragma unroll
+    for (int j = 0; j < 12; j++) { g.x.v[j] = G1_GEN_X[j]; g.y.v[j] = G1_GEN_Y[j]; }
+    g.inf = false;
+    XYZZ acc = XYZZ::infinity();
+    bool started = false;
+    for (int b = 63; b >= 0; b--) {
+        if (started) acc.dbl();
+        if ((k >> b) & 1ull) { acc.add_affine(g, false); started = true; }
+    }
+    store_affine(points, stride, i, acc.to_affine());
+}
+
+int msm_generate_bases_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, cudaStream_t stream) {
+    if (stride < 104 || (stride & 7)) return (int)cudaErrorInvalidValue;
+    if (npoints == 0) return 0;
+    k_generate_bases<<<(unsigned)((npoints + 127) / 128), 128, 0, stream>>>((uint8_t*)d_points, npoints, stride, seed);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+}  // namespace b200

@@ -1,0 +1,50 @@
+// Pippenger multi-scalar multiplication over BLS12-377 G1 for sm_100a.
+//
+// Replaces the hot loops of the reference's VariableBase::msm
+// (algorithms/src/msm/variable_base/mod.rs:30-49 → batched.rs:366-415):
+//   batched_window  (batched.rs:328-364)  →  k_digit_hist / k_digit_scatter  (bucket sort)
+//   batch_add       (batched.rs:175-325)  →  k_bucket_accumulate             (bucket sums)
+//   running sum     (batched.rs:356-361)  →  k_bucket_reduce / k_group_sum
+//   window combine  (batched.rs:404-413)  →  host Horner over ≤ 24 window sums (host_ec.hpp)
+//
+// Design differences (the result is a group element, so any window size / digit
+// recoding / coordinate system yields the same to_affine() image):
+//   * signed c-bit digits  → 2^(c-1) buckets per window instead of 2^c − 1
+//   * counting sort by (window, bucket) with global atomics instead of sort_unstable
+//   * XYZZ mixed additions instead of Montgomery-trick batched affine additions
+//   * every bucket is cut into work items of ≤ cap points so a hot bucket (all scalars
+//     equal, repeated bases — benches/msm/variable_base.rs:29-32) cannot serialise a thread.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+struct MsmPlan {
+    int c;              // window bits
+    int nwin;           // number of windows = 253 / c + 1 (room for the signed-digit carry)
+    uint32_t nbuckets;  // 2^(c-1) buckets per window (bucket value 1 .. 2^(c-1))
+    uint32_t cap;       // max points per work item
+};
+
+MsmPlan msm_make_plan(size_t npoints);
+
+// Computes the per-window sums Σ_b b·S_{w,b} as XYZZ points (48 words each) into
+// d_window_sums[plan.nwin][48].  All pointers are device pointers.  Scratch is taken
+// from the stream-ordered pool of the current device.  Returns cudaError_t as int.
+int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const void* d_points, size_t stride,
+                           const void* d_scalars, size_t npoints, cudaStream_t stream);
+
+// Deterministic test/bench input: P_i = h(seed, i)·G with a 64-bit multiplier h
+// (every point is in the prime-order subgroup because G is).  Writes the reference
+// affine layout with the given stride.
+int msm_generate_bases_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, cudaStream_t stream);
+
+// out[i] = Σ_r in[r][i]  over `nranks` arrays of `count` XYZZ points (multi-GPU combine).
+int xyzz_sum_ranks_device(uint32_t* d_out, const uint32_t* d_in, int nranks, int count, cudaStream_t stream);
+
+uint64_t launch_count();
+void count_launch(int n = 1);
+
+}  // namespace b200

@@ -1,0 +1,315 @@
+// See ntt.cuh for semantics and the reference map.
+//
+// Structure: radix-2 decimation-in-frequency butterflies (the reference's io_helper,
+// domain.rs:691-735, butterfly_fn_io :651-656) grouped into passes of S ≤ 8 stages.
+// A pass keeps a tile of 2^S rows × 2^Q columns of Fr in shared memory, runs its S
+// stages there, and touches HBM once (32 B read + 32 B write per element).  Twiddles
+// ω^e come from one precomputed table of ω_N^j (j < N/2) that is strided for smaller
+// domains, exactly like precomputation_for_subdomain (domain.rs:895-908); inverse
+// transforms use ω^{-e} = −ω^{n/2−e}, so no second table exists.  The last pass writes
+// bit-reversed addresses (derange, domain.rs:789-804) so the output is natural-order,
+// and fuses the n^{-1} / coset scaling (domain.rs:421, 440-443); the first pass fuses
+// the coset pre-scaling g^j (domain.rs:201-206).
+#include "ntt.cuh"
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "ff.cuh"
+#include "msm.cuh"   // count_launch
+
+namespace b200 {
+
+#define CUDA_TRY(x)                                          \
+    do {                                                     \
+        cudaError_t e_ = (x);                                \
+        if (e_ != cudaSuccess) { rc = (int)e_; goto done; }  \
+    } while (0)
+
+// TWO_ADIC_ROOT_OF_UNITY (order 2^47), GENERATOR = 22 and its inverse, Montgomery form (fr.rs:115-135)
+__constant__ uint32_t FR_ROOT47[8] = {0xda3ad648u, 0xaf80da4du, 0xfc381dacu, 0x5e223adbu, 0xb2f92525u, 0x03ba0666u, 0x3befb0ceu, 0x0f906c5bu};
+__constant__ uint32_t FR_GEN[8] = {0xfffffed3u, 0x296c7fffu, 0x6ffffec7u, 0x92921665u, 0x92860e69u, 0x4c01534du, 0xb9819970u, 0x0c79cfc4u};
+__constant__ uint32_t FR_GEN_INV[8] = {0xd1745d17u, 0xb76f9745u, 0xafffffffu, 0xfed18274u, 0x5b36a173u, 0xfce61983u, 0x78dc8d16u, 0x068b6ffdu};
+
+FF_DEV Fr fr_from_const(const uint32_t* c) { Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = c[i]; return r; }
+
+// out[k] = ω_N^(2^k), k < lgN   (get_root_of_unity, fields/src/traits/fft_field.rs:38-86)
+__global__ void k_root_pow2(Fr* out, int lgN) {
+    Fr w = fr_from_const(FR_ROOT47);
+    for (int i = lgN; i < 47; i++) w = w.sqr();
+    for (int k = 0; k < lgN; k++) { out[k] = w; w = w.sqr(); }
+}
+// gp[k] = g^(±2^k), k < 40 ; ninv[0] = 2^{-lg} (size_inv, domain.rs:138-139), ninv[1] = 1
+__global__ void k_coset_setup(Fr* gp, Fr* ninv, int lg, int inverse) {
+    Fr g = fr_from_const(inverse ? FR_GEN_INV : FR_GEN);
+    for (int k = 0; k < 40; k++) { gp[k] = g; g = g.sqr(); }
+    Fr h = Fr::one();
+    for (int k = 0; k < lg; k++) h = h.half();
+    ninv[0] = h;
+    ninv[1] = Fr::one();
+}
+// out[j] = scale · Π_{bit k of j} pow2[k + shift]
+__global__ void k_pow_table(Fr* out, size_t count, const Fr* __restrict__ pow2, int shift, const Fr* __restrict__ scale) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    Fr acc = scale ? *scale : Fr::one();
+    size_t e = j;
+    for (int k = shift; e; k++, e >>= 1) if (e & 1) acc = acc * pow2[k];
+    out[j] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// Per-device caches (the FFI is entered concurrently from many threads — SURVEY §8b)
+// ---------------------------------------------------------------------------
+struct CosetTables { Fr* lo; Fr* hi; Fr* ninv; };   // lo[4096] = g^{±j}, hi[h] = c·g^{±4096h}, ninv[0] = n^{-1}
+struct DeviceCache {
+    std::mutex mu;
+    Fr* tw = nullptr;      // ω_N^j, j < N/2
+    int lgN = 0;
+    std::map<uint64_t, CosetTables> coset;   // key = lg | dir << 8
+};
+static DeviceCache g_cache[64];
+
+static int get_twiddles(int lg, const Fr** tw, int* lgN) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    DeviceCache& c = g_cache[dev & 63];
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (c.lgN < lg) {
+        int want = lg < 16 ? 16 : lg;
+        Fr *tab = nullptr, *pw = nullptr;
+        size_t count = (size_t)1 << (want - 1);
+        if ((e = cudaMalloc(&tab, count * sizeof(Fr))) != cudaSuccess) return (int)e;
+        if ((e = cudaMalloc(&pw, 64 * sizeof(Fr))) != cudaSuccess) { cudaFree(tab); return (int)e; }
+        k_root_pow2<<<1, 1>>>(pw, want);
+        k_pow_table<<<(unsigned)((count + 255) / 256), 256>>>(tab, count, pw, 0, nullptr);
+        count_launch(2);
+        e = cudaDeviceSynchronize();
+        cudaFree(pw);
+        if (e != cudaSuccess) { cudaFree(tab); return (int)e; }
+        // the previous (smaller) table is intentionally kept alive: other threads may still be reading it
+        c.tw = tab;
+        c.lgN = want;
+    }
+    *tw = c.tw;
+    *lgN = c.lgN;
+    return 0;
+}
+
+static int get_coset_tables(int lg, int inverse, CosetTables* out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    DeviceCache& c = g_cache[dev & 63];
+    std::lock_guard<std::mutex> lock(c.mu);
+    uint64_t key = (uint64_t)lg | ((uint64_t)inverse << 8);
+    auto it = c.coset.find(key);
+    if (it == c.coset.end()) {
+        CosetTables t{nullptr, nullptr, nullptr};
+        Fr* gp = nullptr;
+        size_t nhi = lg > 12 ? ((size_t)1 << (lg - 12)) : 1;
+        if ((e = cudaMalloc(&t.lo, 4096 * sizeof(Fr))) != cudaSuccess) return (int)e;
+        if ((e = cudaMalloc(&t.hi, nhi * sizeof(Fr))) != cudaSuccess) return (int)e;
+        if ((e = cudaMalloc(&t.ninv, 2 * sizeof(Fr))) != cudaSuccess) return (int)e;
+        if ((e = cudaMalloc(&gp, 40 * sizeof(Fr))) != cudaSuccess) return (int)e;
+        k_coset_setup<<<1, 1>>>(gp, t.ninv, lg, inverse);
+        k_pow_table<<<16, 256>>>(t.lo, 4096, gp, 0, nullptr);
+        // forward: hi carries no scale; inverse: hi carries n^{-1} so the post-scale is two multiplications
+        k_pow_table<<<(unsigned)((nhi + 255) / 256), 256>>>(t.hi, nhi, gp, 12, inverse ? t.ninv : t.ninv + 1);
+        count_launch(3);
+        e = cudaDeviceSynchronize();
+        cudaFree(gp);
+        if (e != cudaSuccess) return (int)e;
+        it = c.coset.emplace(key, t).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// One pass = stages [t0, t0+S) of the DIF network on a 2^S × 2^Q tile in shared memory.
+// ---------------------------------------------------------------------------
+struct PassArgs {
+    const Fr* in;
+    Fr* out;
+    const Fr* tw;        // ω_N^j table
+    const Fr* coset_lo;  // may be null
+    const Fr* coset_hi;
+    const Fr* ninv;      // n^{-1} (used when post == 1)
+    int lg, lgN;
+    int t0, S, Q;
+    int last;            // 1: rows are contiguous sub-arrays, output is bit-reversed scatter
+    int inverse;
+    int pre;             // 1: multiply input j by coset_lo/hi (forward coset)
+    int post;            // 0 none, 1: × n^{-1}, 2: × coset_lo/hi[k] (hi already carries n^{-1})
+};
+
+FF_DEV Fr coset_factor(const Fr* lo, const Fr* hi, size_t idx) { return lo[idx & 4095] * hi[idx >> 12]; }
+
+__global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
+    extern __shared__ uint4 smem_raw[];
+    Fr* sm = reinterpret_cast<Fr*>(smem_raw);
+    const int S = a.S, Q = a.Q, lg = a.lg, t0 = a.t0;
+    const int L = lg - t0 - S;                       // low index bits below the tile's row digit
+    const uint32_t rows = 1u << S, cols = 1u << Q, tile_elems = rows << Q;
+    const size_t tile = blockIdx.x;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+
+    size_t H = 0, low_base = 0, hprime_base = 0;
+    if (!a.last) { H = tile >> (L - Q); low_base = (tile & (((size_t)1 << (L - Q)) - 1)) << Q; }
+    else hprime_base = tile << Q;
+
+    // ---- load (+ optional coset pre-scale) ----
+    for (uint32_t e = tid; e < tile_elems; e += nthr) {
+        uint32_t d, c;
+        size_t idx;
+        if (!a.last) { c = e & (cols - 1); d = e >> Q; idx = (H << (S + L)) | ((size_t)d << L) | low_base | c; }
+        else {
+            d = e & (rows - 1); c = e >> S;
+            size_t hp = hprime_base + c;
+            size_t Hrow = t0 ? (size_t)(__brevll((unsigned long long)hp) >> (64 - t0)) : 0;
+            idx = (Hrow << S) | d;
+        }
+        Fr x = Fr::load(a.in + idx);
+        if (a.pre) x = x * coset_factor(a.coset_lo, a.coset_hi, idx);
+        sm[((size_t)d << Q) | c] = x;
+    }
+    __syncthreads();
+
+    // ---- S butterfly stages ----
+    const uint32_t nbf = tile_elems >> 1;
+    const int tw_shift = a.lgN - lg;
+    for (int u = 0; u < S; u++) {
+        const int t = t0 + u;
+        const uint32_t hb = S - 1 - u;               // log2 of the local gap (in rows)
+        for (uint32_t b = tid; b < nbf; b += nthr) {
+            uint32_t c = b & (cols - 1), j = b >> Q;
+            uint32_t r_lo = j & ((1u << hb) - 1u);
+            uint32_t d_lo = ((j >> hb) << (hb + 1)) | r_lo;
+            uint32_t i_lo = (d_lo << Q) | c, i_hi = i_lo + ((1u << hb) << Q);
+            // exponent of ω_n: (index mod gap) · 2^t
+            size_t r = a.last ? (size_t)r_lo : (((size_t)r_lo << L) | low_base | c);
+            size_t ex = r << t;
+            Fr x = sm[i_lo], y = sm[i_hi];
+            Fr sum = x + y, dif = x - y;
+            if (ex != 0) {
+                if (!a.inverse) dif = dif * Fr::load(a.tw + (ex << tw_shift));
+                else dif = (dif * Fr::load(a.tw + ((((size_t)1 << (lg - 1)) - ex) << tw_shift))).neg();
+            }
+            sm[i_lo] = sum; sm[i_hi] = dif;
+        }
+        __syncthreads();
+    }
+
+    // ---- store (+ optional post-scale) ----
+    for (uint32_t e = tid; e < tile_elems; e += nthr) {
+        uint32_t c = e & (cols - 1), d = e >> Q;
+        size_t k;
+        if (!a.last) k = (H << (S + L)) | ((size_t)d << L) | low_base | c;
+        else {
+            size_t drev = S ? (size_t)(__brev(d) >> (32 - S)) : 0;
+            k = (drev << t0) | (hprime_base + c);
+        }
+        Fr x = sm[((size_t)d << Q) | c];
+        if (a.post == 1) x = x * (*a.ninv);
+        else if (a.post == 2) x = x * coset_factor(a.coset_lo, a.coset_hi, k);
+        x.store(a.out + k);
+    }
+}
+
+__global__ void k_pointwise_mul(Fr* acc, const Fr* __restrict__ x, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) (Fr::load(acc + i) * Fr::load(x + i)).store(acc + i);
+}
+__global__ void k_fr_convert(Fr* out, const Fr* __restrict__ in, size_t n, int to_mont) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { Fr x = Fr::load(in + i); (to_mont ? x.to_mont() : x.from_mont()).store(out + i); }
+}
+
+int fr_pointwise_mul_device(void* d_acc, const void* d_x, size_t n, cudaStream_t stream) {
+    if (!n) return 0;
+    k_pointwise_mul<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((Fr*)d_acc, (const Fr*)d_x, n);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+int fr_from_mont_device(void* d_out, const void* d_in, size_t n, cudaStream_t stream) {
+    if (!n) return 0;
+    k_fr_convert<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((Fr*)d_out, (const Fr*)d_in, n, 0);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+int fr_to_mont_device(void* d_out, const void* d_in, size_t n, cudaStream_t stream) {
+    if (!n) return 0;
+    k_fr_convert<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((Fr*)d_out, (const Fr*)d_in, n, 1);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+static constexpr int MAX_STAGES = 8;    // rows per tile ≤ 256
+static constexpr int TILE_LG = 11;      // 2^11 elements × 32 B = 64 KiB of shared memory per CTA
+
+int ntt_device(void* d_inout, uint32_t lg, int direction, int type, void* d_scratch, cudaStream_t stream) {
+    if (lg > NTT_MAX_LG) return (int)cudaErrorInvalidValue;
+    if (direction != NTT_FORWARD && direction != NTT_INVERSE) return (int)cudaErrorInvalidValue;
+    if (type != NTT_STANDARD && type != NTT_COSET) return (int)cudaErrorInvalidValue;
+    int rc = 0;
+    Fr* A = (Fr*)d_inout;
+    Fr* B = (Fr*)d_scratch;
+    bool own_scratch = false;
+    const Fr* tw = nullptr;
+    int lgN = 0;
+    CosetTables ct{nullptr, nullptr, nullptr};
+    const bool inverse = direction == NTT_INVERSE, coset = type == NTT_COSET;
+    static std::once_flag smem_once[64];
+
+    if ((rc = get_twiddles((int)lg, &tw, &lgN)) != 0) return rc;
+    if (inverse || coset) { if ((rc = get_coset_tables((int)lg, inverse ? 1 : 0, &ct)) != 0) return rc; }
+    {
+        int dev = 0; cudaGetDevice(&dev);
+        std::call_once(smem_once[dev & 63], [] {
+            cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << TILE_LG) * (int)sizeof(Fr));
+        });
+    }
+    {
+        // split lg into P passes of near-equal stage counts
+        int P = lg <= (uint32_t)TILE_LG ? 1 : (int)((lg + MAX_STAGES - 1) / MAX_STAGES);
+        if (P > 1 && !B) {
+            CUDA_TRY(cudaMallocAsync((void**)&B, ((size_t)1 << lg) * sizeof(Fr), stream));
+            own_scratch = true;
+        }
+        int t0 = 0;
+        for (int p = 0; p < P; p++) {
+            int remaining = (int)lg - t0;
+            int S = (remaining + (P - p) - 1) / (P - p);
+            PassArgs a;
+            a.tw = tw; a.coset_lo = ct.lo; a.coset_hi = ct.hi; a.ninv = ct.ninv;
+            a.lg = (int)lg; a.lgN = lgN; a.t0 = t0; a.S = S;
+            a.last = (p == P - 1) ? 1 : 0;
+            a.inverse = inverse ? 1 : 0;
+            a.pre = (p == 0 && coset && !inverse) ? 1 : 0;
+            a.post = (a.last && inverse) ? (coset ? 2 : 1) : 0;
+            int Q = TILE_LG - S;
+            if (Q > 3) Q = 3;
+            if (a.last) { if (Q > t0) Q = t0; }
+            else { int L = (int)lg - t0 - S; if (Q > L) Q = L; }
+            a.Q = Q;
+            a.in = (p == 0) ? A : B;
+            a.out = (P == 1) ? A : (a.last ? A : B);
+            size_t tiles = ((size_t)1 << lg) >> (S + Q);
+            size_t smem = ((size_t)1 << (S + Q)) * sizeof(Fr);
+            k_ntt_pass<<<(unsigned)tiles, 256, smem, stream>>>(a);
+            count_launch();
+            t0 += S;
+        }
+        CUDA_TRY(cudaGetLastError());
+    }
+done:
+    if (own_scratch) cudaFreeAsync(B, stream);
+    return rc;
+}
+
+}  // namespace b200

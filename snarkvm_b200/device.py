@@ -1,0 +1,151 @@
+"""Device-resident entry points (PART 2 of include/snarkvm_b200.h) on torch CUDA tensors.
+
+PyTorch is plumbing only: it owns the HBM allocations and the stream; every kernel that runs
+is one of this repository's hand-written sm_100a kernels inside libsnarkvm_b200.so.
+Tensor conventions: any dtype, contiguous, interpreted as raw bytes in the reference layouts
+(Fr: 32 B/elt; scalar: 32 B; affine: `stride` B/point, stride ≥ 104 and a multiple of 8).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .cuda import NTTDirection, NTTInputOutputOrder, NTTType
+
+XYZZ_BYTES = 192
+AFFINE_STRIDE = 104
+
+
+def _check(t: torch.Tensor, name: str) -> int:
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
+        raise TypeError(f"{name} must be a contiguous CUDA tensor")
+    return t.data_ptr()
+
+
+def _nbytes(t: torch.Tensor) -> int:
+    return t.numel() * t.element_size()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ntt_(x: torch.Tensor, direction: NTTDirection = NTTDirection.Forward, ntt_type: NTTType = NTTType.Standard,
+         scratch: torch.Tensor | None = None) -> torch.Tensor:
+    """In-place natural-order NTT of the 2^lg Fr elements in `x` (32 B each)."""
+    n = _nbytes(x) // 32
+    if n <= 0 or n & (n - 1) or n * 32 != _nbytes(x):
+        raise ValueError("domain_size is not power of 2")
+    lg = n.bit_length() - 1
+    sp = 0
+    if scratch is not None:
+        if _nbytes(scratch) < _nbytes(x):
+            raise ValueError("scratch too small")
+        sp = _check(scratch, "scratch")
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().snarkvm_b200_ntt_device(_check(x, "x"), lg, int(NTTInputOutputOrder.NN), int(direction),
+                                                       int(ntt_type), sp, _stream()))
+    return x
+
+
+def polymul(polys: list, evals: list, lg: int) -> torch.Tensor:
+    dev = (polys + evals)[0].device
+    n = 1 << lg
+    out = torch.zeros((n, 4), dtype=torch.int64, device=dev)
+    pp = (ctypes.c_void_p * max(1, len(polys)))(*[_check(p, "poly") for p in polys])
+    pl = (ctypes.c_size_t * max(1, len(polys)))(*[_nbytes(p) // 32 for p in polys])
+    ep = (ctypes.c_void_p * max(1, len(evals)))(*[_check(e, "eval") for e in evals])
+    el = (ctypes.c_size_t * max(1, len(evals)))(*[_nbytes(e) // 32 for e in evals])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().snarkvm_b200_polymul_device(out.data_ptr(), len(polys), ctypes.cast(pp, ctypes.c_void_p),
+                                                           ctypes.cast(pl, ctypes.c_void_p), len(evals),
+                                                           ctypes.cast(ep, ctypes.c_void_p), ctypes.cast(el, ctypes.c_void_p),
+                                                           lg, _stream()))
+    return out
+
+
+def msm_plan(npoints: int) -> dict:
+    c, nwin, cap = ctypes.c_int(), ctypes.c_int(), ctypes.c_uint32()
+    _lib.check(_lib.lib().snarkvm_b200_msm_plan(npoints, ctypes.byref(c), ctypes.byref(nwin), ctypes.byref(cap)))
+    return {"c": c.value, "nwin": nwin.value, "cap": cap.value}
+
+
+def _msm_args(bases: torch.Tensor, scalars: torch.Tensor, stride: int):
+    npoints = _nbytes(scalars) // 32
+    if npoints * 32 != _nbytes(scalars):
+        raise ValueError("scalars must be a whole number of 32-byte integers")
+    if npoints * stride > _nbytes(bases):
+        raise ValueError(f"length mismatch {_nbytes(bases) // stride} points < {npoints} scalars")
+    return npoints
+
+
+def msm(bases: torch.Tensor, scalars: torch.Tensor, stride: int = AFFINE_STRIDE) -> np.ndarray:
+    """VariableBase::msm with bases and scalars resident in HBM → normalised projective uint64[18]."""
+    npoints = _msm_args(bases, scalars, stride)
+    out = np.zeros(18, dtype=np.uint64)
+    with torch.cuda.device(bases.device):
+        _lib.check(_lib.lib().snarkvm_b200_msm_device(out.ctypes.data, _check(bases, "bases"), npoints,
+                                                       _check(scalars, "scalars"), stride, _stream()))
+    return out
+
+
+def msm_window_sums(bases: torch.Tensor, scalars: torch.Tensor, stride: int = AFFINE_STRIDE) -> torch.Tensor:
+    """Per-window XYZZ sums [nwin, 24] (int64 view of 192-byte points), left in HBM."""
+    npoints = _msm_args(bases, scalars, stride)
+    plan = msm_plan(npoints)
+    sums = torch.empty((plan["nwin"], XYZZ_BYTES // 8), dtype=torch.int64, device=bases.device)
+    with torch.cuda.device(bases.device):
+        _lib.check(_lib.lib().snarkvm_b200_msm_window_sums_device(sums.data_ptr(), _check(bases, "bases"), npoints,
+                                                                   _check(scalars, "scalars"), stride, _stream()))
+    return sums
+
+
+def xyzz_sum_ranks(gathered: torch.Tensor, nranks: int, count: int) -> torch.Tensor:
+    out = torch.empty((count, XYZZ_BYTES // 8), dtype=torch.int64, device=gathered.device)
+    with torch.cuda.device(gathered.device):
+        _lib.check(_lib.lib().snarkvm_b200_xyzz_sum_ranks_device(out.data_ptr(), _check(gathered, "gathered"), nranks, count,
+                                                                  _stream()))
+    return out
+
+
+def msm_finish(window_sums_host: np.ndarray, c: int) -> np.ndarray:
+    """Host fold Σ_w 2^{c·w}·S_w of XYZZ window sums (c = 0: plain sum) → normalised projective."""
+    ws = np.ascontiguousarray(window_sums_host).view(np.uint8).reshape(-1, XYZZ_BYTES)
+    out = np.zeros(18, dtype=np.uint64)
+    _lib.check(_lib.lib().snarkvm_b200_msm_finish(out.ctypes.data, ws.ctypes.data, ws.shape[0], c))
+    return out
+
+
+def kzg_commit(powers: torch.Tensor, coeffs_mont: torch.Tensor, stride: int = AFFINE_STRIDE) -> np.ndarray:
+    """KZG10::commit core: Σ to_bigint(coeff_i)·powers_i (kzg10/mod.rs:98-156), all operands in HBM."""
+    n = _msm_args(powers, coeffs_mont, stride)
+    out = np.zeros(18, dtype=np.uint64)
+    with torch.cuda.device(powers.device):
+        _lib.check(_lib.lib().snarkvm_b200_kzg_commit_device(out.ctypes.data, _check(powers, "powers"), stride,
+                                                              _check(coeffs_mont, "coeffs"), n, _stream()))
+    return out
+
+
+def fr_from_mont(x: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().snarkvm_b200_fr_from_mont_device(out.data_ptr(), _check(x, "x"), _nbytes(x) // 32, _stream()))
+    return out
+
+
+def fr_to_mont(x: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().snarkvm_b200_fr_to_mont_device(out.data_ptr(), _check(x, "x"), _nbytes(x) // 32, _stream()))
+    return out
+
+
+def generate_bases(npoints: int, seed: int, device="cuda", stride: int = AFFINE_STRIDE) -> torch.Tensor:
+    """Synthetic G1 bases P_i = h(seed, i)·G in the reference affine layout, generated in HBM."""
+    t = torch.empty((npoints, stride), dtype=torch.uint8, device=device)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.lib().snarkvm_b200_generate_bases_device(t.data_ptr(), npoints, stride, seed & (2**64 - 1), _stream()))
+    return t

@@ -1,0 +1,226 @@
+"""GPU parity: the CUDA MSM vs the oracle, bit-exact on the to_affine()-normalised projective image.
+Restates test_msm / test_msm_cuda (algorithms/src/msm/variable_base/mod.rs:90-119: sizes 1…1000 and
+2^2…2^16 vs the CPU algorithms) and the unequal-length test (msm/tests.rs:53-67)."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bls12_377 as py
+
+from helpers import (affine_array, generated_base_multiplier, generated_base_multipliers, oracle_bases,
+                     random_canonical_fr, scalars_from_ints)
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _dev(x):
+    import torch
+    if x.dtype == np.uint64:
+        x = x.view(np.int64)
+    return torch.from_numpy(x.copy()).cuda()
+
+
+@pytest.fixture(scope="module")
+def bases64k(oracle_cpu):
+    return oracle_bases(oracle_cpu, 1 << 16, seed=3)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 10, 14, 15, 16, 31, 32, 33, 50, 100, 500, 1000, 1024, 1025, 4096, 1 << 14, 1 << 16])
+def test_msm_host_ffi_vs_oracle(oracle_cpu, bases64k, n):
+    """through the drop-in symbol snarkvm_msm with HOST buffers, as variable_base/mod.rs:33-42 calls it"""
+    from snarkvm_b200.algorithms import VariableBase
+    scal = random_canonical_fr(n, seed=n)
+    got = VariableBase.msm(bases64k[:n], scal)
+    want = oracle_cpu.msm(bases64k[:n], scal, oracle_cpu.BATCHED)
+    assert (got == want).all(), n
+    if n <= 1000:
+        assert (got == oracle_cpu.msm(bases64k[:n], scal, oracle_cpu.NAIVE)).all()
+
+
+def test_msm_unequal_lengths(oracle_cpu, bases64k):
+    from snarkvm_b200.algorithms import VariableBase
+    scal = random_canonical_fr(700, seed=1)
+    assert (VariableBase.msm(bases64k[:1000], scal) == oracle_cpu.msm(bases64k[:700], scal, 0)).all()
+
+
+def test_msm_edge_scalars_and_points(oracle_cpu, bases64k):
+    """zero / one / r−1 scalars, ∞ bases, duplicated bases with equal scalars (doubling inside a bucket),
+    P and −P with equal scalars (cancellation inside a bucket)."""
+    from snarkvm_b200.algorithms import VariableBase
+    n = 2048
+    bases = bases64k[:n].copy()
+    scal = random_canonical_fr(n, seed=9)
+    scal[0:16] = 0
+    scal[16:32] = scalars_from_ints([1])[0]
+    scal[32:48] = scalars_from_ints([py.R_MOD - 1])[0]
+    bases[48:64, 96] = 1                                              # infinity flag set (coordinates ignored)
+    bases[100:200] = bases[300]; scal[100:200] = scal[300]           # 101 copies of one (point, scalar)
+    neg = affine_array([py.g1_neg(py.affine_from_bytes(bases[400].tobytes()))])[0]
+    bases[401] = neg; scal[401] = scal[400]
+    got = VariableBase.msm(bases, scal)
+    assert (got == oracle_cpu.msm(bases, scal, 0)).all()
+    assert (got == oracle_cpu.msm(bases, scal, 1)).all()
+
+
+def test_msm_degenerate_results(oracle_cpu, bases64k):
+    from snarkvm_b200.algorithms import VariableBase
+    inf = np.frombuffer(py.projective_bytes_normalised(None), dtype=np.uint64)
+    n = 512
+    zeros = np.zeros((n, 4), dtype=np.uint64)
+    assert (VariableBase.msm(bases64k[:n], zeros) == inf).all()                         # all-zero scalars
+    allinf = bases64k[:n].copy(); allinf[:, 96] = 1
+    assert (VariableBase.msm(allinf, random_canonical_fr(n, 4)) == inf).all()           # all-∞ bases
+    assert (VariableBase.msm(bases64k[:n], zeros[:0]) == inf).all()                     # empty
+    # Σ s·P + Σ s·(−P) = ∞
+    pts = [py.affine_from_bytes(bases64k[i].tobytes()) for i in range(64)]
+    both = affine_array(pts + [py.g1_neg(p) for p in pts])
+    s = random_canonical_fr(64, 5)
+    assert (VariableBase.msm(both, np.concatenate([s, s])) == inf).all()
+
+
+def test_msm_skewed_distributions(oracle_cpu, bases64k):
+    """the reference bench's shape (benches/msm/variable_base.rs:29-32): few distinct bases repeated many
+    times, and ALL scalars equal — every window has one hot bucket."""
+    from snarkvm_b200.algorithms import VariableBase
+    n = 1 << 15
+    rep = np.tile(bases64k[:32], (n // 32, 1))
+    scal = random_canonical_fr(n, seed=13)
+    assert (VariableBase.msm(rep, scal) == oracle_cpu.msm(rep, scal, 1)).all()
+    same = np.tile(scal[:1], (n, 1))
+    got = VariableBase.msm(bases64k[:n], same)
+    assert (got == oracle_cpu.msm(bases64k[:n], same, 1)).all()
+    assert (VariableBase.msm(rep, same) == oracle_cpu.msm(rep, same, 1)).all()
+
+
+def test_msm_real_srs_points(oracle_cpu):
+    with open(os.path.join(HERE, "golden", "powers_of_beta_15_first512.usrs"), "rb") as f:
+        pts = py.parse_usrs_points(f.read(), 512)
+    from snarkvm_b200.algorithms import VariableBase
+    bases = affine_array(pts)
+    scal = random_canonical_fr(512, seed=21)
+    got = VariableBase.msm(bases, scal)
+    assert (got == oracle_cpu.msm(bases, scal, 0)).all()
+    sc_int = [py.from_limbs(r) for r in scal[:48]]
+    assert VariableBase.msm(bases[:48], scal[:48]).tobytes() == py.projective_bytes_normalised(py.msm_naive(pts[:48], sc_int))
+
+
+def test_generated_bases_match_scalar_multiples(oracle_cpu):
+    """snarkvm_b200_generate_bases_device: P_i = h(seed, i)·G — checked against the oracle's mul_bits."""
+    from snarkvm_b200 import device
+    seed = 0xB200
+    b = device.generate_bases(300, seed).cpu().numpy()
+    g = affine_array([py.G1_GENERATOR])[0]
+    for i in (0, 1, 2, 77, 299):
+        k = generated_base_multiplier(seed, i)
+        want = oracle_cpu.g1_mul(g, scalars_from_ints([k])[0])
+        assert b[i, 96] == 0 and (b[i, 97:] == 0).all()
+        assert b[i, :96].tobytes() == want.tobytes()[:96], i
+        assert oracle_cpu.g1_is_on_curve(b[i])
+
+
+@pytest.mark.parametrize("lg", [17, 18])
+def test_msm_device_api_vs_oracle(oracle_cpu, lg):
+    from snarkvm_b200 import device
+    n = 1 << lg
+    bases = device.generate_bases(n, seed=lg)
+    scal = random_canonical_fr(n, seed=lg)
+    got = device.msm(bases, _dev(scal))
+    assert (got == oracle_cpu.msm(bases.cpu().numpy(), scal, 0)).all()
+
+
+def test_kzg_commit_vs_oracle(oracle_cpu):
+    """KZG10::commit core: Montgomery coefficients → to_bigint → MSM (kzg10/mod.rs:98-156, 455-474)"""
+    from snarkvm_b200.algorithms import KZG10
+    from snarkvm_b200 import device
+    n = 1 << 14
+    powers = device.generate_bases(n, seed=99)
+    coeffs = random_canonical_fr(n, seed=31)              # Montgomery images of random field elements
+    coeffs[-100:] = 0                                     # trailing zero coefficients (skip_leading_zeros…)
+    got = KZG10.commit(powers, _dev(coeffs))
+    plain = oracle_cpu.fr_from_mont(coeffs)
+    assert (got == oracle_cpu.msm(powers.cpu().numpy(), plain, 0)).all()
+
+
+def test_window_sums_and_host_finish(oracle_cpu):
+    """the sharded-MSM pieces on one GPU: window sums in HBM → host fold == full MSM; and two half shards
+    summed by the device rank-sum kernel == the full MSM."""
+    import torch
+    from snarkvm_b200 import device
+    n = 1 << 13
+    bases = device.generate_bases(n, seed=5)
+    scal = random_canonical_fr(n, seed=6)
+    dscal = _dev(scal)
+    plan = device.msm_plan(n)
+    sums = device.msm_window_sums(bases, dscal)
+    want = oracle_cpu.msm(bases.cpu().numpy(), scal, 0)
+    assert (device.msm_finish(sums.cpu().numpy(), plan["c"]) == want).all()
+    h = n // 2
+    planh = device.msm_plan(h)
+    s0 = device.msm_window_sums(bases[:h].contiguous(), dscal[:h].contiguous())
+    s1 = device.msm_window_sums(bases[h:].contiguous(), dscal[h:].contiguous())
+    tot = device.xyzz_sum_ranks(torch.stack([s0, s1]).contiguous(), 2, planh["nwin"])
+    assert (device.msm_finish(tot.cpu().numpy(), planh["c"]) == want).all()
+
+
+@pytest.mark.parametrize("lg", [20, 22, 24])
+def test_msm_full_size_properties(oracle_cpu, lg):
+    """BASELINE config 2 sizes through size-independent properties: (1) bases are known multiples k_i·G, so
+    Σ s_i·P_i = (Σ s_i·k_i mod r)·G — one scalar multiplication by the oracle; (2) linearity in the scalars;
+    (3) at 2^20 also the full oracle MSM."""
+    from snarkvm_b200 import device
+    n = 1 << lg
+    seed = 1000 + lg
+    bases = device.generate_bases(n, seed)
+    scal = random_canonical_fr(n, seed=lg)
+    got = device.msm(bases, _dev(scal))
+    # (1) closed form
+    ks = np.zeros((n, 4), dtype=np.uint64)
+    ks[:, 0] = generated_base_multipliers(seed, n)
+    dot = oracle_cpu.fr_dot_canonical(scal, ks)
+    g = affine_array([py.G1_GENERATOR])[0]
+    want = oracle_cpu.g1_mul(g, dot)
+    assert (got == want).all()
+    if lg <= 20:
+        assert (got == oracle_cpu.msm(bases.cpu().numpy(), scal, 0)).all()
+    # (2) msm(s) + msm(t) == msm(s + t mod r)
+    t = random_canonical_fr(n, seed=lg + 50)
+    st = np.empty_like(scal)
+    for i0 in range(0, n, 1 << 18):
+        a = scal[i0:i0 + (1 << 18)]
+        b = t[i0:i0 + (1 << 18)]
+        st[i0:i0 + (1 << 18)] = _add_mod_r(a, b)
+    lhs = oracle_cpu.g1_add(got, device.msm(bases, _dev(t)))
+    assert (lhs == device.msm(bases, _dev(st))).all()
+
+
+def _add_mod_r(a, b):
+    """(a + b) mod r on uint64 [n, 4] limb arrays (vectorised carry chain)."""
+    r = np.array(py.to_limbs(py.R_MOD, 4), dtype=np.uint64)
+    out = np.empty_like(a)
+    carry = np.zeros(a.shape[0], dtype=np.uint64)
+    for k in range(4):
+        s = a[:, k] + b[:, k]
+        c1 = s < a[:, k]
+        s2 = s + carry
+        c2 = s2 < s
+        out[:, k] = s2
+        carry = (c1 | c2).astype(np.uint64)
+    # subtract r where out >= r (no carry out of 256 bits since a, b < r < 2^253)
+    ge = np.ones(a.shape[0], dtype=bool); gt = np.zeros(a.shape[0], dtype=bool)
+    for k in (3, 2, 1, 0):
+        gt |= ge & (out[:, k] > r[k]); ge &= out[:, k] == r[k]
+    sel = gt | ge
+    borrow = np.zeros(a.shape[0], dtype=np.uint64)
+    sub = np.empty_like(out)
+    for k in range(4):
+        d = out[:, k] - r[k]
+        b1 = out[:, k] < r[k]
+        d2 = d - borrow
+        b2 = d < borrow
+        sub[:, k] = d2
+        borrow = (b1 | b2).astype(np.uint64)
+    out[sel] = sub[sel]
+    return out
