@@ -115,6 +115,13 @@ SNARKVM_API int snarkvm_b200_kzg_commit_device(void* out144, const void* d_power
 SNARKVM_API int snarkvm_b200_fr_from_mont_device(void* d_out, const void* d_in, size_t n, void* stream);
 SNARKVM_API int snarkvm_b200_fr_to_mont_device(void* d_out, const void* d_in, size_t n, void* stream);
 
+/* Per-kernel CUDA-event timing on the launching stream (off by default).  kind: 0 = MSM bucket sort
+ * (digit histogram + scatter), 1 = MSM bucket accumulation, 2 = MSM bucket reduction, 3 = NTT passes.
+ * collect() waits for the recorded launches of that kind, returns their summed milliseconds and count, and
+ * clears them. */
+SNARKVM_API int snarkvm_b200_profile_enable(int on);
+SNARKVM_API int snarkvm_b200_profile_collect(int kind, double* total_ms, uint64_t* count);
+
 /* Deterministic synthetic bases P_i = h(seed, i) * G written in the reference affine layout. */
 SNARKVM_API int snarkvm_b200_generate_bases_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, void* stream);
 

@@ -11,7 +11,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsnarkvm_b200.so")
+LIB_PATH = os.environ.get("SNARKVM_B200_LIB") or os.path.join(_HERE, "libsnarkvm_b200.so")   # override: A/B builds
 
 # every symbol include/snarkvm_b200.h declares
 SYMBOLS = (
@@ -20,7 +20,7 @@ SYMBOLS = (
     "snarkvm_b200_polymul_device", "snarkvm_b200_msm_plan", "snarkvm_b200_msm_device",
     "snarkvm_b200_msm_window_sums_device", "snarkvm_b200_xyzz_sum_ranks_device", "snarkvm_b200_msm_finish",
     "snarkvm_b200_kzg_commit_device", "snarkvm_b200_fr_from_mont_device", "snarkvm_b200_fr_to_mont_device",
-    "snarkvm_b200_generate_bases_device",
+    "snarkvm_b200_profile_enable", "snarkvm_b200_profile_collect", "snarkvm_b200_generate_bases_device",
 )
 
 
@@ -72,6 +72,8 @@ def lib():
     L.snarkvm_b200_kzg_commit_device.argtypes = [vp, vp, sz, vp, sz, vp]
     L.snarkvm_b200_fr_from_mont_device.argtypes = [vp, vp, sz, vp]
     L.snarkvm_b200_fr_to_mont_device.argtypes = [vp, vp, sz, vp]
+    L.snarkvm_b200_profile_enable.argtypes = [i32]
+    L.snarkvm_b200_profile_collect.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
     L.snarkvm_b200_generate_bases_device.argtypes = [vp, sz, sz, u64, vp]
     for s in SYMBOLS[5:]:
         getattr(L, s).restype = i32
@@ -99,3 +101,17 @@ def check(code: int) -> None:
 
 def launch_count() -> int:
     return int(lib().snarkvm_b200_launch_count())
+
+
+PROF_MSM_SORT, PROF_MSM_ACCUMULATE, PROF_MSM_REDUCE, PROF_NTT_PASS = 0, 1, 2, 3
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().snarkvm_b200_profile_enable(1 if on else 0))
+
+
+def profile_collect(kind: int):
+    """(total_ms, launches) of the recorded kernels of `kind` since the last collect."""
+    ms, cnt = ctypes.c_double(), ctypes.c_uint64()
+    check(lib().snarkvm_b200_profile_collect(kind, ctypes.byref(ms), ctypes.byref(cnt)))
+    return ms.value, cnt.value

@@ -38,21 +38,13 @@ struct ThreadCtx {
     ~ThreadCtx() {}
 };
 thread_local ThreadCtx t_ctx;
-std::once_flag g_pool_once[64];
 
 int thread_stream(cudaStream_t* out) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     dev &= 63;
-    std::call_once(g_pool_once[dev], [dev] {
-        // keep freed scratch in the stream-ordered pool instead of returning it to the driver
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            uint64_t thr = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-    });
+    ensure_pool_configured();
     if (!t_ctx.have[dev]) {
         e = cudaStreamCreateWithFlags(&t_ctx.stream[dev], cudaStreamNonBlocking);
         if (e != cudaSuccess) return (int)e;
@@ -71,6 +63,7 @@ int msm_device_impl(void* out144, const void* d_points, size_t npoints, const vo
                     cudaStream_t stream) {
     if (npoints == 0) { write_infinity(out144); return 0; }
     if (stride < 104 || (stride & 7)) return (int)cudaErrorInvalidValue;
+    ensure_pool_configured();
     MsmPlan plan = msm_make_plan(npoints);
     uint32_t* d_sums = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&d_sums, (size_t)plan.nwin * 192, stream);
@@ -88,6 +81,7 @@ int msm_device_impl(void* out144, const void* d_points, size_t npoints, const vo
 
 int polymul_device_impl(void* d_out, size_t pcount, const void* const* d_polys, const size_t* plens, size_t ecount,
                         const void* const* d_evals, const size_t* elens, uint32_t lg, cudaStream_t stream) {
+    ensure_pool_configured();
     const size_t n = (size_t)1 << lg, bytes = n * 32;
     if (pcount + ecount == 0) return 0;
     for (size_t i = 0; i < pcount; i++) if (plens[i] > n) return (int)cudaErrorInvalidValue;
@@ -275,6 +269,9 @@ int snarkvm_b200_fr_from_mont_device(void* d_out, const void* d_in, size_t n, vo
 int snarkvm_b200_fr_to_mont_device(void* d_out, const void* d_in, size_t n, void* stream) {
     return fr_to_mont_device(d_out, d_in, n, (cudaStream_t)stream);
 }
+
+int snarkvm_b200_profile_enable(int on) { prof_enable(on != 0); return 0; }
+int snarkvm_b200_profile_collect(int kind, double* total_ms, uint64_t* count) { return prof_collect(kind, total_ms, count); }
 
 int snarkvm_b200_generate_bases_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, void* stream) {
     return msm_generate_bases_device(d_points, npoints, stride, seed, (cudaStream_t)stream);

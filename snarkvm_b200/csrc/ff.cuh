@@ -91,7 +91,20 @@ FF_DEV void mont_step(uint32_t (&ev)[N], uint32_t (&od)[N], const uint32_t (&a)[
 #pragma unroll
     for (int k = 0; k < N; k++) pm[k] = P::mod(k);
     row_mad<N>(od, &pm[1], m);                          // odd columns of p (pm[N] is never read: j < N-1)
-    row_mad<N>(ev, &pm[0], m);
+#ifdef FF_NO_P0_SHORTCUT
+    if (false) {
+#else
+    if (P::MOD0_IS_ONE) {
+#endif
+        // both BLS12-377 moduli are ≡ 1 mod 2^32: p[0]·m = m, so column 0 is ev[0] + m = 0 with carry
+        // (ev[0] != 0) and the high word of that product is 0 — two adds instead of a 32x32->64 multiply.
+        ev[0] = ptx_add_cc(ev[0], m);
+        ev[1] = ptx_addc_cc(ev[1], 0u);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) { ev[j] = ptx_madc_lo_cc(pm[j], m, ev[j]); ev[j + 1] = ptx_madc_hi_cc(pm[j], m, ev[j + 1]); }
+    } else {
+        row_mad<N>(ev, &pm[0], m);
+    }
     od[N - 1] = ptx_addc(od[N - 1], 0u);
 }
 
@@ -160,7 +173,7 @@ struct Fp {
     FF_DEV Fp neg() const { return is_zero() ? *this : (zero() - *this); }
     FF_DEV Fp dbl() const { return *this + *this; }
 
-    FF_DEV friend Fp operator*(const Fp& a, const Fp& b) {
+    FF_DEV static Fp mul_inline(const Fp& a, const Fp& b) {
         uint32_t e[N], o[N];
 #pragma unroll
         for (int i = 0; i < N; i += 2) {
@@ -175,6 +188,16 @@ struct Fp {
         r.v[N - 1] = ptx_addc(e[N - 1], 0u);
         r.final_sub();
         return r;
+    }
+    // Out-of-line copy (arguments and result travel in registers — checked in SASS).  Kernels whose hot
+    // loop contains many multiplications call this one so the loop stays inside the instruction cache.
+    static __device__ __noinline__ Fp mul_call(Fp a, Fp b) { return mul_inline(a, b); }
+    FF_DEV friend Fp operator*(const Fp& a, const Fp& b) {
+#ifdef FF_CALL_MUL
+        return mul_call(a, b);
+#else
+        return mul_inline(a, b);
+#endif
     }
     FF_DEV Fp sqr() const { return (*this) * (*this); }
 
@@ -252,6 +275,7 @@ struct Fp {
 struct FrParams {
     static constexpr int N = 8;
     static constexpr uint32_t INV32 = 0xffffffffu;     // -r^{-1} mod 2^32 (low word of INV, fr.rs:137)
+    static constexpr bool MOD0_IS_ONE = true;
     FF_TABLE(mod, 0x00000001u, 0x0a118000u, 0xd0000001u, 0x59aa76feu, 0x5c37b001u, 0x60b44d1eu, 0x9a2ca556u, 0x12ab655eu)
     FF_TABLE(r1,  0xfffffff3u, 0x7d1c7fffu, 0x6ffffff2u, 0x7257f50fu, 0x512c0feeu, 0x16d81575u, 0x2bbb9a9du, 0x0d4bda32u)
     FF_TABLE(r2,  0xb861857bu, 0x25d577bau, 0x8860591fu, 0xcc2c27b5u, 0xe5dc8593u, 0xa7cc008fu, 0xeff1c939u, 0x011fdae7u)
@@ -259,6 +283,7 @@ struct FrParams {
 struct FqParams {
     static constexpr int N = 12;
     static constexpr uint32_t INV32 = 0xffffffffu;     // -q^{-1} mod 2^32 (low word of INV, fq.rs:111)
+    static constexpr bool MOD0_IS_ONE = true;
     FF_TABLE(mod, 0x00000001u, 0x8508c000u, 0x30000000u, 0x170b5d44u, 0xba094800u, 0x1ef3622fu, 0x00f5138fu, 0x1a22d9f3u, 0x6ca1493bu, 0xc63b05c0u, 0x17c510eau, 0x01ae3a46u)
     FF_TABLE(r1,  0xffffff68u, 0x02cdffffu, 0x7fffffb1u, 0x51409f83u, 0x8a7d3ff2u, 0x9f7db3a9u, 0x6e7c6305u, 0x7b4e97b7u, 0x803c84e8u, 0x4cf495bfu, 0xe2fdf49au, 0x008d6661u)
     FF_TABLE(r2,  0x9400cd22u, 0xb786686cu, 0xb00431b1u, 0x0329fcaau, 0x62d6b46du, 0x22a5f111u, 0x827dc3acu, 0xbfdf7d03u, 0x41790bf9u, 0x837e92f0u, 0x1e914b88u, 0x006dfccbu)

@@ -2,10 +2,14 @@
 #include "msm.cuh"
 
 #include <atomic>
+#include <mutex>
+#include <utility>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 #include <cub/device/device_scan.cuh>
 
+#define FF_CALL_MUL 1
 #include "ec.cuh"
 
 namespace b200 {
@@ -13,6 +17,52 @@ namespace b200 {
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n); }
+
+void ensure_pool_configured() {
+    static std::once_flag once[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    std::call_once(once[dev & 63], [dev] {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    });
+}
+
+static std::atomic<bool> g_prof{false};
+static std::mutex g_prof_mu;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_recs[PROF_KINDS];
+void prof_enable(bool on) { g_prof.store(on); }
+bool prof_enabled() { return g_prof.load(); }
+ProfScope::ProfScope(int kind_, cudaStream_t stream_) : stream(stream_), kind(kind_) {
+    if (!g_prof.load()) return;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; return; }
+    cudaEventRecord(a, stream);
+}
+ProfScope::~ProfScope() {
+    if (!a) return;
+    cudaEventRecord(b, stream);
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    g_prof_recs[kind].emplace_back(a, b);
+}
+int prof_collect(int kind, double* total_ms, uint64_t* count) {
+    if (kind < 0 || kind >= PROF_KINDS) return (int)cudaErrorInvalidValue;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> recs;
+    { std::lock_guard<std::mutex> lock(g_prof_mu); recs.swap(g_prof_recs[kind]); }
+    double tot = 0; int rc = 0;
+    for (auto& r : recs) {
+        float ms = 0;
+        cudaError_t e = cudaEventSynchronize(r.second);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.first, r.second);
+        if (e != cudaSuccess) rc = (int)e; else tot += ms;
+        cudaEventDestroy(r.first); cudaEventDestroy(r.second);
+    }
+    if (total_ms) *total_ms = tot;
+    if (count) *count = recs.size();
+    return rc;
+}
 
 #define CUDA_TRY(x)                                   \
     do {                                              \
@@ -90,7 +140,14 @@ __global__ void k_items_per_bucket(const uint32_t* __restrict__ hist, uint32_t* 
 
 // One thread per work item (a run of ≤ cap sorted entries of one bucket): XYZZ mixed additions
 // of gathered affine bases.  partial[item] receives the item's sum.
-__global__ void __launch_bounds__(256) k_bucket_accumulate(const uint8_t* __restrict__ points, size_t stride,
+// 128-thread CTAs, 4 per SM (≤ 128 registers/thread, a few hundred bytes of spill): measured on B200 at
+// 2^24 points — 129 ms vs 140 ms for 256×1 at 207 registers (profiles/README.md).  The kernel is bound by
+// the IMAD pipe, and 16 warps/SM hide its latency better than 8.
+#ifndef MSM_ACC_THREADS
+#define MSM_ACC_THREADS 128
+#define MSM_ACC_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(MSM_ACC_THREADS, MSM_ACC_MINBLOCKS) k_bucket_accumulate(const uint8_t* __restrict__ points, size_t stride,
                                                             const uint32_t* __restrict__ sorted,
                                                             const uint32_t* __restrict__ bucket_start /* [TB+1] */,
                                                             const uint32_t* __restrict__ item_start /* [TB+1] */,
@@ -183,6 +240,7 @@ int xyzz_sum_ranks_device(uint32_t* d_out, const uint32_t* d_in, int nranks, int
 int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const void* d_points, size_t stride,
                            const void* d_scalars, size_t npoints, cudaStream_t stream) {
     int rc = 0;
+    ensure_pool_configured();
     const uint32_t TB = (uint32_t)plan.nwin * plan.nbuckets;      // total buckets
     const size_t max_entries = npoints * (size_t)plan.nwin;
     const size_t max_items = (size_t)TB + max_entries / plan.cap + 1;
@@ -211,14 +269,20 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
     CUDA_TRY(cudaMemsetAsync(items, 0, (size_t)(TB + 1) * 4, stream));
     {
         const unsigned grid = (unsigned)((npoints + 255) / 256);
+        ProfScope* sort_scope = new ProfScope(PROF_MSM_SORT, stream);
         k_digits<false><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, hist, nullptr);
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, hist, bucket_start, (int)(TB + 1), stream));
         CUDA_TRY(cudaMemcpyAsync(cursors, bucket_start, (size_t)(TB + 1) * 4, cudaMemcpyDeviceToDevice, stream));
         k_digits<true><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, cursors, sorted);
         k_items_per_bucket<<<(TB + 255) / 256, 256, 0, stream>>>(hist, items, TB, plan.cap);
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(TB + 1), stream));
-        const unsigned agrid = (unsigned)((max_items + 255) / 256);
-        k_bucket_accumulate<<<agrid, 256, 0, stream>>>((const uint8_t*)d_points, stride, sorted, bucket_start, item_start, TB, plan.cap, partial);
+        delete sort_scope;
+        const unsigned agrid = (unsigned)((max_items + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
+        {
+            ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
+            k_bucket_accumulate<<<agrid, MSM_ACC_THREADS, 0, stream>>>((const uint8_t*)d_points, stride, sorted, bucket_start, item_start, TB, plan.cap, partial);
+        }
+        ProfScope red_scope(PROF_MSM_REDUCE, stream);
         const uint32_t nthreads = chunks_per_window * (uint32_t)plan.nwin;
         k_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, stream>>>(partial, item_start, plan.nbuckets, chunk, chunks_per_window, (uint32_t)plan.nwin, red_a);
         count_launch(7);

@@ -44,7 +44,26 @@ int msm_generate_bases_device(void* d_points, size_t npoints, size_t stride, uin
 // out[i] = Σ_r in[r][i]  over `nranks` arrays of `count` XYZZ points (multi-GPU combine).
 int xyzz_sum_ranks_device(uint32_t* d_out, const uint32_t* d_in, int nranks, int count, cudaStream_t stream);
 
+// Once per device: keep freed scratch inside the stream-ordered pool (release threshold = max) so that
+// steady-state calls never go back to the driver for their ~GB of workspace.
+void ensure_pool_configured();
+
 uint64_t launch_count();
 void count_launch(int n = 1);
+
+// Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline numbers).
+enum ProfKind { PROF_MSM_SORT = 0, PROF_MSM_ACCUMULATE = 1, PROF_MSM_REDUCE = 2, PROF_NTT_PASS = 3, PROF_KINDS = 4 };
+void prof_enable(bool on);
+bool prof_enabled();
+// records an event pair around whatever is enqueued on `stream` between begin and end
+struct ProfScope {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t stream;
+    int kind;
+    ProfScope(int kind, cudaStream_t stream);
+    ~ProfScope();
+};
+// waits for all recorded pairs of `kind`, returns their summed duration and count, and clears them
+int prof_collect(int kind, double* total_ms, uint64_t* count);
 
 }  // namespace b200

@@ -257,6 +257,7 @@ int ntt_device(void* d_inout, uint32_t lg, int direction, int type, void* d_scra
     if (direction != NTT_FORWARD && direction != NTT_INVERSE) return (int)cudaErrorInvalidValue;
     if (type != NTT_STANDARD && type != NTT_COSET) return (int)cudaErrorInvalidValue;
     int rc = 0;
+    ensure_pool_configured();
     Fr* A = (Fr*)d_inout;
     Fr* B = (Fr*)d_scratch;
     bool own_scratch = false;
@@ -301,7 +302,10 @@ int ntt_device(void* d_inout, uint32_t lg, int direction, int type, void* d_scra
             a.out = (P == 1) ? A : (a.last ? A : B);
             size_t tiles = ((size_t)1 << lg) >> (S + Q);
             size_t smem = ((size_t)1 << (S + Q)) * sizeof(Fr);
-            k_ntt_pass<<<(unsigned)tiles, 256, smem, stream>>>(a);
+            {
+                ProfScope pass_scope(PROF_NTT_PASS, stream);
+                k_ntt_pass<<<(unsigned)tiles, 256, smem, stream>>>(a);
+            }
             count_launch();
             t0 += S;
         }
