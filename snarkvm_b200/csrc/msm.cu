@@ -88,6 +88,17 @@ MsmPlan msm_make_plan(size_t npoints) {
     if (cap < 16) cap = 16;
     if (const char* e = getenv("SNARKVM_B200_MSM_CAP")) { long v = atol(e); if (v >= 1) cap = (size_t)v; }
     p.cap = (uint32_t)cap;
+    // Batched-affine pair levels before the XYZZ accumulation: halve buckets while they still hold ≥ ~16 points
+    // on average and the dense scratch (≈ 0.9 · n · W · 96 B) fits the budget.
+    size_t avg = npoints >> (c - 1);
+    int levels = 0;
+    while ((avg >> levels) >= 16 && levels < 8) levels++;
+    size_t scratch = total * 96 / 2 + total * 48 / 2 + total * 96 / 4 + npoints * 128;
+    size_t budget = (size_t)64 << 30;
+    if (const char* e = getenv("SNARKVM_B200_MSM_SCRATCH_GB")) { long v = atol(e); if (v >= 1) budget = (size_t)v << 30; }
+    if (scratch > budget) levels = 0;
+    if (const char* e = getenv("SNARKVM_B200_MSM_LEVELS")) { int v = atoi(e); if (v >= 0 && v <= 16) levels = v; }
+    p.levels = levels;
     return p;
 }
 
@@ -180,6 +191,173 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, MSM_ACC_MINBLOCKS) k_bucket_a
     acc.store(partial + (size_t)t * XYZZ_WORDS);
 }
 
+// =================================================================================================
+// Batched-affine pair levels (the reference's own idea — batch_add, batched.rs:175-325: pair up the
+// points of a bucket, add all pairs with ONE field inversion per batch via Montgomery's trick,
+// affine.rs:224-273 — restated for the GPU).  One level halves every bucket: output element i of a
+// bucket is in[2i] + in[2i+1] (or a copy of in[2i] when the count is odd).  A thread owns T consecutive
+// OUTPUT elements (across bucket boundaries, so hot buckets are spread over many threads), walks them
+// forward accumulating the running product of the denominators (x2 − x1, or 2·y1 for a doubling) into
+// `prefix`, inverts once (Fermat, ≈ 570 Fq mul amortised over T = 64…1024 additions), then walks them
+// backward peeling off one inverse per pair: 6 Fq mul per addition instead of 10 for an XYZZ mixed add.
+// Dense points are 96 B (x, y Montgomery); infinity is encoded as (0, 0), which is not on y² = x³ + 1.
+// =================================================================================================
+static constexpr int DENSE_WORDS = 24;
+static constexpr int BASE_WORDS = 32;       // level-0 copy of the bases: 96 B padded to one 128-byte line per point
+
+struct DensePoint { Fq x, y; bool inf; };
+FF_DEV DensePoint load_dense(const uint32_t* p) {
+    DensePoint d; d.x = Fq::load_ldg(p); d.y = Fq::load_ldg(p + 12);
+    d.inf = d.x.is_zero() && d.y.is_zero();
+    return d;
+}
+FF_DEV void store_dense(uint32_t* p, const DensePoint& d) {
+    if (d.inf) { Fq z = Fq::zero(); z.store(p); z.store(p + 12); }
+    else { d.x.store(p); d.y.store(p + 12); }
+}
+// Level-0 inputs are gathered through `sorted` from a dense, 128-byte-aligned copy of the bases made once
+// per call by k_densify_bases: a gathered point then costs one DRAM line instead of the two or three that
+// the reference's 104-byte stride straddles.
+template <bool GATHER>
+FF_DEV DensePoint load_level_input(const uint32_t* __restrict__ dense_bases, const uint32_t* __restrict__ sorted,
+                                   const uint32_t* __restrict__ dense_in, uint32_t idx) {
+    DensePoint d;
+    if (GATHER) {
+        uint32_t e = sorted[idx];
+        d = load_dense(dense_bases + (size_t)(e & 0x7fffffffu) * BASE_WORDS);
+        if ((e >> 31) && !d.inf) d.y = d.y.neg();
+    } else {
+        d = load_dense(dense_in + (size_t)idx * DENSE_WORDS);
+    }
+    return d;
+}
+// address of the record (forward pass reads x only: the denominator x2 − x1 needs nothing else unless the x's collide)
+template <bool GATHER>
+FF_DEV const uint32_t* level_input_ptr(const uint32_t* __restrict__ dense_bases, const uint32_t* __restrict__ sorted,
+                                       const uint32_t* __restrict__ dense_in, uint32_t idx) {
+    if (GATHER) return dense_bases + (size_t)(sorted[idx] & 0x7fffffffu) * BASE_WORDS;
+    return dense_in + (size_t)idx * DENSE_WORDS;
+}
+__global__ void k_densify_bases(const uint8_t* __restrict__ points, size_t stride, size_t n, uint32_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    AffinePoint a = load_affine(points, stride, i);
+    DensePoint d; d.x = a.x; d.y = a.y; d.inf = a.inf;
+    store_dense(out + i * BASE_WORDS, d);
+}
+enum PairKind { PAIR_COPY1 = 0, PAIR_COPY2 = 1, PAIR_INF = 2, PAIR_ADD = 3, PAIR_DBL = 4 };
+FF_DEV int classify_pair(const DensePoint& P, const DensePoint& Q, bool has2, Fq& d) {
+    if (!has2 || Q.inf) return PAIR_COPY1;
+    if (P.inf) return PAIR_COPY2;
+    if (P.x == Q.x) {
+        if (P.y == Q.y && !P.y.is_zero()) { d = P.y.dbl(); return PAIR_DBL; }
+        return PAIR_INF;                                   // P + (−P)  (or a 2-torsion point doubled)
+    }
+    d = Q.x - P.x;
+    return PAIR_ADD;
+}
+
+template <bool GATHER>
+__global__ void __launch_bounds__(128, 4) k_pair_level(const uint32_t* __restrict__ dense_bases,
+                                                        const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ dense_in,
+                                                        const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out,
+                                                        uint32_t total_buckets, uint32_t T, uint32_t* __restrict__ prefix,
+                                                        uint32_t* __restrict__ dense_out) {
+    const uint32_t total = off_out[total_buckets];
+    const uint64_t o0_64 = (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * T;
+    if (o0_64 >= total) return;
+    const uint32_t o0 = (uint32_t)o0_64;
+    const uint32_t o1 = (o0_64 + T < total) ? o0 + T : total;
+    uint32_t lo = 0, hi = total_buckets;                  // off_out[lo] <= o0 < off_out[hi]
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (off_out[mid] <= o0) lo = mid; else hi = mid; }
+    uint32_t b = lo;
+
+    // ---- forward: running product of denominators (x coordinates only on the common path) ----
+    Fq run = Fq::one();
+    for (uint32_t o = o0; o < o1; o++) {
+        while (o >= off_out[b + 1]) b++;
+        const uint32_t i = o - off_out[b], base_in = off_in[b], cnt = off_in[b + 1] - base_in;
+        const bool has2 = 2 * i + 1 < cnt;
+        if (has2) {
+            const uint32_t* pp = level_input_ptr<GATHER>(dense_bases, sorted, dense_in, base_in + 2 * i);
+            const uint32_t* qp = level_input_ptr<GATHER>(dense_bases, sorted, dense_in, base_in + 2 * i + 1);
+            Fq x1 = Fq::load_ldg(pp), x2 = Fq::load_ldg(qp);
+            if (x1 == x2 || x1.is_zero() || x2.is_zero()) {
+                // rare: equal x (doubling / cancellation) or a possible infinity — take the full path
+                DensePoint P = load_level_input<GATHER>(dense_bases, sorted, dense_in, base_in + 2 * i);
+                DensePoint Q = load_level_input<GATHER>(dense_bases, sorted, dense_in, base_in + 2 * i + 1);
+                Fq d;
+                int kind = classify_pair(P, Q, true, d);
+                if (kind >= PAIR_ADD) run = run * d;
+            } else {
+                run = run * (x2 - x1);
+            }
+        }
+        run.store(prefix + (size_t)o * 12);
+    }
+    Fq inv = run.inverse();
+    // ---- backward: one inverse per pair, then the affine addition / doubling ----
+    for (uint32_t o = o1; o-- > o0;) {
+        while (o < off_out[b]) b--;
+        const uint32_t i = o - off_out[b], base_in = off_in[b], cnt = off_in[b + 1] - base_in;
+        const bool has2 = 2 * i + 1 < cnt;
+        DensePoint P = load_level_input<GATHER>(dense_bases, sorted, dense_in, base_in + 2 * i);
+        DensePoint Q = P;
+        if (has2) Q = load_level_input<GATHER>(dense_bases, sorted, dense_in, base_in + 2 * i + 1);
+        Fq d;
+        int kind = classify_pair(P, Q, has2, d);
+        DensePoint R;
+        if (kind == PAIR_COPY1) R = P;
+        else if (kind == PAIR_COPY2) R = Q;
+        else if (kind == PAIR_INF) { R.inf = true; R.x = Fq::zero(); R.y = Fq::zero(); }
+        else {
+            Fq inv_d = (o == o0) ? inv : inv * Fq::load(prefix + (size_t)(o - 1) * 12);
+            inv = inv * d;
+            Fq lambda;
+            if (kind == PAIR_ADD) lambda = (Q.y - P.y) * inv_d;
+            else { Fq xx = P.x.sqr(); lambda = (xx.dbl() + xx) * inv_d; }
+            Fq x3 = lambda.sqr() - P.x - Q.x;                // Q.x == P.x in the doubling case
+            R.y = lambda * (P.x - x3) - P.y;
+            R.x = x3;
+            R.inf = false;
+        }
+        store_dense(dense_out + (size_t)o * DENSE_WORDS, R);
+    }
+}
+
+__global__ void k_halve_counts(const uint32_t* __restrict__ off_in, uint32_t* __restrict__ cnt_out, uint32_t total_buckets) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total_buckets) cnt_out[i] = (off_in[i + 1] - off_in[i] + 1u) >> 1;
+    else if (i == total_buckets) cnt_out[i] = 0;
+}
+__global__ void k_items_from_offsets(const uint32_t* __restrict__ off, uint32_t* __restrict__ items, uint32_t total_buckets, uint32_t cap) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total_buckets) items[i] = (off[i + 1] - off[i] + cap - 1u) / cap;
+    else if (i == total_buckets) items[i] = 0;
+}
+
+// XYZZ accumulation of what the pair levels left: contiguous dense points, no gather, no signs.
+__global__ void __launch_bounds__(MSM_ACC_THREADS, MSM_ACC_MINBLOCKS) k_bucket_accumulate_dense(
+    const uint32_t* __restrict__ dense, const uint32_t* __restrict__ bucket_start, const uint32_t* __restrict__ item_start,
+    uint32_t total_buckets, uint32_t cap, uint32_t* __restrict__ partial) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t total_items = item_start[total_buckets];
+    if (t >= total_items) return;
+    uint32_t lo = 0, hi = total_buckets;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (item_start[mid] <= t) lo = mid; else hi = mid; }
+    uint32_t wb = lo, seg = t - item_start[wb];
+    uint32_t b0 = bucket_start[wb], b1 = bucket_start[wb + 1];
+    uint32_t s0 = b0 + seg * cap, s1 = s0 + cap < b1 ? s0 + cap : b1;
+    XYZZ acc = XYZZ::infinity();
+    DensePoint p = load_dense(dense + (size_t)s0 * DENSE_WORDS);
+    for (uint32_t k = s0; k < s1; k++) {
+        AffinePoint cur; cur.x = p.x; cur.y = p.y; cur.inf = p.inf;
+        if (k + 1 < s1) p = load_dense(dense + (size_t)(k + 1) * DENSE_WORDS);
+        acc.add_affine(cur, false);
+    }
+    acc.store(partial + (size_t)t * XYZZ_WORDS);
+}
+
 // Σ of a bucket's item partials
 FF_DEV XYZZ bucket_sum(const uint32_t* __restrict__ partial, const uint32_t* __restrict__ item_start, uint32_t wb) {
     uint32_t i0 = item_start[wb], i1 = item_start[wb + 1];
@@ -248,6 +426,11 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
 
     uint32_t *hist = nullptr, *bucket_start = nullptr, *cursors = nullptr, *items = nullptr, *item_start = nullptr;
     uint32_t *sorted = nullptr, *partial = nullptr, *red_a = nullptr, *red_b = nullptr;
+    uint32_t *off_a = nullptr, *off_b = nullptr, *dense_a = nullptr, *dense_b = nullptr, *prefix = nullptr, *dense_bases = nullptr;
+    const int levels = plan.levels;
+    const size_t dense_cap_a = max_entries / 2 + TB + 1, dense_cap_b = max_entries / 4 + 2 * (size_t)TB + 1;
+    size_t pair_threads = 65536;                 // target thread count of a pair level (T = outputs / this, clamped to 64…1024)
+    if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_THREADS")) { long v = atol(e); if (v >= 1024) pair_threads = (size_t)v; }
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0;
     const uint32_t chunk = plan.nbuckets < 32u ? plan.nbuckets : 32u;
@@ -260,6 +443,14 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
     CUDA_TRY(cudaMallocAsync(&item_start, (size_t)(TB + 1) * 4, stream));
     CUDA_TRY(cudaMallocAsync(&sorted, max_entries * 4, stream));
     CUDA_TRY(cudaMallocAsync(&partial, max_items * XYZZ_WORDS * 4, stream));
+    if (levels > 0) {
+        CUDA_TRY(cudaMallocAsync(&off_a, (size_t)(TB + 1) * 4, stream));
+        CUDA_TRY(cudaMallocAsync(&off_b, (size_t)(TB + 1) * 4, stream));
+        CUDA_TRY(cudaMallocAsync(&dense_a, dense_cap_a * DENSE_WORDS * 4, stream));
+        if (levels > 1) CUDA_TRY(cudaMallocAsync(&dense_b, dense_cap_b * DENSE_WORDS * 4, stream));
+        CUDA_TRY(cudaMallocAsync(&prefix, dense_cap_a * 12 * 4, stream));
+        CUDA_TRY(cudaMallocAsync(&dense_bases, npoints * (size_t)BASE_WORDS * 4, stream));
+    }
     CUDA_TRY(cudaMallocAsync(&red_a, (size_t)plan.nwin * chunks_per_window * XYZZ_WORDS * 4, stream));
     CUDA_TRY(cudaMallocAsync(&red_b, (size_t)plan.nwin * (chunks_per_window / 32 + 1) * XYZZ_WORDS * 4, stream));
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, hist, bucket_start, (int)(TB + 1), stream));
@@ -274,18 +465,54 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, hist, bucket_start, (int)(TB + 1), stream));
         CUDA_TRY(cudaMemcpyAsync(cursors, bucket_start, (size_t)(TB + 1) * 4, cudaMemcpyDeviceToDevice, stream));
         k_digits<true><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, cursors, sorted);
-        k_items_per_bucket<<<(TB + 255) / 256, 256, 0, stream>>>(hist, items, TB, plan.cap);
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(TB + 1), stream));
         delete sort_scope;
-        const unsigned agrid = (unsigned)((max_items + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
-        {
+        count_launch(4);
+        if (levels == 0) {
+            k_items_per_bucket<<<(TB + 255) / 256, 256, 0, stream>>>(hist, items, TB, plan.cap);
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(TB + 1), stream));
+            count_launch(3);
+            const unsigned agrid = (unsigned)((max_items + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
             ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
             k_bucket_accumulate<<<agrid, MSM_ACC_THREADS, 0, stream>>>((const uint8_t*)d_points, stride, sorted, bucket_start, item_start, TB, plan.cap, partial);
+        } else {
+            ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
+            k_densify_bases<<<(unsigned)((npoints + 255) / 256), 256, 0, stream>>>((const uint8_t*)d_points, stride, npoints, dense_bases);
+            count_launch();
+            const uint32_t* off_in = bucket_start;
+            uint32_t* off_bufs[2] = {off_a, off_b};
+            uint32_t* dense_bufs[2] = {dense_a, dense_b};
+            const uint32_t* dense_in = nullptr;
+            size_t bound = max_entries;                                  // upper bound on the level's input count
+            for (int l = 0; l < levels; l++) {
+                uint32_t* off_out = off_bufs[l & 1];
+                uint32_t* dense_out = dense_bufs[l & 1];
+                k_halve_counts<<<(TB + 256) / 256, 256, 0, stream>>>(off_in, cursors, TB);
+                CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cursors, off_out, (int)(TB + 1), stream));
+                bound = bound / 2 + TB;                                  // Σ ceil(cnt/2) ≤ Σ cnt/2 + #buckets
+                size_t T = bound / pair_threads;
+                if (T < 64) T = 64;
+                if (T > 1024) T = 1024;
+                const size_t nthreads = (bound + T - 1) / T;
+                const unsigned lgrid = (unsigned)((nthreads + 127) / 128);
+                if (l == 0)
+                    k_pair_level<true><<<lgrid, 128, 0, stream>>>(dense_bases, sorted, nullptr, off_in, off_out, TB, (uint32_t)T, prefix, dense_out);
+                else
+                    k_pair_level<false><<<lgrid, 128, 0, stream>>>(nullptr, nullptr, dense_in, off_in, off_out, TB, (uint32_t)T, prefix, dense_out);
+                count_launch(4);
+                off_in = off_out;
+                dense_in = dense_out;
+            }
+            k_items_from_offsets<<<(TB + 256) / 256, 256, 0, stream>>>(off_in, items, TB, plan.cap);
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(TB + 1), stream));
+            const size_t max_items_dense = (size_t)TB + bound / plan.cap + 1;
+            const unsigned agrid = (unsigned)((max_items_dense + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
+            k_bucket_accumulate_dense<<<agrid, MSM_ACC_THREADS, 0, stream>>>(dense_in, off_in, item_start, TB, plan.cap, partial);
+            count_launch(4);
         }
         ProfScope red_scope(PROF_MSM_REDUCE, stream);
         const uint32_t nthreads = chunks_per_window * (uint32_t)plan.nwin;
         k_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, stream>>>(partial, item_start, plan.nbuckets, chunk, chunks_per_window, (uint32_t)plan.nwin, red_a);
-        count_launch(7);
+        count_launch(1);
         // tree over the per-chunk sums: groups of 32 until one point per window remains
         uint32_t per_row = chunks_per_window;
         const uint32_t* src = red_a;
@@ -306,6 +533,8 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
 done:
     cudaFreeAsync(hist, stream); cudaFreeAsync(bucket_start, stream); cudaFreeAsync(cursors, stream);
     cudaFreeAsync(items, stream); cudaFreeAsync(item_start, stream); cudaFreeAsync(sorted, stream);
+    cudaFreeAsync(off_a, stream); cudaFreeAsync(off_b, stream); cudaFreeAsync(dense_a, stream); cudaFreeAsync(dense_b, stream);
+    cudaFreeAsync(prefix, stream); cudaFreeAsync(dense_bases, stream);
     cudaFreeAsync(partial, stream); cudaFreeAsync(red_a, stream); cudaFreeAsync(red_b, stream); cudaFreeAsync(cub_tmp, stream);
     return rc;
 }

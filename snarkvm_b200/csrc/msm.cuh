@@ -26,6 +26,7 @@ struct MsmPlan {
     int nwin;           // number of windows = 253 / c + 1 (room for the signed-digit carry)
     uint32_t nbuckets;  // 2^(c-1) buckets per window (bucket value 1 .. 2^(c-1))
     uint32_t cap;       // max points per work item
+    int levels;         // batched-affine pair levels run before the XYZZ accumulation (0 = gather + XYZZ only)
 };
 
 MsmPlan msm_make_plan(size_t npoints);
