@@ -155,14 +155,20 @@ def run_reference(args, rank, world):
         return
     from oracle import cpu
     cpu.build()
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it may run on (rayon's default)
+    try:
+        cpu.set_num_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        cpu.set_num_threads(os.cpu_count() or 1)
     lg = args.ref_lg
     bases = cpu_bases(1 << lg)
     threads = cpu.num_threads()
     for _ in range(args.warmup):
         cpu_msm_points_per_s(min(lg, 16), bases)
+    scal = random_scalars(1 << lg, 777)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu.msm(bases, random_scalars(1 << lg, 777), cpu.BATCHED)
+        cpu.msm(bases, scal, cpu.BATCHED)
     dt = (time.perf_counter() - t0) / args.steps
     value = (1 << lg) / dt
     ntt_v, ntt_dt = cpu_ntt_elements_per_s(args.ref_ntt_lg)
@@ -317,6 +323,24 @@ def run_product(args, rank, world, local_rank):
                          "note": "per pass: 64 B/element algorithmic; a transform is %d passes" % (pass_n // reps)},
         }
 
+    # ---- BASELINE config 4: KZG10 commit core at 2^22 coefficients (Montgomery → canonical → MSM), operands resident ----
+    kzg = None
+    if not args.skip_kzg:
+        nk = 1 << args.kzg_lg
+        coeffs = torch.from_numpy(random_scalars(nk, 4242 + rank).view(np.int64)).to(dev)
+        powers = bases[:nk] if nk <= n else device.generate_bases(nk, seed=0xB200 + rank, device=dev)
+        for _ in range(3):
+            device.kzg_commit(powers, coeffs)
+        barrier()
+        e0.record()
+        for _ in range(5):
+            device.kzg_commit(powers, coeffs)
+        e1.record()
+        barrier()
+        kzg_ms = max_over_ranks(e0.elapsed_time(e1)) / 5
+        kzg = {"metric": "kzg10_commit_coefficients_per_sec", "value": nk * world / (kzg_ms * 1e-3), "unit": "coefficients/s",
+               "ms_per_commit": kzg_ms, "workload": f"2^{args.kzg_lg}-coefficient polynomial, powers resident in HBM, per GPU"}
+
     if rank != 0:
         return
 
@@ -325,6 +349,10 @@ def run_product(args, rank, world, local_rank):
     if world == 1 and not args.skip_cpu:
         from oracle import cpu
         cpu.build()
+        try:
+            cpu.set_num_threads(len(os.sched_getaffinity(0)))
+        except AttributeError:
+            cpu.set_num_threads(os.cpu_count() or 1)
         lg_s = args.cpu_lg
         hb = b_np[: 1 << lg_s]
         v, dt = cpu_msm_points_per_s(lg_s, hb)
@@ -358,6 +386,7 @@ def run_product(args, rank, world, local_rank):
                      "note": "algorithmic 128 B/point; the kernel is bound by the INT32 IMAD pipe (377-bit Montgomery), not HBM"},
         "cpu_baseline": cpu_baseline,
         "ntt": ntt,
+        "kzg_commit": kzg,
     }
     print(json.dumps(line), flush=True)
 
@@ -375,6 +404,8 @@ def main():
     ap.add_argument("--cpu-ntt-lg", type=int, default=22)
     ap.add_argument("--ref-lg", type=int, default=20, help="--impl reference: points per step")
     ap.add_argument("--ref-ntt-lg", type=int, default=22)
+    ap.add_argument("--kzg-lg", type=int, default=22)
+    ap.add_argument("--skip-kzg", action="store_true")
     ap.add_argument("--skip-ntt", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()

@@ -53,9 +53,9 @@ typedef struct {
 
 /* Replaces `snarkvm_ntt` (lib.rs:43-49 ; snarkvm_api.cu:53-62 ; called from
  * algorithms/src/fft/domain.rs:375-388, 404-417, 425-438).  In-place transform of 2^lg_domain_size
- * Fr elements in HOST memory.  Only NN order is implemented (the only order any reference caller
- * passes); other orders return cudaErrorNotSupported, which makes the Rust caller fall back to CPU.
- * On failure `inout` is left untouched. */
+ * Fr elements in HOST memory.  NN (the only order any reference caller passes) is native; NR / RN / RR
+ * add explicit bit-reversal passes (R = bit-reversed index order on that side).  On failure `inout` is
+ * left untouched and a non-zero cudaError_t is returned, which makes the Rust caller fall back to CPU. */
 SNARKVM_API snarkvm_error_t snarkvm_ntt(void* inout, uint32_t lg_domain_size, snarkvm_ntt_order_t ntt_order,
                             snarkvm_ntt_direction_t ntt_direction, snarkvm_ntt_type_t ntt_type);
 
@@ -82,7 +82,7 @@ SNARKVM_API const char* snarkvm_b200_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 SNARKVM_API uint64_t snarkvm_b200_launch_count(void);
 
-/* In-place NN transform of 2^lg Fr elements resident in HBM.  d_scratch: 2^lg elements or NULL. */
+/* In-place transform of 2^lg Fr elements resident in HBM (any of the four orders).  d_scratch: 2^lg elements or NULL. */
 SNARKVM_API int snarkvm_b200_ntt_device(void* d_inout, uint32_t lg, int ntt_order, int ntt_direction, int ntt_type,
                             void* d_scratch, void* stream);
 

@@ -79,6 +79,17 @@ int msm_device_impl(void* out144, const void* d_points, size_t npoints, const vo
     return 0;
 }
 
+// NN is native (bit reversal fused into the last pass); the other orders add explicit derange passes:
+// R-input ⇒ permute before, R-output ⇒ permute after.
+int ntt_ordered(void* d, uint32_t lg, int order, int dir, int type, void* scratch, cudaStream_t stream) {
+    if (order < 0 || order > 3) return (int)cudaErrorInvalidValue;
+    int rc = 0;
+    if (order == SNARKVM_NTT_RN || order == SNARKVM_NTT_RR) rc = fr_bitrev_device(d, lg, stream);
+    if (rc == 0) rc = ntt_device(d, lg, dir, type, scratch, stream);
+    if (rc == 0 && (order == SNARKVM_NTT_NR || order == SNARKVM_NTT_RR)) rc = fr_bitrev_device(d, lg, stream);
+    return rc;
+}
+
 int polymul_device_impl(void* d_out, size_t pcount, const void* const* d_polys, const size_t* plens, size_t ecount,
                         const void* const* d_evals, const size_t* elens, uint32_t lg, cudaStream_t stream) {
     ensure_pool_configured();
@@ -123,8 +134,7 @@ uint64_t snarkvm_b200_launch_count(void) { return launch_count(); }
 // ----------------------------------------------------------------------------------------
 snarkvm_error_t snarkvm_ntt(void* inout, uint32_t lg, snarkvm_ntt_order_t order, snarkvm_ntt_direction_t dir,
                             snarkvm_ntt_type_t type) {
-    if (order != SNARKVM_NTT_NN) return make_error((int)cudaErrorNotSupported);
-    if (lg > NTT_MAX_LG || !inout) return make_error((int)cudaErrorInvalidValue);
+    if (lg > NTT_MAX_LG || !inout || (int)order < 0 || (int)order > 3) return make_error((int)cudaErrorInvalidValue);
     cudaStream_t stream;
     int rc = thread_stream(&stream);
     if (rc) return make_error(rc);
@@ -133,7 +143,7 @@ snarkvm_error_t snarkvm_ntt(void* inout, uint32_t lg, snarkvm_ntt_order_t order,
     rc = (int)cudaMallocAsync(&d, bytes, stream);
     if (rc == 0) rc = (int)cudaMallocAsync(&scratch, bytes, stream);
     if (rc == 0) rc = (int)cudaMemcpyAsync(d, inout, bytes, cudaMemcpyHostToDevice, stream);
-    if (rc == 0) rc = ntt_device(d, lg, (int)dir, (int)type, scratch, stream);
+    if (rc == 0) rc = ntt_ordered(d, lg, (int)order, (int)dir, (int)type, scratch, stream);
     if (rc == 0) rc = (int)cudaStreamSynchronize(stream);          // only copy back on success (snarkvm.cu:178-183)
     if (rc == 0) rc = (int)cudaMemcpyAsync(inout, d, bytes, cudaMemcpyDeviceToHost, stream);
     if (d) cudaFreeAsync(d, stream);
@@ -205,8 +215,8 @@ snarkvm_error_t snarkvm_msm(void* out, const void* points, size_t npoints, const
 // PART 2 — extended device-resident API
 // ----------------------------------------------------------------------------------------
 int snarkvm_b200_ntt_device(void* d_inout, uint32_t lg, int order, int dir, int type, void* d_scratch, void* stream) {
-    if (order != SNARKVM_NTT_NN) return (int)cudaErrorNotSupported;
-    return ntt_device(d_inout, lg, dir, type, d_scratch, (cudaStream_t)stream);
+    if (lg > NTT_MAX_LG) return (int)cudaErrorInvalidValue;
+    return ntt_ordered(d_inout, lg, order, dir, type, d_scratch, (cudaStream_t)stream);
 }
 
 int snarkvm_b200_polymul_device(void* d_out, size_t pcount, const void* const* d_polys, const size_t* plens, size_t ecount,

@@ -358,6 +358,29 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, MSM_ACC_MINBLOCKS) k_bucket_a
     acc.store(partial + (size_t)t * XYZZ_WORDS);
 }
 
+// Hot buckets (all scalars equal; or the top signed-digit window, which holds only the carry and therefore
+// puts ~n/2 points into ONE bucket) produce thousands of item partials for one bucket.  They are folded
+// 32 at a time by as many threads as there are groups, pass after pass, until every bucket has one partial.
+__global__ void k_group_counts(const uint32_t* __restrict__ start_in, uint32_t* __restrict__ cnt_out, uint32_t total_buckets) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total_buckets) cnt_out[i] = (start_in[i + 1] - start_in[i] + 31u) >> 5;
+    else if (i == total_buckets) cnt_out[i] = 0;
+}
+__global__ void __launch_bounds__(128) k_partial_group_sum(const uint32_t* __restrict__ partial_in, const uint32_t* __restrict__ start_in,
+                                                            const uint32_t* __restrict__ start_out, uint32_t total_buckets,
+                                                            uint32_t* __restrict__ partial_out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= start_out[total_buckets]) return;
+    uint32_t lo = 0, hi = total_buckets;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (start_out[mid] <= t) lo = mid; else hi = mid; }
+    uint32_t g = t - start_out[lo];
+    uint32_t i0 = start_in[lo] + g * 32u, i1 = start_in[lo + 1];
+    if (i0 + 32u < i1) i1 = i0 + 32u;
+    XYZZ s = XYZZ::load(partial_in + (size_t)i0 * XYZZ_WORDS);
+    for (uint32_t i = i0 + 1; i < i1; i++) s.add(XYZZ::load(partial_in + (size_t)i * XYZZ_WORDS));
+    s.store(partial_out + (size_t)t * XYZZ_WORDS);
+}
+
 // Σ of a bucket's item partials
 FF_DEV XYZZ bucket_sum(const uint32_t* __restrict__ partial, const uint32_t* __restrict__ item_start, uint32_t wb) {
     uint32_t i0 = item_start[wb], i1 = item_start[wb + 1];
@@ -427,6 +450,8 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
     uint32_t *hist = nullptr, *bucket_start = nullptr, *cursors = nullptr, *items = nullptr, *item_start = nullptr;
     uint32_t *sorted = nullptr, *partial = nullptr, *red_a = nullptr, *red_b = nullptr;
     uint32_t *off_a = nullptr, *off_b = nullptr, *dense_a = nullptr, *dense_b = nullptr, *prefix = nullptr, *dense_bases = nullptr;
+    uint32_t *partial2 = nullptr, *items2 = nullptr, *final_partial = nullptr, *final_start = nullptr;
+    size_t items_bound = 1;                      // upper bound on the item count of a single bucket
     const int levels = plan.levels;
     const size_t dense_cap_a = max_entries / 2 + TB + 1, dense_cap_b = max_entries / 4 + 2 * (size_t)TB + 1;
     size_t pair_threads = 65536;                 // target thread count of a pair level (T = outputs / this, clamped to 64…1024)
@@ -443,6 +468,8 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
     CUDA_TRY(cudaMallocAsync(&item_start, (size_t)(TB + 1) * 4, stream));
     CUDA_TRY(cudaMallocAsync(&sorted, max_entries * 4, stream));
     CUDA_TRY(cudaMallocAsync(&partial, max_items * XYZZ_WORDS * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&partial2, ((size_t)TB + max_items / 32 + 2) * XYZZ_WORDS * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&items2, (size_t)(TB + 1) * 4, stream));
     if (levels > 0) {
         CUDA_TRY(cudaMallocAsync(&off_a, (size_t)(TB + 1) * 4, stream));
         CUDA_TRY(cudaMallocAsync(&off_b, (size_t)(TB + 1) * 4, stream));
@@ -472,6 +499,7 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(TB + 1), stream));
             count_launch(3);
             const unsigned agrid = (unsigned)((max_items + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
+            items_bound = npoints / plan.cap + 1;                       // a bucket belongs to one window: ≤ n entries
             ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
             k_bucket_accumulate<<<agrid, MSM_ACC_THREADS, 0, stream>>>((const uint8_t*)d_points, stride, sorted, bucket_start, item_start, TB, plan.cap, partial);
         } else {
@@ -505,13 +533,31 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
             k_items_from_offsets<<<(TB + 256) / 256, 256, 0, stream>>>(off_in, items, TB, plan.cap);
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(TB + 1), stream));
             const size_t max_items_dense = (size_t)TB + bound / plan.cap + 1;
+            items_bound = ((npoints >> levels) + 1) / plan.cap + 1;
             const unsigned agrid = (unsigned)((max_items_dense + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
             k_bucket_accumulate_dense<<<agrid, MSM_ACC_THREADS, 0, stream>>>(dense_in, off_in, item_start, TB, plan.cap, partial);
             count_launch(4);
         }
         ProfScope red_scope(PROF_MSM_REDUCE, stream);
+        {
+            // fold item partials 32:1 until no bucket can hold more than one (worst case: all entries in one bucket)
+            size_t worst = items_bound;
+            uint32_t* p_in = partial; uint32_t* p_out = partial2;
+            uint32_t* st_in = item_start; uint32_t* st_out = items2;
+            while (worst > 1) {
+                k_group_counts<<<(TB + 256) / 256, 256, 0, stream>>>(st_in, cursors, TB);
+                CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cursors, st_out, (int)(TB + 1), stream));
+                const size_t out_bound = (size_t)TB + (worst + 31) / 32;
+                k_partial_group_sum<<<(unsigned)((out_bound + 127) / 128), 128, 0, stream>>>(p_in, st_in, st_out, TB, p_out);
+                count_launch(4);
+                worst = (worst + 31) / 32;
+                uint32_t* t1 = p_in; p_in = p_out; p_out = t1;
+                uint32_t* t2 = st_in; st_in = st_out; st_out = t2;
+            }
+            final_partial = p_in; final_start = st_in;
+        }
         const uint32_t nthreads = chunks_per_window * (uint32_t)plan.nwin;
-        k_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, stream>>>(partial, item_start, plan.nbuckets, chunk, chunks_per_window, (uint32_t)plan.nwin, red_a);
+        k_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, stream>>>(final_partial, final_start, plan.nbuckets, chunk, chunks_per_window, (uint32_t)plan.nwin, red_a);
         count_launch(1);
         // tree over the per-chunk sums: groups of 32 until one point per window remains
         uint32_t per_row = chunks_per_window;
@@ -535,6 +581,7 @@ done:
     cudaFreeAsync(items, stream); cudaFreeAsync(item_start, stream); cudaFreeAsync(sorted, stream);
     cudaFreeAsync(off_a, stream); cudaFreeAsync(off_b, stream); cudaFreeAsync(dense_a, stream); cudaFreeAsync(dense_b, stream);
     cudaFreeAsync(prefix, stream); cudaFreeAsync(dense_bases, stream);
+    cudaFreeAsync(partial2, stream); cudaFreeAsync(items2, stream);
     cudaFreeAsync(partial, stream); cudaFreeAsync(red_a, stream); cudaFreeAsync(red_b, stream); cudaFreeAsync(cub_tmp, stream);
     return rc;
 }

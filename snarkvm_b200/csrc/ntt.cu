@@ -221,6 +221,21 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
     }
 }
 
+// derange (domain.rs:789-804) as a stand-alone pass: used only for the NR / RN / RR orders of the FFI, which no
+// reference caller requests (they all pass NN, where the permutation is fused into the last NTT pass).
+__global__ void k_bitrev_inplace(Fr* x, uint32_t lg) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >> lg) return;
+    size_t r = lg ? (size_t)(__brevll((unsigned long long)i) >> (64 - lg)) : 0;
+    if (i < r) { Fr a = Fr::load(x + i), b = Fr::load(x + r); b.store(x + i); a.store(x + r); }
+}
+int fr_bitrev_device(void* d_x, uint32_t lg, cudaStream_t stream) {
+    size_t n = (size_t)1 << lg;
+    k_bitrev_inplace<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((Fr*)d_x, lg);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 __global__ void k_pointwise_mul(Fr* acc, const Fr* __restrict__ x, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) (Fr::load(acc + i) * Fr::load(x + i)).store(acc + i);

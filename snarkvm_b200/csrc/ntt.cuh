@@ -26,6 +26,9 @@ enum NttType { NTT_STANDARD = 0, NTT_COSET = 1 };
 // is taken from the stream-ordered pool).  Returns cudaError_t as int.
 int ntt_device(void* d_inout, uint32_t lg, int direction, int type, void* d_scratch, cudaStream_t stream);
 
+// in-place bit-reversal permutation of 2^lg Fr elements (NR / RN / RR orders)
+int fr_bitrev_device(void* d_x, uint32_t lg, cudaStream_t stream);
+
 // d_acc[i] *= d_x[i]
 int fr_pointwise_mul_device(void* d_acc, const void* d_x, size_t n, cudaStream_t stream);
 

@@ -133,3 +133,29 @@ def test_fr_mont_conversions(oracle_cpu):
     x = random_fr_mont(5000, seed=77)
     assert (_host(device.fr_from_mont(_dev(x))) == oracle_cpu.fr_from_mont(x)).all()
     assert (_host(device.fr_to_mont(_dev(x))) == oracle_cpu.fr_to_mont(x)).all()
+
+
+def _bitrev_perm(n):
+    lg = n.bit_length() - 1
+    idx = np.arange(n, dtype=np.uint64)
+    rev = np.zeros(n, dtype=np.uint64)
+    for b in range(lg):
+        rev |= ((idx >> np.uint64(b)) & np.uint64(1)) << np.uint64(lg - 1 - b)
+    return rev.astype(np.int64)
+
+
+@pytest.mark.parametrize("lg", [3, 10, 13])
+def test_ntt_input_output_orders(oracle_cpu, lg):
+    """NR / RN / RR of the FFI enum (lib.rs:22-28): R = bit-reversed index order on that side."""
+    from snarkvm_b200 import cuda
+    n = 1 << lg
+    x = random_fr_mont(n, seed=900 + lg)
+    perm = _bitrev_perm(n)
+    for d, t in MODES:
+        want = oracle_cpu.ntt(x, d, t)
+        got = x.copy(); cuda.NTT(n, got, cuda.NTTInputOutputOrder.NR, cuda.NTTDirection(d), cuda.NTTType(t))
+        assert (got == want[perm]).all()
+        got = np.ascontiguousarray(x[perm]); cuda.NTT(n, got, cuda.NTTInputOutputOrder.RN, cuda.NTTDirection(d), cuda.NTTType(t))
+        assert (got == want).all()
+        got = np.ascontiguousarray(x[perm]); cuda.NTT(n, got, cuda.NTTInputOutputOrder.RR, cuda.NTTDirection(d), cuda.NTTType(t))
+        assert (got == want[perm]).all()
