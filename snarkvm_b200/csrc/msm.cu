@@ -75,8 +75,9 @@ static int ceil_log2(size_t x) { int l = 0; size_t v = x > 1 ? x - 1 : 0; while 
 MsmPlan msm_make_plan(size_t npoints) {
     MsmPlan p;
     int lg = ceil_log2(npoints < 2 ? 2 : npoints);
-    // Work model (Fq mults): n·W·10 for the mixed adds + W·2^(c-1)·~30 for the bucket reduction.
-    int c = lg <= 8 ? 4 : lg <= 12 ? lg - 4 : lg <= 16 ? lg - 3 : lg <= 20 ? 14 : lg <= 22 ? 15 : 16;
+    // Window bits from a sweep on B200 (tools/tune_msm.py, profiles/tune_msm_r1.log): wider windows mean fewer
+    // bucket additions (n·W) but more buckets to reduce and shorter, more divergent bucket runs.
+    int c = lg <= 8 ? 4 : lg <= 12 ? lg - 4 : lg <= 18 ? 11 : lg <= 20 ? 16 : 17;
     if (const char* e = getenv("SNARKVM_B200_MSM_C")) { int v = atoi(e); if (v >= 2 && v <= 24) c = v; }
     p.c = c;
     p.nwin = 253 / c + 1;
@@ -88,11 +89,10 @@ MsmPlan msm_make_plan(size_t npoints) {
     if (cap < 16) cap = 16;
     if (const char* e = getenv("SNARKVM_B200_MSM_CAP")) { long v = atol(e); if (v >= 1) cap = (size_t)v; }
     p.cap = (uint32_t)cap;
-    // Batched-affine pair levels before the XYZZ accumulation: halve buckets while they still hold ≥ ~16 points
-    // on average and the dense scratch (≈ 0.9 · n · W · 96 B) fits the budget.
-    size_t avg = npoints >> (c - 1);
-    int levels = 0;
-    while ((avg >> levels) >= 16 && levels < 8) levels++;
+    // Batched-affine pair levels before the XYZZ accumulation pay off only when every level still fills the
+    // GPU (same sweep): none up to 2^20 points, 2 at 2^21–2^22, 3 from 2^23, if the dense scratch fits.
+    int levels = lg >= 23 ? 3 : lg >= 21 ? 2 : 0;
+    while (levels > 0 && ((npoints >> (c - 1)) >> levels) < 2) levels--;
     size_t scratch = total * 96 / 2 + total * 48 / 2 + total * 96 / 4 + npoints * 128;
     size_t budget = (size_t)64 << 30;
     if (const char* e = getenv("SNARKVM_B200_MSM_SCRATCH_GB")) { long v = atol(e); if (v >= 1) budget = (size_t)v << 30; }

@@ -224,3 +224,32 @@ def _add_mod_r(a, b):
         borrow = (b1 | b2).astype(np.uint64)
     out[sel] = sub[sel]
     return out
+
+
+@pytest.mark.parametrize("levels,c", [(1, 6), (2, 7), (4, 5), (6, 4)])
+def test_msm_pair_levels_edge_cases(oracle_cpu, bases64k, monkeypatch, levels, c):
+    """The batched-affine pair levels (normally enabled only from 2^21 points) forced on small inputs so that
+    their special cases run: equal points (doubling through 2·y), opposite points (cancellation to ∞), ∞ inputs,
+    odd bucket sizes, hot buckets (all scalars equal) and repeated bases."""
+    from snarkvm_b200.algorithms import VariableBase
+    monkeypatch.setenv("SNARKVM_B200_MSM_LEVELS", str(levels))
+    monkeypatch.setenv("SNARKVM_B200_MSM_C", str(c))
+    n = 3000
+    bases = bases64k[:n].copy()
+    scal = random_canonical_fr(n, seed=40 + levels)
+    scal[0:16] = 0
+    scal[16:32] = scalars_from_ints([1])[0]
+    scal[32:48] = scalars_from_ints([py.R_MOD - 1])[0]
+    bases[48:64, 96] = 1
+    bases[100:301] = bases[400]; scal[100:301] = scal[400]            # 202 copies of one (point, scalar): doublings at every level
+    neg = affine_array([py.g1_neg(py.affine_from_bytes(bases[500].tobytes()))])[0]
+    bases[501:521:2] = neg; bases[502:522:2] = bases[500]; scal[500:522] = scal[500]   # P, −P, P, −P … in the same buckets
+    want = oracle_cpu.msm(bases, scal, 1)
+    assert (VariableBase.msm(bases, scal) == want).all()
+    same = np.tile(scal[700:701], (n, 1))                             # every window has one hot bucket
+    assert (VariableBase.msm(bases, same) == oracle_cpu.msm(bases, same, 1)).all()
+    rep = np.tile(bases64k[:8], (n // 8, 1))                           # 8 distinct bases repeated
+    assert (VariableBase.msm(rep, scal) == oracle_cpu.msm(rep, scal, 1)).all()
+    assert (VariableBase.msm(rep, same) == oracle_cpu.msm(rep, same, 1)).all()
+    inf = np.frombuffer(py.projective_bytes_normalised(None), dtype=np.uint64)
+    assert (VariableBase.msm(bases, np.zeros((n, 4), dtype=np.uint64)) == inf).all()
