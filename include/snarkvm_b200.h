@@ -115,6 +115,13 @@ SNARKVM_API int snarkvm_b200_kzg_commit_device(void* out144, const void* d_power
 SNARKVM_API int snarkvm_b200_fr_from_mont_device(void* d_out, const void* d_in, size_t n, void* stream);
 SNARKVM_API int snarkvm_b200_fr_to_mont_device(void* d_out, const void* d_in, size_t n, void* stream);
 
+/* Resident bases for the drop-in snarkvm_msm: upload `host_points` (npoints x stride bytes) to the current device once;
+ * later snarkvm_msm calls whose `points_with_infinity` is this same pointer (same stride, npoints <= registered) skip the
+ * upload.  The SRS powers of a proving key are constant (polycommit/sonic_pc/data_structures.rs:41-63) and the reference
+ * passes the same slice to every commitment.  The caller must not mutate the slice while it is registered. */
+SNARKVM_API int snarkvm_b200_register_bases(const void* host_points, size_t npoints, size_t stride);
+SNARKVM_API int snarkvm_b200_unregister_bases(const void* host_points);
+
 /* Per-kernel CUDA-event timing on the launching stream (off by default).  kind: 0 = MSM bucket sort
  * (digit histogram + scatter), 1 = MSM bucket accumulation, 2 = MSM bucket reduction, 3 = NTT passes.
  * collect() waits for the recorded launches of that kind, returns their summed milliseconds and count, and

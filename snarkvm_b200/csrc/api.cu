@@ -6,6 +6,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -52,6 +53,23 @@ int thread_stream(cudaStream_t* out) {
     }
     *out = t_ctx.stream[dev];
     return 0;
+}
+
+// Registered (resident) bases: the SRS powers of a proving key are constant, and the reference re-passes the same
+// host slice on every commitment (kzg10/mod.rs:119,149).  A caller may register that slice once; snarkvm_msm then
+// recognises the pointer and skips the 104 B/point upload.  Opt-in: the caller promises not to mutate the slice.
+struct ResidentBases { void* d_ptr; size_t npoints; size_t stride; int device; };
+std::mutex g_bases_mu;
+std::map<const void*, ResidentBases> g_bases;
+
+bool find_resident(const void* host, size_t npoints, size_t stride, ResidentBases* out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> lock(g_bases_mu);
+    auto it = g_bases.find(host);
+    if (it == g_bases.end() || it->second.device != dev || it->second.stride != stride || it->second.npoints < npoints) return false;
+    *out = it->second;
+    return true;
 }
 
 void write_infinity(void* out144) {
@@ -198,12 +216,14 @@ snarkvm_error_t snarkvm_msm(void* out, const void* points, size_t npoints, const
     int rc = thread_stream(&stream);
     if (rc) return make_error(rc);
     void *d_points = nullptr, *d_scalars = nullptr;
-    rc = (int)cudaMallocAsync(&d_points, npoints * ffi_affine_sz, stream);
+    ResidentBases rb;
+    const bool resident = find_resident(points, npoints, ffi_affine_sz, &rb);
+    if (!resident) rc = (int)cudaMallocAsync(&d_points, npoints * ffi_affine_sz, stream);
     if (rc == 0) rc = (int)cudaMallocAsync(&d_scalars, npoints * 32, stream);
     if (rc == 0) rc = (int)cudaMemcpyAsync(d_scalars, scalars, npoints * 32, cudaMemcpyHostToDevice, stream);
-    if (rc == 0) rc = (int)cudaMemcpyAsync(d_points, points, npoints * ffi_affine_sz, cudaMemcpyHostToDevice, stream);
+    if (rc == 0 && !resident) rc = (int)cudaMemcpyAsync(d_points, points, npoints * ffi_affine_sz, cudaMemcpyHostToDevice, stream);
     uint64_t result[18];
-    if (rc == 0) rc = msm_device_impl(result, d_points, npoints, d_scalars, ffi_affine_sz, stream);
+    if (rc == 0) rc = msm_device_impl(result, resident ? rb.d_ptr : d_points, npoints, d_scalars, ffi_affine_sz, stream);
     if (d_points) cudaFreeAsync(d_points, stream);
     if (d_scalars) cudaFreeAsync(d_scalars, stream);
     int rs = (int)cudaStreamSynchronize(stream);
@@ -278,6 +298,29 @@ int snarkvm_b200_fr_from_mont_device(void* d_out, const void* d_in, size_t n, vo
 }
 int snarkvm_b200_fr_to_mont_device(void* d_out, const void* d_in, size_t n, void* stream) {
     return fr_to_mont_device(d_out, d_in, n, (cudaStream_t)stream);
+}
+
+int snarkvm_b200_register_bases(const void* host_points, size_t npoints, size_t stride) {
+    if (!host_points || npoints == 0 || stride < 104 || (stride & 7)) return (int)cudaErrorInvalidValue;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    void* d = nullptr;
+    if ((e = cudaMalloc(&d, npoints * stride)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemcpy(d, host_points, npoints * stride, cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d); return (int)e; }
+    std::lock_guard<std::mutex> lock(g_bases_mu);
+    auto it = g_bases.find(host_points);
+    if (it != g_bases.end()) { cudaFree(it->second.d_ptr); g_bases.erase(it); }
+    g_bases[host_points] = ResidentBases{d, npoints, stride, dev};
+    return 0;
+}
+int snarkvm_b200_unregister_bases(const void* host_points) {
+    std::lock_guard<std::mutex> lock(g_bases_mu);
+    auto it = g_bases.find(host_points);
+    if (it == g_bases.end()) return (int)cudaErrorInvalidValue;
+    cudaFree(it->second.d_ptr);
+    g_bases.erase(it);
+    return 0;
 }
 
 int snarkvm_b200_profile_enable(int on) { prof_enable(on != 0); return 0; }

@@ -186,21 +186,42 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
     for (int u = 0; u < S; u++) {
         const int t = t0 + u;
         const uint32_t hb = S - 1 - u;               // log2 of the local gap (in rows)
-        for (uint32_t b = tid; b < nbf; b += nthr) {
-            uint32_t c = b & (cols - 1), j = b >> Q;
-            uint32_t r_lo = j & ((1u << hb) - 1u);
-            uint32_t d_lo = ((j >> hb) << (hb + 1)) | r_lo;
-            uint32_t i_lo = (d_lo << Q) | c, i_hi = i_lo + ((1u << hb) << Q);
-            // exponent of ω_n: (index mod gap) · 2^t
-            size_t r = a.last ? (size_t)r_lo : (((size_t)r_lo << L) | low_base | c);
-            size_t ex = r << t;
-            Fr x = sm[i_lo], y = sm[i_hi];
-            Fr sum = x + y, dif = x - y;
-            if (ex != 0) {
-                if (!a.inverse) dif = dif * Fr::load(a.tw + (ex << tw_shift));
-                else dif = (dif * Fr::load(a.tw + ((((size_t)1 << (lg - 1)) - ex) << tw_shift))).neg();
+#ifndef NTT_UNROLL
+#define NTT_UNROLL 1
+#endif
+        // NTT_UNROLL butterflies per thread per trip with all operands requested up front.  Measured on B200 at
+        // 2^24: unroll 1 → 4.15 ms, 2 → 4.95 ms, 4 → 7.36 ms (the extra registers cost more occupancy than the
+        // overlapped latency gains), so the default is 1.
+        for (uint32_t b0 = tid; b0 < nbf; b0 += nthr * NTT_UNROLL) {
+            Fr x[NTT_UNROLL], y[NTT_UNROLL], w[NTT_UNROLL];
+            uint32_t il[NTT_UNROLL], ih[NTT_UNROLL];
+            bool live[NTT_UNROLL], tw[NTT_UNROLL];
+#pragma unroll
+            for (int k = 0; k < NTT_UNROLL; k++) {
+                const uint32_t b = b0 + k * nthr;
+                live[k] = b < nbf;
+                tw[k] = false;
+                if (!live[k]) continue;
+                uint32_t c = b & (cols - 1), j = b >> Q;
+                uint32_t r_lo = j & ((1u << hb) - 1u);
+                uint32_t d_lo = ((j >> hb) << (hb + 1)) | r_lo;
+                il[k] = (d_lo << Q) | c; ih[k] = il[k] + ((1u << hb) << Q);
+                // exponent of ω_n: (index mod gap) · 2^t
+                size_t r = a.last ? (size_t)r_lo : (((size_t)r_lo << L) | low_base | c);
+                size_t ex = r << t;
+                x[k] = sm[il[k]]; y[k] = sm[ih[k]];
+                if (ex != 0) {
+                    tw[k] = true;
+                    w[k] = Fr::load(a.tw + ((a.inverse ? (((size_t)1 << (lg - 1)) - ex) : ex) << tw_shift));
+                }
             }
-            sm[i_lo] = sum; sm[i_hi] = dif;
+#pragma unroll
+            for (int k = 0; k < NTT_UNROLL; k++) {
+                if (!live[k]) continue;
+                Fr sum = x[k] + y[k], dif = x[k] - y[k];
+                if (tw[k]) { dif = dif * w[k]; if (a.inverse) dif = dif.neg(); }
+                sm[il[k]] = sum; sm[ih[k]] = dif;
+            }
         }
         __syncthreads();
     }

@@ -87,3 +87,15 @@ def msm(points: np.ndarray, scalars: np.ndarray) -> np.ndarray:
     err = _lib.lib().snarkvm_msm(out.ctypes.data, points.ctypes.data, npoints, scalars.ctypes.data, points.shape[1])
     _lib.check_rust_error(err)
     return out
+
+
+def register_bases(points: np.ndarray) -> None:
+    """Extension: keep `points` resident on the current device; later msm(points, …) calls with this same array skip
+    the upload (the array must stay alive and unmodified until unregister_bases)."""
+    if not (isinstance(points, np.ndarray) and points.dtype == np.uint8 and points.ndim == 2 and points.flags["C_CONTIGUOUS"]):
+        raise TypeError("points must be a C-contiguous uint8 array [n, ffi_affine_sz]")
+    _lib.check(_lib.lib().snarkvm_b200_register_bases(points.ctypes.data, points.shape[0], points.shape[1]))
+
+
+def unregister_bases(points: np.ndarray) -> None:
+    _lib.check(_lib.lib().snarkvm_b200_unregister_bases(points.ctypes.data))

@@ -253,3 +253,21 @@ def test_msm_pair_levels_edge_cases(oracle_cpu, bases64k, monkeypatch, levels, c
     assert (VariableBase.msm(rep, same) == oracle_cpu.msm(rep, same, 1)).all()
     inf = np.frombuffer(py.projective_bytes_normalised(None), dtype=np.uint64)
     assert (VariableBase.msm(bases, np.zeros((n, 4), dtype=np.uint64)) == inf).all()
+
+
+def test_registered_bases(oracle_cpu, bases64k):
+    """snarkvm_b200_register_bases: snarkvm_msm recognises the registered host pointer and skips the upload"""
+    from snarkvm_b200 import CudaError, cuda
+    n = 5000
+    pts = np.ascontiguousarray(bases64k[:n])
+    scal = random_canonical_fr(n, seed=3)
+    want = oracle_cpu.msm(pts, scal, 0)
+    cuda.register_bases(pts)
+    try:
+        assert (cuda.msm(pts, scal) == want).all()
+        assert (cuda.msm(pts, scal[:1234]) == oracle_cpu.msm(pts[:1234], scal[:1234], 0)).all()   # prefix of the registered slice
+    finally:
+        cuda.unregister_bases(pts)
+    assert (cuda.msm(pts, scal) == want).all()                      # falls back to uploading
+    with pytest.raises(CudaError):
+        cuda.unregister_bases(pts)

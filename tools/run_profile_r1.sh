@@ -1,7 +1,10 @@
+# Round-1 measurement script (run under gpurun from the repo root).  Outputs land in gpurun_out/.
 set -x
-timeout 300 python bench.py > gpurun_out/bench_r1a.json 2> gpurun_out/bench_r1a.err; echo rc=$?
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 2 --warmup 3 --skip-cpu --e2e-steps 1 > gpurun_out/ncu_launch_bench.json 2> gpurun_out/ncu_launch.err; echo rc=$?
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_bucket_accumulate -s 1 -c 1 -f -o gpurun_out/prof_msm_acc_r1 python bench.py --steps 1 --skip-cpu --skip-ntt --e2e-steps 1 > /dev/null 2> gpurun_out/ncu_acc.err; echo rc=$?
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ntt_pass -s 3 -c 3 -f -o gpurun_out/prof_ntt_pass_r1 python bench.py --lg 20 --steps 1 --skip-cpu --e2e-steps 1 > /dev/null 2> gpurun_out/ncu_ntt.err; echo rc=$?
-cat gpurun_out/bench_r1a.json
-ls -la gpurun_out
+timeout 400 python bench.py > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; echo rc=$?
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1_reference.json 2> gpurun_out/bench_r1_reference.err; echo rc=$?
+# every launch of the same command with its device time (cold-cache, serialised: compare shares)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 2 --warmup 3 --skip-cpu --e2e-steps 1 > gpurun_out/ncu_launch_bench.json 2> gpurun_out/ncu_launch.err; echo rc=$?
+# the dominant kernels once each with the full set
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_pair_level|k_bucket_accumulate" -s 4 -c 5 -f -o gpurun_out/prof_msm_r1 python bench.py --steps 1 --skip-cpu --skip-ntt --skip-kzg --e2e-steps 1 > /dev/null 2> gpurun_out/ncu_msm.err; echo rc=$?
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ntt_pass -s 3 -c 3 -f -o gpurun_out/prof_ntt_r1 python bench.py --lg 20 --steps 1 --skip-cpu --skip-kzg --e2e-steps 1 > /dev/null 2> gpurun_out/ncu_ntt.err; echo rc=$?
+cat gpurun_out/bench_r1.json
