@@ -454,7 +454,8 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
     size_t items_bound = 1;                      // upper bound on the item count of a single bucket
     const int levels = plan.levels;
     const size_t dense_cap_a = max_entries / 2 + TB + 1, dense_cap_b = max_entries / 4 + 2 * (size_t)TB + 1;
-    size_t pair_threads = 65536;                 // target thread count of a pair level (T = outputs / this, clamped to 64…1024)
+    size_t pair_threads = 131072;                // target thread count of a pair level (T = outputs / this, clamped to 64…1024);
+                                                 // 131072 measured 2 % faster than 65536 and 5 % faster than 262144 at 2^24
     if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_THREADS")) { long v = atol(e); if (v >= 1024) pair_threads = (size_t)v; }
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0;

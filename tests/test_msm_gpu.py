@@ -271,3 +271,36 @@ def test_registered_bases(oracle_cpu, bases64k):
     assert (cuda.msm(pts, scal) == want).all()                      # falls back to uploading
     with pytest.raises(CudaError):
         cuda.unregister_bases(pts)
+
+
+def test_ffi_concurrent_callers(oracle_cpu, bases64k):
+    """The reference enters the FFI from many rayon workers at once (sonic_pc/mod.rs:186-245: all commitments of a
+    round in parallel; ExecutionPool of FFTs).  Eight host threads call snarkvm_msm / snarkvm_ntt concurrently
+    (ctypes releases the GIL); every result must equal the oracle's."""
+    import threading
+    from snarkvm_b200 import cuda
+    from helpers import random_fr_mont
+    jobs, results, errors = [], {}, []
+    for k in range(8):
+        n = 3000 + 517 * k
+        scal = random_canonical_fr(n, seed=200 + k)
+        x = random_fr_mont(1 << (10 + k % 4), seed=300 + k)
+        jobs.append((k, n, scal, x))
+
+    def work(k, n, scal, x):
+        try:
+            for _ in range(3):
+                m = cuda.msm(bases64k[:n], scal)
+                y = x.copy()
+                cuda.NTT(x.shape[0], y, cuda.NTTInputOutputOrder.NN, cuda.NTTDirection.Forward, cuda.NTTType.Coset)
+            results[k] = (m, y)
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=j) for j in jobs]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for k, n, scal, x in jobs:
+        assert (results[k][0] == oracle_cpu.msm(bases64k[:n], scal, 0)).all(), k
+        assert (results[k][1] == oracle_cpu.ntt(x, 0, 1)).all(), k
