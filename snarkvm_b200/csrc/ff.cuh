@@ -199,7 +199,106 @@ struct Fp {
         return mul_inline(a, b);
 #endif
     }
-    FF_DEV Fp sqr() const { return (*this) * (*this); }
+    // Dedicated squaring: N(N−1)/2 cross products (doubled by a 1-bit shift) + N diagonal products instead of N²,
+    // then N Montgomery reduction rows on the 2N-limb square.  Cross products use the same even/odd carry-chain
+    // layout as the multiplier: E holds columns of even position, O (offset by one limb) those of odd position.
+    FF_DEV static Fp sqr_inline(const Fp& a) {
+        uint32_t E[2 * N], O[2 * N];
+#pragma unroll
+        for (int k = 0; k < 2 * N; k++) { E[k] = 0u; O[k] = 0u; }
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) {
+            // products a_i·a_j, j > i: position i+j.  Same parity as i ⇒ even position ⇒ E; else O (index pos−1).
+            {   // j = i+2, i+4, …  (even positions 2i+2, …)
+                bool first = true;
+#pragma unroll
+                for (int j = i + 2; j < N; j += 2) {
+                    const int p = i + j;
+                    if (first) { E[p] = ptx_mad_lo_cc(a.v[i], a.v[j], E[p]); first = false; }
+                    else E[p] = ptx_madc_lo_cc(a.v[i], a.v[j], E[p]);
+                    E[p + 1] = ptx_madc_hi_cc(a.v[i], a.v[j], E[p + 1]);
+                    if (j + 2 >= N) E[p + 2] = ptx_addc(E[p + 2], 0u);       // untouched so far: receives the carry
+                }
+            }
+            {   // j = i+1, i+3, …  (odd positions 2i+1, …) → O[pos−1]
+                bool first = true;
+#pragma unroll
+                for (int j = i + 1; j < N; j += 2) {
+                    const int p = i + j - 1;
+                    if (first) { O[p] = ptx_mad_lo_cc(a.v[i], a.v[j], O[p]); first = false; }
+                    else O[p] = ptx_madc_lo_cc(a.v[i], a.v[j], O[p]);
+                    O[p + 1] = ptx_madc_hi_cc(a.v[i], a.v[j], O[p + 1]);
+                    if (j + 2 >= N) O[p + 2] = ptx_addc(O[p + 2], 0u);
+                }
+            }
+        }
+        // T = E + (O << 32)
+        uint32_t T[2 * N];
+        T[0] = E[0];
+        T[1] = ptx_add_cc(E[1], O[0]);
+#pragma unroll
+        for (int k = 2; k < 2 * N - 1; k++) T[k] = ptx_addc_cc(E[k], O[k - 1]);
+        T[2 * N - 1] = ptx_addc(E[2 * N - 1], O[2 * N - 2]);
+        // T = 2·T (the cross terms appear twice) …
+#pragma unroll
+        for (int k = 2 * N - 1; k > 0; k--) T[k] = __funnelshift_l(T[k - 1], T[k], 1);
+        T[0] <<= 1;
+        // … + Σ a_i²·2^{64 i}
+        T[0] = ptx_mad_lo_cc(a.v[0], a.v[0], T[0]);
+        T[1] = ptx_madc_hi_cc(a.v[0], a.v[0], T[1]);
+#pragma unroll
+        for (int i = 1; i < N; i++) { T[2 * i] = ptx_madc_lo_cc(a.v[i], a.v[i], T[2 * i]); T[2 * i + 1] = ptx_madc_hi_cc(a.v[i], a.v[i], T[2 * i + 1]); }
+        // Montgomery reduction of the 2N-limb square: V = ev + od·2^32 starts as the low half; every step clears
+        // the low limb with m·p, shifts one limb down and lets the next high limb of T in at the top.
+        uint32_t ev[N], od[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) { ev[k] = T[k]; od[k] = 0u; }
+        uint32_t pm[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) pm[k] = P::mod(k);
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const uint32_t m = ev[0] * P::INV32;
+            row_mad<N>(od, &pm[1], m);
+            if (P::MOD0_IS_ONE) {
+                ev[0] = ptx_add_cc(ev[0], m);
+                ev[1] = ptx_addc_cc(ev[1], 0u);
+#pragma unroll
+                for (int j = 2; j < N; j += 2) { ev[j] = ptx_madc_lo_cc(pm[j], m, ev[j]); ev[j + 1] = ptx_madc_hi_cc(pm[j], m, ev[j + 1]); }
+            } else {
+                row_mad<N>(ev, &pm[0], m);
+            }
+            od[N - 1] = ptx_addc(od[N - 1], 0u);
+            // shift one limb: (ev, od) ← (od + ev[1], ev[2..] ‖ T[N+i] ‖ 0) with the carry of the first add rippling up
+            uint32_t nev[N], nod[N];
+            nev[0] = ptx_add_cc(od[0], ev[1]);
+#pragma unroll
+            for (int k = 0; k < N - 2; k++) nod[k] = ptx_addc_cc(ev[k + 2], 0u);
+            nod[N - 2] = ptx_addc_cc(T[N + i], 0u);
+            nod[N - 1] = ptx_addc(0u, 0u);
+#pragma unroll
+            for (int k = 1; k < N; k++) nev[k] = od[k];
+#pragma unroll
+            for (int k = 0; k < N; k++) { ev[k] = nev[k]; od[k] = nod[k]; }
+        }
+        Fp r;
+        r.v[0] = ev[0];
+        r.v[1] = ptx_add_cc(ev[1], od[0]);
+#pragma unroll
+        for (int k = 2; k < N; k++) r.v[k] = ptx_addc_cc(ev[k], od[k - 1]);
+        r.final_sub();
+        return r;
+    }
+    static __device__ __noinline__ Fp sqr_call(Fp a) { return sqr_inline(a); }
+    FF_DEV Fp sqr() const {
+#if defined(FF_NO_SQR)
+        return (*this) * (*this);
+#elif defined(FF_CALL_MUL)
+        return sqr_call(*this);
+#else
+        return sqr_inline(*this);
+#endif
+    }
 
     // a^e for a fixed public exponent given as 32-bit limbs (MSB-first square-and-multiply)
     template <int L>

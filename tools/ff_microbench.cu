@@ -26,6 +26,18 @@ template <int N64> static void host_mont_mul(uint64_t* r, const uint64_t* a, con
     memcpy(r, t, 8 * N64);
 }
 
+template <class F> __global__ void k_sqr_check(const uint32_t* a, uint32_t* out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+    F x = F::load(a + F::N * i);
+    F d = x.sqr() - x * x;
+    d.store(out + F::N * i);
+}
+template <class F> __global__ void k_sqr_chain(const uint32_t* a, uint32_t* out, int iters) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    F x = F::load(a + F::N * (i % 1024));
+    for (int it = 0; it < iters; it++) x = x.sqr();
+    if (x.v[0] == 0x12345678u) x.store(out + F::N * (i % 1024));
+}
 template <class F> __global__ void k_ops(const uint32_t* a, const uint32_t* b, uint32_t* mul, uint32_t* add, uint32_t* sub, uint32_t* inv, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
     F x = F::load(a + F::N * i), y = F::load(b + F::N * i);
@@ -83,7 +95,10 @@ template <class F, class P, int N64> static int check(const char* name, uint64_t
         bool az = true; for (int j = 0; j < N64; j++) az &= a[i * N64 + j] == 0;
         if (!az && memcmp(one, &ri[i * N64], 8 * N64)) { if (bad < 5) printf("%s inverse mismatch at %d\n", name, i); bad++; }
     }
-    printf("%s: %d checks, %d mismatches\n", name, n * 4, bad);
+    k_sqr_check<F><<<n / 128, 128>>>(da, dm, n);
+    cudaMemcpy(rm.data(), dm, bytes, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < n * N64; i++) if (rm[i] != 0) { if (bad < 5) printf("%s sqr mismatch at %d\n", name, i / N64); bad++; break; }
+    printf("%s: %d checks, %d mismatches\n", name, n * 5, bad);
     // throughput
     uint32_t* dout; cudaMalloc(&dout, 1024 * N64 * 8);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -96,7 +111,9 @@ template <class F, class P, int N64> static int check(const char* name, uint64_t
         k_chain<F, 2><<<blocks, tpb>>>(da, dout, 10); cudaDeviceSynchronize();
         cudaEventRecord(e0); k_chain<F, 2><<<blocks, tpb>>>(da, dout, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
         double r2 = (double)blocks * tpb * iters * 2 / (ms * 1e-3);
-        printf("%s mul/s: tpb=%d blocks/SM=%d  ILP1 %.3e  ILP2 %.3e\n", name, tpb, bps, r1, r2);
+        cudaEventRecord(e0); k_sqr_chain<F><<<blocks, tpb>>>(da, dout, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+        double rs = (double)blocks * tpb * iters / (ms * 1e-3);
+        printf("%s mul/s: tpb=%d blocks/SM=%d  ILP1 %.3e  ILP2 %.3e  sqr %.3e\n", name, tpb, bps, r1, r2, rs);
     }
     return bad;
 }
