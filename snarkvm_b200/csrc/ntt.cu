@@ -151,11 +151,25 @@ struct PassArgs {
 FF_DEV Fr coset_factor(const Fr* lo, const Fr* hi, size_t idx) { return lo[idx & 4095] * hi[idx >> 12]; }
 
 __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
+    // Shared memory holds the tile as two planes of 16-byte halves (low limbs of element i at [i], high limbs at
+    // [tile_elems + i]): consecutive threads then touch consecutive 16-byte words — conflict-free LDS/STS.128 — where
+    // the 32-byte array-of-structures layout made every access a 2-way bank conflict (profiles/r1a_ntt_pass_metrics.csv).
     extern __shared__ uint4 smem_raw[];
-    Fr* sm = reinterpret_cast<Fr*>(smem_raw);
+    struct Tile {
+        uint4* p; uint32_t n;
+        __device__ __forceinline__ Fr get(uint32_t i) const {
+            uint4 a = p[i], b = p[n + i]; Fr r;
+            r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+            return r;
+        }
+        __device__ __forceinline__ void put(uint32_t i, const Fr& r) const {
+            p[i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]); p[n + i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+        }
+    };
     const int S = a.S, Q = a.Q, lg = a.lg, t0 = a.t0;
     const int L = lg - t0 - S;                       // low index bits below the tile's row digit
     const uint32_t rows = 1u << S, cols = 1u << Q, tile_elems = rows << Q;
+    const Tile sm{smem_raw, tile_elems};
     const size_t tile = blockIdx.x;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
 
@@ -176,7 +190,7 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
         }
         Fr x = Fr::load(a.in + idx);
         if (a.pre) x = x * coset_factor(a.coset_lo, a.coset_hi, idx);
-        sm[((size_t)d << Q) | c] = x;
+        sm.put((d << Q) | c, x);
     }
     __syncthreads();
 
@@ -209,7 +223,7 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
                 // exponent of ω_n: (index mod gap) · 2^t
                 size_t r = a.last ? (size_t)r_lo : (((size_t)r_lo << L) | low_base | c);
                 size_t ex = r << t;
-                x[k] = sm[il[k]]; y[k] = sm[ih[k]];
+                x[k] = sm.get(il[k]); y[k] = sm.get(ih[k]);
                 if (ex != 0) {
                     tw[k] = true;
                     w[k] = Fr::load(a.tw + ((a.inverse ? (((size_t)1 << (lg - 1)) - ex) : ex) << tw_shift));
@@ -220,7 +234,7 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
                 if (!live[k]) continue;
                 Fr sum = x[k] + y[k], dif = x[k] - y[k];
                 if (tw[k]) { dif = dif * w[k]; if (a.inverse) dif = dif.neg(); }
-                sm[il[k]] = sum; sm[ih[k]] = dif;
+                sm.put(il[k], sum); sm.put(ih[k], dif);
             }
         }
         __syncthreads();
@@ -235,7 +249,7 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
             size_t drev = S ? (size_t)(__brev(d) >> (32 - S)) : 0;
             k = (drev << t0) | (hprime_base + c);
         }
-        Fr x = sm[((size_t)d << Q) | c];
+        Fr x = sm.get((d << Q) | c);
         if (a.post == 1) x = x * (*a.ninv);
         else if (a.post == 2) x = x * coset_factor(a.coset_lo, a.coset_hi, k);
         x.store(a.out + k);
