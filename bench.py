@@ -390,7 +390,7 @@ def run_product(args, rank, world, local_rank):
                                    "sample": f"one 2^{args.cpu_ntt_lg} forward fft_in_place ({ndt:.2f} s), best team size of 16/32/64/all"}
 
     plan = device.msm_plan(n)
-    plan_levels = 3 if args.lg >= 23 else 2 if args.lg >= 21 else 0      # msm_make_plan (csrc/msm.cu)
+    plan_levels = 4 if args.lg >= 23 else 2 if args.lg >= 21 else 0      # msm_make_plan (csrc/msm.cu)
     line = {
         "metric": "bls12_377_g1_msm_points_per_sec", "value": value, "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

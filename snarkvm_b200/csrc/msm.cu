@@ -90,8 +90,8 @@ MsmPlan msm_make_plan(size_t npoints) {
     if (const char* e = getenv("SNARKVM_B200_MSM_CAP")) { long v = atol(e); if (v >= 1) cap = (size_t)v; }
     p.cap = (uint32_t)cap;
     // Batched-affine pair levels before the XYZZ accumulation pay off only when every level still fills the
-    // GPU (same sweep): none up to 2^20 points, 2 at 2^21–2^22, 3 from 2^23, if the dense scratch fits.
-    int levels = lg >= 23 ? 3 : lg >= 21 ? 2 : 0;
+    // GPU (same sweep): none up to 2^20 points, 2 at 2^21–2^22, 4 from 2^23, if the dense scratch fits.
+    int levels = lg >= 23 ? 4 : lg >= 21 ? 2 : 0;
     while (levels > 0 && ((npoints >> (c - 1)) >> levels) < 2) levels--;
     size_t scratch = total * 96 / 2 + total * 48 / 2 + total * 96 / 4 + npoints * 128;
     size_t budget = (size_t)64 << 30;
@@ -454,9 +454,10 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
     size_t items_bound = 1;                      // upper bound on the item count of a single bucket
     const int levels = plan.levels;
     const size_t dense_cap_a = max_entries / 2 + TB + 1, dense_cap_b = max_entries / 4 + 2 * (size_t)TB + 1;
-    size_t pair_threads = 131072;                // target thread count of a pair level (T = outputs / this, clamped to 64…1024);
-                                                 // 131072 measured 2 % faster than 65536 and 5 % faster than 262144 at 2^24
-    if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_THREADS")) { long v = atol(e); if (v >= 1024) pair_threads = (size_t)v; }
+    size_t pair_waves = 0;                       // 0 = fewest whole waves with T ≤ 1024 outputs per thread
+    if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_WAVES")) { long v = atol(e); if (v >= 1) pair_waves = (size_t)v; }
+    int sm_count = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0;
     const uint32_t chunk = plan.nbuckets < 32u ? plan.nbuckets : 32u;
@@ -518,9 +519,13 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
                 k_halve_counts<<<(TB + 256) / 256, 256, 0, stream>>>(off_in, cursors, TB);
                 CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cursors, off_out, (int)(TB + 1), stream));
                 bound = bound / 2 + TB;                                  // Σ ceil(cnt/2) ≤ Σ cnt/2 + #buckets
-                size_t T = bound / pair_threads;
-                if (T < 64) T = 64;
-                if (T > 1024) T = 1024;
+                // Whole waves: 148 SMs × 4 resident CTAs × 128 threads = 75776 threads run at once; give every thread the
+                // same number T of outputs and launch an integer number of such waves, so no partial last wave idles
+                // most of the machine (a level is one long-running CTA per slot, not many short ones).
+                const size_t wave = (size_t)sm_count * 4 * 128;
+                size_t waves = (bound + 1024 * wave - 1) / (1024 * wave);
+                if (pair_waves) waves = pair_waves;
+                size_t T = (bound + waves * wave - 1) / (waves * wave);
                 const size_t nthreads = (bound + T - 1) / T;
                 const unsigned lgrid = (unsigned)((nthreads + 127) / 128);
                 if (l == 0)
