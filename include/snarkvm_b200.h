@@ -115,6 +115,12 @@ SNARKVM_API int snarkvm_b200_kzg_commit_device(void* out144, const void* d_power
 SNARKVM_API int snarkvm_b200_fr_from_mont_device(void* d_out, const void* d_in, size_t n, void* stream);
 SNARKVM_API int snarkvm_b200_fr_to_mont_device(void* d_out, const void* d_in, size_t n, void* stream);
 
+/* SRS ingest: npoints uncompressed canonical G1 points as stored in a `.usrs` file after its 8-byte count (x LE 48 B, y LE 48 B,
+ * bit 6 of the last byte = infinity; parameters/src/mainnet/powers.rs, utilities/src/serialize/flags.rs:72-98) -> the reference's
+ * Affine images (Montgomery, `stride` bytes apart) in HBM.  *d_invalid (device u32) receives the number of points that are
+ * out of range, off the curve y^2 = x^3 + 1 or badly flagged.  d_in96 must be 4-byte aligned. */
+SNARKVM_API int snarkvm_b200_srs_decode_device(void* d_out, size_t stride, const void* d_in96, size_t npoints, uint32_t* d_invalid, void* stream);
+
 /* Resident bases for the drop-in snarkvm_msm: upload `host_points` (npoints x stride bytes) to the current device once;
  * later snarkvm_msm calls whose `points_with_infinity` is this same pointer (same stride, npoints <= registered) skip the
  * upload.  The SRS powers of a proving key are constant (polycommit/sonic_pc/data_structures.rs:41-63) and the reference

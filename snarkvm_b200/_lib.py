@@ -20,7 +20,7 @@ SYMBOLS = (
     "snarkvm_b200_polymul_device", "snarkvm_b200_msm_plan", "snarkvm_b200_msm_device",
     "snarkvm_b200_msm_window_sums_device", "snarkvm_b200_xyzz_sum_ranks_device", "snarkvm_b200_msm_finish",
     "snarkvm_b200_kzg_commit_device", "snarkvm_b200_fr_from_mont_device", "snarkvm_b200_fr_to_mont_device",
-    "snarkvm_b200_register_bases", "snarkvm_b200_unregister_bases", "snarkvm_b200_profile_enable", "snarkvm_b200_profile_collect", "snarkvm_b200_generate_bases_device",
+    "snarkvm_b200_srs_decode_device", "snarkvm_b200_register_bases", "snarkvm_b200_unregister_bases", "snarkvm_b200_profile_enable", "snarkvm_b200_profile_collect", "snarkvm_b200_generate_bases_device",
 )
 
 
@@ -72,6 +72,7 @@ def lib():
     L.snarkvm_b200_kzg_commit_device.argtypes = [vp, vp, sz, vp, sz, vp]
     L.snarkvm_b200_fr_from_mont_device.argtypes = [vp, vp, sz, vp]
     L.snarkvm_b200_fr_to_mont_device.argtypes = [vp, vp, sz, vp]
+    L.snarkvm_b200_srs_decode_device.argtypes = [vp, sz, vp, sz, vp, vp]
     L.snarkvm_b200_register_bases.argtypes = [vp, sz, sz]
     L.snarkvm_b200_unregister_bases.argtypes = [vp]
     L.snarkvm_b200_profile_enable.argtypes = [i32]

@@ -300,6 +300,11 @@ int snarkvm_b200_fr_to_mont_device(void* d_out, const void* d_in, size_t n, void
     return fr_to_mont_device(d_out, d_in, n, (cudaStream_t)stream);
 }
 
+int snarkvm_b200_srs_decode_device(void* d_out, size_t stride, const void* d_in96, size_t npoints, uint32_t* d_invalid, void* stream) {
+    if (!d_out || !d_in96 || !d_invalid) return (int)cudaErrorInvalidValue;
+    return srs_decode_device(d_out, stride, d_in96, npoints, d_invalid, (cudaStream_t)stream);
+}
+
 int snarkvm_b200_register_bases(const void* host_points, size_t npoints, size_t stride) {
     if (!host_points || npoints == 0 || stride < 104 || (stride & 7)) return (int)cudaErrorInvalidValue;
     int dev = 0;

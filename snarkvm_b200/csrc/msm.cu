@@ -624,6 +624,50 @@ __global__ void __launch_bounds__(128) k_generate_bases(uint8_t* points, size_t 
     store_affine(points, stride, i, acc.to_affine());
 }
 
+// ---------------------------------------------------------------------------
+// SRS ingest (first half): uncompressed canonical points of a `.usrs` file
+// (x LE 48 B, y LE 48 B, flags in the top two bits of the last byte: bit 6 = infinity —
+// utilities/src/serialize/flags.rs:72-98, curves/src/templates/macros.rs:86-96,136) → the reference's
+// in-memory Affine image (Montgomery x, y, infinity flag) straight in HBM, with the on-curve check
+// y² = x³ + 1 (affine.rs:205-215) and the canonical-range check (< q) counted into *invalid.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_srs_decode(const uint8_t* __restrict__ in, size_t n, uint8_t* __restrict__ out, size_t stride,
+                                                     uint32_t* __restrict__ invalid) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(in + i * 96);     // 96-byte records are 4-byte aligned after the 8-byte header
+    Fq x, y;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { x.v[k] = __ldg(w + k); y.v[k] = __ldg(w + 12 + k); }
+    const uint32_t flags = y.v[11] >> 30;                                   // bit 31 = y sign (unused when uncompressed), bit 30 = infinity
+    y.v[11] &= 0x3fffffffu;
+    AffinePoint a;
+    bool bad = false;
+    if (flags & 1u) {
+        a.x = Fq::zero(); a.y = Fq::one(); a.inf = true;                    // Affine::zero(), affine.rs:57-59
+        bad = (flags & 2u) != 0u;                                           // (sign, infinity) both set is not a valid encoding
+    } else {
+        // canonical range: x, y < q  ⇔  (v − q) borrows
+        Fq tx = x, ty = y;
+        tx.final_sub(); ty.final_sub();
+        bad = (tx != x) || (ty != y);
+        a.x = x.to_mont(); a.y = y.to_mont(); a.inf = false;
+        Fq lhs = a.y.sqr(), rhs = a.x.sqr() * a.x + Fq::one();
+        bad = bad || (lhs != rhs);
+    }
+    if (bad) atomicAdd(invalid, 1u);
+    store_affine(out, stride, i, a);
+}
+int srs_decode_device(void* d_out, size_t stride, const void* d_in, size_t npoints, uint32_t* d_invalid, cudaStream_t stream) {
+    if (stride < 104 || (stride & 7) || ((uintptr_t)d_in & 3)) return (int)cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(d_invalid, 0, 4, stream);
+    if (e != cudaSuccess) return (int)e;
+    if (npoints == 0) return 0;
+    k_srs_decode<<<(unsigned)((npoints + 127) / 128), 128, 0, stream>>>((const uint8_t*)d_in, npoints, (uint8_t*)d_out, stride, d_invalid);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 int msm_generate_bases_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, cudaStream_t stream) {
     if (stride < 104 || (stride & 7)) return (int)cudaErrorInvalidValue;
     if (npoints == 0) return 0;

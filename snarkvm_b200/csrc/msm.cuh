@@ -42,6 +42,10 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
 // affine layout with the given stride.
 int msm_generate_bases_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, cudaStream_t stream);
 
+// `.usrs` uncompressed points (96 B canonical each) → reference Affine images in HBM; *d_invalid counts points that are
+// off the curve, out of range or badly flagged.
+int srs_decode_device(void* d_out, size_t stride, const void* d_in, size_t npoints, uint32_t* d_invalid, cudaStream_t stream);
+
 // out[i] = Σ_r in[r][i]  over `nranks` arrays of `count` XYZZ points (multi-GPU combine).
 int xyzz_sum_ranks_device(uint32_t* d_out, const uint32_t* d_in, int nranks, int count, cudaStream_t stream);
 

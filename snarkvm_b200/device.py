@@ -149,3 +149,18 @@ def generate_bases(npoints: int, seed: int, device="cuda", stride: int = AFFINE_
     with torch.cuda.device(t.device):
         _lib.check(_lib.lib().snarkvm_b200_generate_bases_device(t.data_ptr(), npoints, stride, seed & (2**64 - 1), _stream()))
     return t
+
+
+def srs_decode(usrs_points: torch.Tensor, stride: int = AFFINE_STRIDE):
+    """`.usrs` payload in HBM (uint8, 96 B per uncompressed canonical point, count header already stripped) →
+    (bases in the reference affine layout, number of invalid points).  parameters/src/mainnet/powers.rs."""
+    nbytes = _nbytes(usrs_points)
+    if nbytes % 96:
+        raise ValueError("payload must be a whole number of 96-byte points")
+    n = nbytes // 96
+    out = torch.empty((n, stride), dtype=torch.uint8, device=usrs_points.device)
+    invalid = torch.zeros(1, dtype=torch.int32, device=usrs_points.device)
+    with torch.cuda.device(usrs_points.device):
+        _lib.check(_lib.lib().snarkvm_b200_srs_decode_device(out.data_ptr(), stride, _check(usrs_points, "usrs_points"), n,
+                                                              invalid.data_ptr(), _stream()))
+    return out, int(invalid.item())

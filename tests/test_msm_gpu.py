@@ -304,3 +304,27 @@ def test_ffi_concurrent_callers(oracle_cpu, bases64k):
     for k, n, scal, x in jobs:
         assert (results[k][0] == oracle_cpu.msm(bases64k[:n], scal, 0)).all(), k
         assert (results[k][1] == oracle_cpu.ntt(x, 0, 1)).all(), k
+
+
+def test_srs_decode_real_powers(oracle_cpu):
+    """SRS ingest: the first 512 mainnet powers (uncompressed canonical) decoded on the device == the reference's in-memory
+    Affine images; a corrupted coordinate, an out-of-range coordinate and an infinity record are detected / handled."""
+    import torch
+    from snarkvm_b200 import device
+    with open(os.path.join(HERE, "golden", "powers_of_beta_15_first512.usrs"), "rb") as f:
+        blob = f.read()
+    pts = py.parse_usrs_points(blob, 512)
+    payload = np.frombuffer(blob[8:8 + 512 * 96], dtype=np.uint8).copy()
+    bases, invalid = device.srs_decode(torch.from_numpy(payload).cuda())
+    assert invalid == 0
+    assert (bases.cpu().numpy() == affine_array(pts)).all()
+    bad = payload.copy()
+    bad[5 * 96 + 3] ^= 1                                   # point 5: x changed → off the curve
+    bad[9 * 96:9 * 96 + 48] = 0xFF; bad[9 * 96 + 47] = 0x3F   # point 9: x ≥ q
+    bad[12 * 96:13 * 96] = 0; bad[12 * 96 + 95] = 0x40        # point 12: infinity
+    got, invalid = device.srs_decode(torch.from_numpy(bad).cuda())
+    assert invalid == 2
+    g = got.cpu().numpy()
+    assert g[12].tobytes() == py.affine_bytes(None)
+    keep = [i for i in range(512) if i not in (5, 9, 12)]
+    assert (g[keep] == affine_array(pts)[keep]).all()
