@@ -2,6 +2,7 @@
 #include "msm.cuh"
 
 #include <atomic>
+#include <memory>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -489,12 +490,12 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
     CUDA_TRY(cudaMemsetAsync(items, 0, (size_t)(TB + 1) * 4, stream));
     {
         const unsigned grid = (unsigned)((npoints + 255) / 256);
-        ProfScope* sort_scope = new ProfScope(PROF_MSM_SORT, stream);
+        std::unique_ptr<ProfScope> sort_scope(new ProfScope(PROF_MSM_SORT, stream));
         k_digits<false><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, hist, nullptr);
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, hist, bucket_start, (int)(TB + 1), stream));
         CUDA_TRY(cudaMemcpyAsync(cursors, bucket_start, (size_t)(TB + 1) * 4, cudaMemcpyDeviceToDevice, stream));
         k_digits<true><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, cursors, sorted);
-        delete sort_scope;
+        sort_scope.reset();
         count_launch(4);
         if (levels == 0) {
             k_items_per_bucket<<<(TB + 255) / 256, 256, 0, stream>>>(hist, items, TB, plan.cap);
