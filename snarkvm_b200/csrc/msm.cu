@@ -94,10 +94,6 @@ MsmPlan msm_make_plan(size_t npoints) {
     // GPU (same sweep): none up to 2^20 points, 2 at 2^21–2^22, 4 from 2^23, if the dense scratch fits.
     int levels = lg >= 23 ? 4 : lg >= 21 ? 2 : 0;
     while (levels > 0 && ((npoints >> (c - 1)) >> levels) < 2) levels--;
-    size_t scratch = total * 96 / 2 + total * 48 / 2 + total * 96 / 4 + npoints * 128;
-    size_t budget = (size_t)64 << 30;
-    if (const char* e = getenv("SNARKVM_B200_MSM_SCRATCH_GB")) { long v = atol(e); if (v >= 1) budget = (size_t)v << 30; }
-    if (scratch > budget) levels = 0;
     if (const char* e = getenv("SNARKVM_B200_MSM_LEVELS")) { int v = atoi(e); if (v >= 0 && v <= 16) levels = v; }
     p.levels = levels;
     return p;
@@ -445,16 +441,30 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
     ensure_pool_configured();
     const uint32_t TB = (uint32_t)plan.nwin * plan.nbuckets;      // total buckets
     const size_t max_entries = npoints * (size_t)plan.nwin;
-    const size_t max_items = (size_t)TB + max_entries / plan.cap + 1;
     if (npoints == 0 || npoints >= (1ull << 31) || max_entries >= (1ull << 32)) return (int)cudaErrorInvalidValue;
+    const int levels = plan.levels;
+
+    // Everything after the bucket sort runs per GROUP of whole windows, so the dense scratch of the pair levels
+    // (96 B per point per window) stays inside a budget: 2^24 points → all 15 windows at once (24 GB),
+    // 2^26 points → 3 groups of 6/6/3 windows.
+    size_t budget = (size_t)40 << 30;
+    if (const char* e = getenv("SNARKVM_B200_MSM_SCRATCH_GB")) { long v = atol(e); if (v >= 1) budget = (size_t)v << 30; }
+    uint32_t gw = (uint32_t)plan.nwin;
+    if (levels > 0) {
+        size_t per_window = npoints * (size_t)96 + 1;
+        size_t fit = budget / per_window;
+        if (fit < 1) fit = 1;
+        if (fit < gw) gw = (uint32_t)fit;
+    }
+    const uint32_t TBg = gw * plan.nbuckets;                      // buckets of the largest group
+    const size_t entries_g = npoints * (size_t)gw;
+    const size_t max_items = (size_t)TBg + entries_g / plan.cap + 1;
 
     uint32_t *hist = nullptr, *bucket_start = nullptr, *cursors = nullptr, *items = nullptr, *item_start = nullptr;
     uint32_t *sorted = nullptr, *partial = nullptr, *red_a = nullptr, *red_b = nullptr;
     uint32_t *off_a = nullptr, *off_b = nullptr, *dense_a = nullptr, *dense_b = nullptr, *prefix = nullptr, *dense_bases = nullptr;
-    uint32_t *partial2 = nullptr, *items2 = nullptr, *final_partial = nullptr, *final_start = nullptr;
-    size_t items_bound = 1;                      // upper bound on the item count of a single bucket
-    const int levels = plan.levels;
-    const size_t dense_cap_a = max_entries / 2 + TB + 1, dense_cap_b = max_entries / 4 + 2 * (size_t)TB + 1;
+    uint32_t *partial2 = nullptr, *items2 = nullptr;
+    const size_t dense_cap_a = entries_g / 2 + TBg + 1, dense_cap_b = entries_g / 4 + 2 * (size_t)TBg + 1;
     size_t pair_waves = 0;                       // 0 = fewest whole waves with T ≤ 1024 outputs per thread
     if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_WAVES")) { long v = atol(e); if (v >= 1) pair_waves = (size_t)v; }
     int sm_count = 148;
@@ -467,120 +477,138 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
     CUDA_TRY(cudaMallocAsync(&hist, (size_t)(TB + 1) * 4, stream));
     CUDA_TRY(cudaMallocAsync(&bucket_start, (size_t)(TB + 1) * 4, stream));
     CUDA_TRY(cudaMallocAsync(&cursors, (size_t)(TB + 1) * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&items, (size_t)(TB + 1) * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&item_start, (size_t)(TB + 1) * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&items, (size_t)(TBg + 1) * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&item_start, (size_t)(TBg + 1) * 4, stream));
     CUDA_TRY(cudaMallocAsync(&sorted, max_entries * 4, stream));
     CUDA_TRY(cudaMallocAsync(&partial, max_items * XYZZ_WORDS * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&partial2, ((size_t)TB + max_items / 32 + 2) * XYZZ_WORDS * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&items2, (size_t)(TB + 1) * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&partial2, ((size_t)TBg + max_items / 32 + 2) * XYZZ_WORDS * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&items2, (size_t)(TBg + 1) * 4, stream));
     if (levels > 0) {
-        CUDA_TRY(cudaMallocAsync(&off_a, (size_t)(TB + 1) * 4, stream));
-        CUDA_TRY(cudaMallocAsync(&off_b, (size_t)(TB + 1) * 4, stream));
+        CUDA_TRY(cudaMallocAsync(&off_a, (size_t)(TBg + 1) * 4, stream));
+        CUDA_TRY(cudaMallocAsync(&off_b, (size_t)(TBg + 1) * 4, stream));
         CUDA_TRY(cudaMallocAsync(&dense_a, dense_cap_a * DENSE_WORDS * 4, stream));
         if (levels > 1) CUDA_TRY(cudaMallocAsync(&dense_b, dense_cap_b * DENSE_WORDS * 4, stream));
         CUDA_TRY(cudaMallocAsync(&prefix, dense_cap_a * 12 * 4, stream));
         CUDA_TRY(cudaMallocAsync(&dense_bases, npoints * (size_t)BASE_WORDS * 4, stream));
     }
-    CUDA_TRY(cudaMallocAsync(&red_a, (size_t)plan.nwin * chunks_per_window * XYZZ_WORDS * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&red_b, (size_t)plan.nwin * (chunks_per_window / 32 + 1) * XYZZ_WORDS * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&red_a, (size_t)gw * chunks_per_window * XYZZ_WORDS * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&red_b, (size_t)gw * (chunks_per_window / 32 + 1) * XYZZ_WORDS * 4, stream));
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, hist, bucket_start, (int)(TB + 1), stream));
     CUDA_TRY(cudaMallocAsync(&cub_tmp, cub_bytes ? cub_bytes : 16, stream));
 
     CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)(TB + 1) * 4, stream));
-    CUDA_TRY(cudaMemsetAsync(items, 0, (size_t)(TB + 1) * 4, stream));
     {
+        // ---- bucket sort of all windows: histogram → offsets → scatter ----
         const unsigned grid = (unsigned)((npoints + 255) / 256);
-        std::unique_ptr<ProfScope> sort_scope(new ProfScope(PROF_MSM_SORT, stream));
-        k_digits<false><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, hist, nullptr);
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, hist, bucket_start, (int)(TB + 1), stream));
-        CUDA_TRY(cudaMemcpyAsync(cursors, bucket_start, (size_t)(TB + 1) * 4, cudaMemcpyDeviceToDevice, stream));
-        k_digits<true><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, cursors, sorted);
-        sort_scope.reset();
-        count_launch(4);
-        if (levels == 0) {
-            k_items_per_bucket<<<(TB + 255) / 256, 256, 0, stream>>>(hist, items, TB, plan.cap);
-            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(TB + 1), stream));
-            count_launch(3);
-            const unsigned agrid = (unsigned)((max_items + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
-            items_bound = npoints / plan.cap + 1;                       // a bucket belongs to one window: ≤ n entries
-            ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
-            k_bucket_accumulate<<<agrid, MSM_ACC_THREADS, 0, stream>>>((const uint8_t*)d_points, stride, sorted, bucket_start, item_start, TB, plan.cap, partial);
-        } else {
+        {
+            ProfScope sort_scope(PROF_MSM_SORT, stream);
+            k_digits<false><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, hist, nullptr);
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, hist, bucket_start, (int)(TB + 1), stream));
+            CUDA_TRY(cudaMemcpyAsync(cursors, bucket_start, (size_t)(TB + 1) * 4, cudaMemcpyDeviceToDevice, stream));
+            k_digits<true><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, cursors, sorted);
+            count_launch(4);
+        }
+        if (levels > 0) {
             ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
             k_densify_bases<<<(unsigned)((npoints + 255) / 256), 256, 0, stream>>>((const uint8_t*)d_points, stride, npoints, dense_bases);
             count_launch();
-            const uint32_t* off_in = bucket_start;
-            uint32_t* off_bufs[2] = {off_a, off_b};
-            uint32_t* dense_bufs[2] = {dense_a, dense_b};
-            const uint32_t* dense_in = nullptr;
-            size_t bound = max_entries;                                  // upper bound on the level's input count
-            for (int l = 0; l < levels; l++) {
-                uint32_t* off_out = off_bufs[l & 1];
-                uint32_t* dense_out = dense_bufs[l & 1];
-                k_halve_counts<<<(TB + 256) / 256, 256, 0, stream>>>(off_in, cursors, TB);
-                CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cursors, off_out, (int)(TB + 1), stream));
-                bound = bound / 2 + TB;                                  // Σ ceil(cnt/2) ≤ Σ cnt/2 + #buckets
-                // Whole waves: 148 SMs × 4 resident CTAs × 128 threads = 75776 threads run at once; give every thread the
-                // same number T of outputs and launch an integer number of such waves, so no partial last wave idles
-                // most of the machine (a level is one long-running CTA per slot, not many short ones).
-                const size_t wave = (size_t)sm_count * 4 * 128;
-                size_t waves = (bound + 1024 * wave - 1) / (1024 * wave);
-                if (pair_waves) waves = pair_waves;
-                size_t T = (bound + waves * wave - 1) / (waves * wave);
-                const size_t nthreads = (bound + T - 1) / T;
-                const unsigned lgrid = (unsigned)((nthreads + 127) / 128);
-                if (l == 0)
-                    k_pair_level<true><<<lgrid, 128, 0, stream>>>(dense_bases, sorted, nullptr, off_in, off_out, TB, (uint32_t)T, prefix, dense_out);
-                else
-                    k_pair_level<false><<<lgrid, 128, 0, stream>>>(nullptr, nullptr, dense_in, off_in, off_out, TB, (uint32_t)T, prefix, dense_out);
+        }
+        for (uint32_t w0 = 0; w0 < (uint32_t)plan.nwin; w0 += gw) {
+            const uint32_t wn = (uint32_t)plan.nwin - w0 < gw ? (uint32_t)plan.nwin - w0 : gw;     // windows in this group
+            const uint32_t tb = wn * plan.nbuckets;
+            const uint32_t* bs = bucket_start + (size_t)w0 * plan.nbuckets;                       // tb + 1 absolute offsets into `sorted`
+            const size_t entries = npoints * (size_t)wn;
+            size_t items_bound = 1;                                                                // ≥ item count of any single bucket
+            const uint32_t* final_partial = nullptr;
+            const uint32_t* final_start = nullptr;
+            if (levels == 0) {
+                CUDA_TRY(cudaMemsetAsync(items, 0, (size_t)(tb + 1) * 4, stream));
+                k_items_per_bucket<<<(tb + 255) / 256, 256, 0, stream>>>(hist + (size_t)w0 * plan.nbuckets, items, tb, plan.cap);
+                CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(tb + 1), stream));
+                count_launch(3);
+                const size_t group_items = (size_t)tb + entries / plan.cap + 1;
+                items_bound = npoints / plan.cap + 1;                   // a bucket belongs to one window: ≤ n entries
+                ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
+                k_bucket_accumulate<<<(unsigned)((group_items + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
+                    (const uint8_t*)d_points, stride, sorted, bs, item_start, tb, plan.cap, partial);
+            } else {
+                ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
+                const uint32_t* off_in = bs;
+                uint32_t* off_bufs[2] = {off_a, off_b};
+                uint32_t* dense_bufs[2] = {dense_a, dense_b};
+                const uint32_t* dense_in = nullptr;
+                size_t bound = entries;                                  // upper bound on the level's input count
+                for (int l = 0; l < levels; l++) {
+                    uint32_t* off_out = off_bufs[l & 1];
+                    uint32_t* dense_out = dense_bufs[l & 1];
+                    k_halve_counts<<<(tb + 256) / 256, 256, 0, stream>>>(off_in, cursors, tb);
+                    CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cursors, off_out, (int)(tb + 1), stream));
+                    bound = bound / 2 + tb;                              // Σ ceil(cnt/2) ≤ Σ cnt/2 + #buckets
+                    // Whole waves: 148 SMs × 4 resident CTAs × 128 threads = 75776 threads run at once; give every thread
+                    // the same number T of outputs and launch an integer number of such waves, so no partial last wave
+                    // idles most of the machine (a level is one long-running CTA per slot, not many short ones).
+                    const size_t wave = (size_t)sm_count * 4 * 128;
+                    size_t waves = (bound + 1024 * wave - 1) / (1024 * wave);
+                    if (pair_waves) waves = pair_waves;
+                    size_t T = (bound + waves * wave - 1) / (waves * wave);
+                    const size_t nthreads = (bound + T - 1) / T;
+                    const unsigned lgrid = (unsigned)((nthreads + 127) / 128);
+                    // level 0 reads absolute positions of `sorted` (off_in = bs); its outputs and all later levels are
+                    // group-relative (the scans start at 0)
+                    if (l == 0)
+                        k_pair_level<true><<<lgrid, 128, 0, stream>>>(dense_bases, sorted, nullptr, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
+                    else
+                        k_pair_level<false><<<lgrid, 128, 0, stream>>>(nullptr, nullptr, dense_in, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
+                    count_launch(4);
+                    off_in = off_out;
+                    dense_in = dense_out;
+                }
+                k_items_from_offsets<<<(tb + 256) / 256, 256, 0, stream>>>(off_in, items, tb, plan.cap);
+                CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(tb + 1), stream));
+                const size_t group_items = (size_t)tb + bound / plan.cap + 1;
+                items_bound = ((npoints >> levels) + 1) / plan.cap + 1;
+                k_bucket_accumulate_dense<<<(unsigned)((group_items + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
+                    dense_in, off_in, item_start, tb, plan.cap, partial);
                 count_launch(4);
-                off_in = off_out;
-                dense_in = dense_out;
             }
-            k_items_from_offsets<<<(TB + 256) / 256, 256, 0, stream>>>(off_in, items, TB, plan.cap);
-            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(TB + 1), stream));
-            const size_t max_items_dense = (size_t)TB + bound / plan.cap + 1;
-            items_bound = ((npoints >> levels) + 1) / plan.cap + 1;
-            const unsigned agrid = (unsigned)((max_items_dense + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
-            k_bucket_accumulate_dense<<<agrid, MSM_ACC_THREADS, 0, stream>>>(dense_in, off_in, item_start, TB, plan.cap, partial);
-            count_launch(4);
-        }
-        ProfScope red_scope(PROF_MSM_REDUCE, stream);
-        {
-            // fold item partials 32:1 until no bucket can hold more than one (worst case: all entries in one bucket)
-            size_t worst = items_bound;
-            uint32_t* p_in = partial; uint32_t* p_out = partial2;
-            uint32_t* st_in = item_start; uint32_t* st_out = items2;
-            while (worst > 1) {
-                k_group_counts<<<(TB + 256) / 256, 256, 0, stream>>>(st_in, cursors, TB);
-                CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cursors, st_out, (int)(TB + 1), stream));
-                const size_t out_bound = (size_t)TB + (worst + 31) / 32;
-                k_partial_group_sum<<<(unsigned)((out_bound + 127) / 128), 128, 0, stream>>>(p_in, st_in, st_out, TB, p_out);
-                count_launch(4);
-                worst = (worst + 31) / 32;
-                uint32_t* t1 = p_in; p_in = p_out; p_out = t1;
-                uint32_t* t2 = st_in; st_in = st_out; st_out = t2;
+            ProfScope red_scope(PROF_MSM_REDUCE, stream);
+            {
+                // fold item partials 32:1 until no bucket can hold more than one (worst case: all entries in one bucket)
+                size_t worst = items_bound;
+                uint32_t* p_in = partial; uint32_t* p_out = partial2;
+                uint32_t* st_in = item_start; uint32_t* st_out = items2;
+                while (worst > 1) {
+                    k_group_counts<<<(tb + 256) / 256, 256, 0, stream>>>(st_in, cursors, tb);
+                    CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cursors, st_out, (int)(tb + 1), stream));
+                    const size_t out_bound = (size_t)tb + (worst + 31) / 32;
+                    k_partial_group_sum<<<(unsigned)((out_bound + 127) / 128), 128, 0, stream>>>(p_in, st_in, st_out, tb, p_out);
+                    count_launch(4);
+                    worst = (worst + 31) / 32;
+                    uint32_t* t1 = p_in; p_in = p_out; p_out = t1;
+                    uint32_t* t2 = st_in; st_in = st_out; st_out = t2;
+                }
+                final_partial = p_in; final_start = st_in;
             }
-            final_partial = p_in; final_start = st_in;
+            uint32_t* group_sums = d_window_sums + (size_t)w0 * XYZZ_WORDS;
+            const uint32_t nthreads = chunks_per_window * wn;
+            k_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, stream>>>(final_partial, final_start, plan.nbuckets, chunk, chunks_per_window, wn, red_a);
+            count_launch(1);
+            // tree over the per-chunk sums: groups of 32 until one point per window remains
+            uint32_t per_row = chunks_per_window;
+            const uint32_t* src = red_a;
+            uint32_t* bufs[2] = {red_b, red_a};
+            int which = 0;
+            while (per_row > 1) {
+                uint32_t out_per_row = (per_row + 31) / 32;
+                uint32_t* target = out_per_row == 1 ? group_sums : bufs[which];
+                uint32_t nt = out_per_row * wn;
+                k_group_sum<<<(nt + 127) / 128, 128, 0, stream>>>(src, per_row, 32, out_per_row, wn, target);
+                count_launch();
+                src = target; which ^= 1; per_row = out_per_row;
+            }
+            if (chunks_per_window == 1)
+                CUDA_TRY(cudaMemcpyAsync(group_sums, red_a, (size_t)wn * XYZZ_WORDS * 4, cudaMemcpyDeviceToDevice, stream));
         }
-        const uint32_t nthreads = chunks_per_window * (uint32_t)plan.nwin;
-        k_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, stream>>>(final_partial, final_start, plan.nbuckets, chunk, chunks_per_window, (uint32_t)plan.nwin, red_a);
-        count_launch(1);
-        // tree over the per-chunk sums: groups of 32 until one point per window remains
-        uint32_t per_row = chunks_per_window;
-        const uint32_t* src = red_a;
-        uint32_t* bufs[2] = {red_b, red_a};
-        int which = 0;
-        while (per_row > 1) {
-            uint32_t out_per_row = (per_row + 31) / 32;
-            uint32_t* target = out_per_row == 1 ? d_window_sums : bufs[which];
-            uint32_t nt = out_per_row * (uint32_t)plan.nwin;
-            k_group_sum<<<(nt + 127) / 128, 128, 0, stream>>>(src, per_row, 32, out_per_row, (uint32_t)plan.nwin, target);
-            count_launch();
-            src = target; which ^= 1; per_row = out_per_row;
-        }
-        if (chunks_per_window == 1)
-            CUDA_TRY(cudaMemcpyAsync(d_window_sums, red_a, (size_t)plan.nwin * XYZZ_WORDS * 4, cudaMemcpyDeviceToDevice, stream));
         CUDA_TRY(cudaGetLastError());
     }
 done:
