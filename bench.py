@@ -264,7 +264,7 @@ def run_product(args, rank, world, local_rank):
     assert (out == first).all(), "MSM result changed between steps"
     ms_per_step = ms_total / args.steps
     value = n * world / (ms_per_step * 1e-3)
-    acc_ms_per_launch = acc_ms / max(1, acc_n)
+    acc_ms_per_launch = acc_ms / max(1, args.steps)        # the whole accumulation phase of one MSM (several kernels)
     achieved = ALGO_BYTES_PER_POINT * n / (acc_ms_per_launch * 1e-3) / 1e9
 
     # ---- `e2e`: through the drop-in C-ABI symbol with pinned HOST buffers (H2D + D2H inside the timing) ----
