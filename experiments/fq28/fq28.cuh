@@ -12,7 +12,7 @@
 // Representation: value = Σ v[i]·2^{28 i}; an element x is stored as x·R' mod p with R' = 2^392
 // ("internal Montgomery form").  Values are NOT canonical: every function documents the limb and value
 // bounds it needs and guarantees.  The exact op sequences and bounds are model-checked on Python
-// integers in tools/fq28_model.py (column sums < 2^64, limbs < 2^32, borrow-free subtraction).
+// integers in tests/manual/fq28_model.py (column sums < 2^64, limbs < 2^32, borrow-free subtraction).
 // Conversion from / to the reference's in-memory form (12 × u32, Montgomery R = 2^384; fp_384.rs:52)
 // happens once per base and once per bucket item.
 #pragma once
@@ -281,7 +281,7 @@ struct XYZZ28 {
         X = X3; Y = Y3; ZZ = V; ZZZ = W; inf = false;
     }
 
-    // this += (negate ? −q : q)   (madd-2008-s; bounds model-checked in tools/fq28_model.py)
+    // this += (negate ? −q : q)   (madd-2008-s; bounds model-checked in tests/manual/fq28_model.py)
     FF_DEV void add_affine(const Affine28& q, bool negate) {
         if (q.inf) return;
         Fq28 qy = negate ? fq28_neg(q.y) : q.y;                 // limbs < 2^29, value ≤ 2p

@@ -1,6 +1,6 @@
 """Ad-hoc large-size sanity run on the GPU: 2^26-point MSM (closed form against the oracle) and 2^26 / 2^27 NTT round trips."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from oracle import bls12_377 as py, cpu
 from helpers import affine_array, generated_base_multipliers, random_canonical_fr

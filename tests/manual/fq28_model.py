@@ -1,13 +1,13 @@
-"""Exact Python model of snarkvm_b200/csrc/fq28.cuh (radix-2^28, 14-limb, lazily reduced Fq arithmetic).
+"""Exact Python model of experiments/fq28/fq28.cuh (radix-2^28, 14-limb, lazily reduced Fq arithmetic).
 
 Mirrors the device code operation by operation on Python integers, asserting every 32-/64-bit register bound
 the CUDA code relies on (column sums < 2^64, limbs < 2^32, borrow-proof subtraction), and checks the result
-against plain modular arithmetic.  Run:  python tools/fq28_model.py
+against plain modular arithmetic.  Run:  python tests/manual/fq28_model.py   (lives under tests/ because it uses the oracle; the CUDA side is experiments/fq28/)
 """
 import random
 import sys
 
-sys.path.insert(0, __file__.rsplit("/experiments/", 1)[0])
+sys.path.insert(0, __file__.rsplit("/tests/", 1)[0])
 from oracle import bls12_377 as o  # noqa: E402
 
 P = o.Q_MOD
