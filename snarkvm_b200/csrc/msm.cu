@@ -471,7 +471,10 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0;
-    const uint32_t chunk = plan.nbuckets < 32u ? plan.nbuckets : 32u;
+    // The reduction tail is a chain of dependent point additions per thread (≈ 16 µs each for a lone warp): short chunks
+    // and a narrow (8:1) tree keep that chain short — what matters at 2^16–2^20 points, where the tail is 20–50 % of the call.
+    const uint32_t chunk = plan.nbuckets < 16u ? plan.nbuckets : 16u;
+    const uint32_t tree = 8;
     const uint32_t chunks_per_window = plan.nbuckets / chunk;
 
     CUDA_TRY(cudaMallocAsync(&hist, (size_t)(TB + 1) * 4, stream));
@@ -492,7 +495,7 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
         CUDA_TRY(cudaMallocAsync(&dense_bases, npoints * (size_t)BASE_WORDS * 4, stream));
     }
     CUDA_TRY(cudaMallocAsync(&red_a, (size_t)gw * chunks_per_window * XYZZ_WORDS * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&red_b, (size_t)gw * (chunks_per_window / 32 + 1) * XYZZ_WORDS * 4, stream));
+    CUDA_TRY(cudaMallocAsync(&red_b, (size_t)gw * (chunks_per_window / tree + 1) * XYZZ_WORDS * 4, stream));
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, hist, bucket_start, (int)(TB + 1), stream));
     CUDA_TRY(cudaMallocAsync(&cub_tmp, cub_bytes ? cub_bytes : 16, stream));
 
@@ -593,16 +596,16 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
             const uint32_t nthreads = chunks_per_window * wn;
             k_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, stream>>>(final_partial, final_start, plan.nbuckets, chunk, chunks_per_window, wn, red_a);
             count_launch(1);
-            // tree over the per-chunk sums: groups of 32 until one point per window remains
+            // tree over the per-chunk sums: groups of `tree` until one point per window remains
             uint32_t per_row = chunks_per_window;
             const uint32_t* src = red_a;
             uint32_t* bufs[2] = {red_b, red_a};
             int which = 0;
             while (per_row > 1) {
-                uint32_t out_per_row = (per_row + 31) / 32;
+                uint32_t out_per_row = (per_row + tree - 1) / tree;
                 uint32_t* target = out_per_row == 1 ? group_sums : bufs[which];
                 uint32_t nt = out_per_row * wn;
-                k_group_sum<<<(nt + 127) / 128, 128, 0, stream>>>(src, per_row, 32, out_per_row, wn, target);
+                k_group_sum<<<(nt + 127) / 128, 128, 0, stream>>>(src, per_row, tree, out_per_row, wn, target);
                 count_launch();
                 src = target; which ^= 1; per_row = out_per_row;
             }
