@@ -2,8 +2,10 @@
 //
 // Replaces the hot loops of the reference's VariableBase::msm
 // (algorithms/src/msm/variable_base/mod.rs:30-49 → batched.rs:366-415):
-//   batched_window  (batched.rs:328-364)  →  k_digit_hist / k_digit_scatter  (bucket sort)
-//   batch_add       (batched.rs:175-325)  →  k_bucket_accumulate             (bucket sums)
+//   batched_window  (batched.rs:328-364)  →  k_digits<0/1>                      (signed digits, counting sort by bucket)
+//   batch_add       (batched.rs:175-325)  →  k_pair_level ×(0/2/4)              (Montgomery-trick affine pair levels)
+//                                            k_bucket_accumulate(_dense)         (XYZZ sums of what is left, per work item)
+//                                            k_partial_group_sum                 (hot buckets: fold item partials 32:1)
 //   running sum     (batched.rs:356-361)  →  k_bucket_reduce / k_group_sum
 //   window combine  (batched.rs:404-413)  →  host Horner over ≤ 24 window sums (host_ec.hpp)
 //
@@ -11,9 +13,10 @@
 // recoding / coordinate system yields the same to_affine() image):
 //   * signed c-bit digits  → 2^(c-1) buckets per window instead of 2^c − 1
 //   * counting sort by (window, bucket) with global atomics instead of sort_unstable
-//   * XYZZ mixed additions instead of Montgomery-trick batched affine additions
-//   * every bucket is cut into work items of ≤ cap points so a hot bucket (all scalars
-//     equal, repeated bases — benches/msm/variable_base.rs:29-32) cannot serialise a thread.
+//   * batched affine additions only for the first levels (where they fill the GPU), XYZZ mixed additions after
+//   * every bucket is cut into work items of ≤ cap points and every pair level is split by OUTPUT elements, so a hot
+//     bucket (all scalars equal, repeated bases — benches/msm/variable_base.rs:29-32 — or the carry-only top window)
+//     cannot serialise a thread.
 #pragma once
 #include <cstddef>
 #include <cstdint>
