@@ -111,6 +111,17 @@ SNARKVM_API int snarkvm_b200_msm_finish(void* out144, const void* h_window_sums,
 SNARKVM_API int snarkvm_b200_kzg_commit_device(void* out144, const void* d_powers, size_t stride, const void* d_coeffs_mont,
                                    size_t ncoeffs, void* stream);
 
+/* Fixed base sets (an SRS kept in HBM across many commitments): precompute the tables 2^(c*w) * P_i, w < nwin, once; every MSM
+ * over those bases then uses ONE bucket set for all windows (c = 22, 12 windows at 2^24 points instead of 17 / 15).  The handle owns
+ * npoints * nwin * 128 bytes of HBM (25.8 GB at 2^24).  nscalars <= npoints selects the prefix P_0..P_{nscalars-1}
+ * (`&powers_of_beta_g[..len]`, polycommit/kzg10/mod.rs:121-135).  Results are the same group elements as snarkvm_b200_msm_device. */
+SNARKVM_API int snarkvm_b200_msm_precompute_device(void** handle_out, const void* d_points, size_t npoints, size_t stride, void* stream);
+SNARKVM_API int snarkvm_b200_msm_precomputed_free(void* handle);
+SNARKVM_API int snarkvm_b200_msm_precomputed_info(const void* handle, size_t* npoints, int* c, int* nwin, size_t* table_bytes);
+SNARKVM_API int snarkvm_b200_msm_precomputed_device(void* out144, const void* handle, const void* d_scalars, size_t nscalars, void* stream);
+SNARKVM_API int snarkvm_b200_kzg_commit_precomputed_device(void* out144, const void* handle, const void* d_coeffs_mont, size_t ncoeffs,
+                                                           void* stream);
+
 /* Fr Montgomery <-> canonical, n elements in HBM (to_bigint / from_bigint, fields/src/fp_256.rs:362-413). */
 SNARKVM_API int snarkvm_b200_fr_from_mont_device(void* d_out, const void* d_in, size_t n, void* stream);
 SNARKVM_API int snarkvm_b200_fr_to_mont_device(void* d_out, const void* d_in, size_t n, void* stream);

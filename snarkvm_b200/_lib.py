@@ -21,6 +21,8 @@ SYMBOLS = (
     "snarkvm_b200_msm_window_sums_device", "snarkvm_b200_xyzz_sum_ranks_device", "snarkvm_b200_msm_finish",
     "snarkvm_b200_kzg_commit_device", "snarkvm_b200_fr_from_mont_device", "snarkvm_b200_fr_to_mont_device",
     "snarkvm_b200_srs_decode_device", "snarkvm_b200_register_bases", "snarkvm_b200_unregister_bases", "snarkvm_b200_profile_enable", "snarkvm_b200_profile_collect", "snarkvm_b200_generate_bases_device",
+    "snarkvm_b200_msm_precompute_device", "snarkvm_b200_msm_precomputed_free", "snarkvm_b200_msm_precomputed_info",
+    "snarkvm_b200_msm_precomputed_device", "snarkvm_b200_kzg_commit_precomputed_device",
 )
 
 
@@ -78,6 +80,11 @@ def lib():
     L.snarkvm_b200_profile_enable.argtypes = [i32]
     L.snarkvm_b200_profile_collect.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
     L.snarkvm_b200_generate_bases_device.argtypes = [vp, sz, sz, u64, vp]
+    L.snarkvm_b200_msm_precompute_device.argtypes = [ctypes.POINTER(vp), vp, sz, sz, vp]
+    L.snarkvm_b200_msm_precomputed_free.argtypes = [vp]
+    L.snarkvm_b200_msm_precomputed_info.argtypes = [vp, ctypes.POINTER(sz), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(sz)]
+    L.snarkvm_b200_msm_precomputed_device.argtypes = [vp, vp, vp, sz, vp]
+    L.snarkvm_b200_kzg_commit_precomputed_device.argtypes = [vp, vp, vp, sz, vp]
     for s in SYMBOLS[5:]:
         getattr(L, s).restype = i32
     L.snarkvm_b200_launch_count.restype = u64

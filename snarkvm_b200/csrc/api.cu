@@ -293,6 +293,77 @@ int snarkvm_b200_kzg_commit_device(void* out144, const void* d_powers, size_t st
     return rc;
 }
 
+// Precomputed tables for a fixed base set (an SRS): handle = {table, n, plan}.  One-time cost: (nwin−1)·c doublings and
+// nwin−1 inversions per point; memory npoints·nwin·128 B.
+struct PrecomputedBases { uint32_t* table; size_t n; MsmPlan plan; int device; };
+
+int snarkvm_b200_msm_precompute_device(void** handle_out, const void* d_points, size_t npoints, size_t stride, void* stream_v) {
+    if (!handle_out || !d_points || npoints == 0 || stride < 104 || (stride & 7)) return (int)cudaErrorInvalidValue;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    MsmPlan plan = msm_make_plan_precomputed(npoints);
+    if (npoints * (size_t)plan.nwin >= (1ull << 31)) return (int)cudaErrorInvalidValue;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    uint32_t* table = nullptr;
+    if ((e = cudaMalloc(&table, npoints * (size_t)plan.nwin * 128)) != cudaSuccess) return (int)e;
+    int rc = msm_precompute_tables_device(table, plan, d_points, stride, npoints, stream);
+    if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
+    if (rc != 0) { cudaFree(table); return rc; }
+    *handle_out = new PrecomputedBases{table, npoints, plan, dev};
+    return 0;
+}
+
+int snarkvm_b200_msm_precomputed_free(void* handle) {
+    if (!handle) return (int)cudaErrorInvalidValue;
+    PrecomputedBases* h = (PrecomputedBases*)handle;
+    cudaError_t e = cudaFree(h->table);
+    delete h;
+    return (int)e;
+}
+
+int snarkvm_b200_msm_precomputed_info(const void* handle, size_t* npoints, int* c, int* nwin, size_t* table_bytes) {
+    if (!handle) return (int)cudaErrorInvalidValue;
+    const PrecomputedBases* h = (const PrecomputedBases*)handle;
+    if (npoints) *npoints = h->n;
+    if (c) *c = h->plan.c;
+    if (nwin) *nwin = h->plan.nwin;
+    if (table_bytes) *table_bytes = h->n * (size_t)h->plan.nwin * 128;
+    return 0;
+}
+
+int snarkvm_b200_msm_precomputed_device(void* out144, const void* handle, const void* d_scalars, size_t nscalars, void* stream_v) {
+    if (!out144 || !handle) return (int)cudaErrorInvalidValue;
+    const PrecomputedBases* h = (const PrecomputedBases*)handle;
+    if (nscalars > h->n) return (int)cudaErrorInvalidValue;
+    if (nscalars == 0) { write_infinity(out144); return 0; }
+    if (!d_scalars) return (int)cudaErrorInvalidValue;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    uint32_t* d_sum = nullptr;
+    cudaError_t e = cudaMallocAsync(&d_sum, 192, stream);
+    if (e != cudaSuccess) return (int)e;
+    int rc = msm_precomputed_sum_device(d_sum, h->plan, h->table, h->n, d_scalars, nscalars, stream);
+    host::Xyzz sum;
+    if (rc == 0) rc = (int)cudaMemcpyAsync(&sum, d_sum, 192, cudaMemcpyDeviceToHost, stream);
+    cudaFreeAsync(d_sum, stream);
+    if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
+    if (rc != 0) return rc;
+    host::xyzz_to_normalised_projective(sum, (uint64_t*)out144);
+    return 0;
+}
+
+int snarkvm_b200_kzg_commit_precomputed_device(void* out144, const void* handle, const void* d_coeffs_mont, size_t ncoeffs, void* stream_v) {
+    if (!out144 || !handle) return (int)cudaErrorInvalidValue;
+    if (ncoeffs == 0) { write_infinity(out144); return 0; }
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    void* d_plain = nullptr;
+    int rc = (int)cudaMallocAsync(&d_plain, ncoeffs * 32, stream);
+    if (rc == 0) rc = fr_from_mont_device(d_plain, d_coeffs_mont, ncoeffs, stream);
+    if (rc == 0) rc = snarkvm_b200_msm_precomputed_device(out144, handle, d_plain, ncoeffs, stream_v);
+    if (d_plain) cudaFreeAsync(d_plain, stream);
+    return rc;
+}
+
 int snarkvm_b200_fr_from_mont_device(void* d_out, const void* d_in, size_t n, void* stream) {
     return fr_from_mont_device(d_out, d_in, n, (cudaStream_t)stream);
 }

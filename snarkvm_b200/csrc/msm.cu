@@ -104,10 +104,12 @@ MsmPlan msm_make_plan(size_t npoints) {
 // digit_w ∈ [-2^(c-1), 2^(c-1)]; returns magnitude and sign for window w given the
 // running carry (sequential over w).
 // ---------------------------------------------------------------------------
+// flat != 0 (precomputed tables 2^{c·w}·P_i): every window feeds the SAME bucket set and the entry names record
+// w·n + i of the table instead of point i.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ scalars, size_t n, int c, int nwin,
                                                 uint32_t nbuckets, uint32_t* __restrict__ counters /* hist or cursors */,
-                                                uint32_t* __restrict__ sorted) {
+                                                uint32_t* __restrict__ sorted, size_t flat /* 0, or the table's points per window */) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -130,10 +132,10 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
         uint32_t mag = neg ? (1u << c) - raw : raw;
         carry = neg;
         if (mag != 0u) {
-            uint32_t slot = (uint32_t)w * nbuckets + (mag - 1u);
+            uint32_t slot = (flat ? 0u : (uint32_t)w * nbuckets) + (mag - 1u);
             if (SCATTER) {
                 uint32_t pos = atomicAdd(&counters[slot], 1u);
-                sorted[pos] = (uint32_t)i | (neg << 31);
+                sorted[pos] = (uint32_t)(flat ? (size_t)w * flat + i : i) | (neg << 31);
             } else {
                 atomicAdd(&counters[slot], 1u);
             }
@@ -242,6 +244,25 @@ __global__ void k_densify_bases(const uint8_t* __restrict__ points, size_t strid
     DensePoint d; d.x = a.x; d.y = a.y; d.inf = a.inf;
     store_dense(out + i * BASE_WORDS, d);
 }
+// Precomputed tables for resident bases: record (w, i) = 2^{c·w}·P_i as a dense 128-byte affine record, w < nwin.
+// One thread per point walks the doubling chain in XYZZ and normalises every multiple (Fermat inversion each:
+// a one-off cost per SRS, ≈ 9k Fq mul per point).
+__global__ void __launch_bounds__(128) k_precompute_tables(const uint8_t* __restrict__ points, size_t stride, size_t n, int c, int nwin,
+                                                            uint32_t* __restrict__ table) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    AffinePoint a = load_affine(points, stride, i);
+    DensePoint d; d.x = a.x; d.y = a.y; d.inf = a.inf;
+    store_dense(table + i * BASE_WORDS, d);
+    XYZZ q = XYZZ::from_affine(a);
+    for (int w = 1; w < nwin; w++) {
+        for (int k = 0; k < c; k++) q.dbl();
+        AffinePoint t = q.to_affine();
+        d.x = t.x; d.y = t.y; d.inf = t.inf;
+        store_dense(table + ((size_t)w * n + i) * BASE_WORDS, d);
+    }
+}
+
 enum PairKind { PAIR_COPY1 = 0, PAIR_COPY2 = 1, PAIR_INF = 2, PAIR_ADD = 3, PAIR_DBL = 4 };
 FF_DEV int classify_pair(const DensePoint& P, const DensePoint& Q, bool has2, Fq& d) {
     if (!has2 || Q.inf) return PAIR_COPY1;
@@ -435,29 +456,35 @@ int xyzz_sum_ranks_device(uint32_t* d_out, const uint32_t* d_in, int nranks, int
     return (int)cudaGetLastError();
 }
 
-int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const void* d_points, size_t stride,
-                           const void* d_scalars, size_t npoints, cudaStream_t stream) {
+// table != nullptr: "flat" mode over precomputed tables (record w·table_n + i = 2^{c·w}·P_i): all windows share one bucket
+// set, so the pipeline sees ONE window of npoints·nwin entries and writes a single sum.
+static int msm_core(uint32_t* d_window_sums, const MsmPlan& plan, const void* d_points, size_t stride, const uint32_t* table,
+                    size_t table_n, const void* d_scalars, size_t npoints, cudaStream_t stream) {
     int rc = 0;
     ensure_pool_configured();
-    const uint32_t TB = (uint32_t)plan.nwin * plan.nbuckets;      // total buckets
+    const bool flat = table != nullptr;
+    const uint32_t nwin_red = flat ? 1u : (uint32_t)plan.nwin;    // bucket sets to reduce
+    const uint32_t TB = nwin_red * plan.nbuckets;                 // total buckets
     const size_t max_entries = npoints * (size_t)plan.nwin;
     if (npoints == 0 || npoints >= (1ull << 31) || max_entries >= (1ull << 32)) return (int)cudaErrorInvalidValue;
+    if (flat && (table_n * (size_t)plan.nwin >= (1ull << 31) || plan.levels < 1 || npoints > table_n)) return (int)cudaErrorInvalidValue;
     const int levels = plan.levels;
+    const size_t bucket_cap = flat ? max_entries : npoints;       // most entries a single bucket can hold
 
     // Everything after the bucket sort runs per GROUP of whole windows, so the dense scratch of the pair levels
     // (96 B per point per window) stays inside a budget: 2^24 points → all 15 windows at once (24 GB),
     // 2^26 points → 3 groups of 6/6/3 windows.
     size_t budget = (size_t)40 << 30;
     if (const char* e = getenv("SNARKVM_B200_MSM_SCRATCH_GB")) { long v = atol(e); if (v >= 1) budget = (size_t)v << 30; }
-    uint32_t gw = (uint32_t)plan.nwin;
-    if (levels > 0) {
+    uint32_t gw = nwin_red;
+    if (levels > 0 && !flat) {
         size_t per_window = npoints * (size_t)96 + 1;
         size_t fit = budget / per_window;
         if (fit < 1) fit = 1;
         if (fit < gw) gw = (uint32_t)fit;
     }
     const uint32_t TBg = gw * plan.nbuckets;                      // buckets of the largest group
-    const size_t entries_g = npoints * (size_t)gw;
+    const size_t entries_g = flat ? max_entries : npoints * (size_t)gw;
     const size_t max_items = (size_t)TBg + entries_g / plan.cap + 1;
 
     uint32_t *hist = nullptr, *bucket_start = nullptr, *cursors = nullptr, *items = nullptr, *item_start = nullptr;
@@ -492,7 +519,7 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
         CUDA_TRY(cudaMallocAsync(&dense_a, dense_cap_a * DENSE_WORDS * 4, stream));
         if (levels > 1) CUDA_TRY(cudaMallocAsync(&dense_b, dense_cap_b * DENSE_WORDS * 4, stream));
         CUDA_TRY(cudaMallocAsync(&prefix, dense_cap_a * 12 * 4, stream));
-        CUDA_TRY(cudaMallocAsync(&dense_bases, npoints * (size_t)BASE_WORDS * 4, stream));
+        if (!flat) CUDA_TRY(cudaMallocAsync(&dense_bases, npoints * (size_t)BASE_WORDS * 4, stream));
     }
     CUDA_TRY(cudaMallocAsync(&red_a, (size_t)gw * chunks_per_window * XYZZ_WORDS * 4, stream));
     CUDA_TRY(cudaMallocAsync(&red_b, (size_t)gw * (chunks_per_window / tree + 1) * XYZZ_WORDS * 4, stream));
@@ -505,22 +532,23 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
         const unsigned grid = (unsigned)((npoints + 255) / 256);
         {
             ProfScope sort_scope(PROF_MSM_SORT, stream);
-            k_digits<false><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, hist, nullptr);
+            k_digits<false><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, hist, nullptr, flat ? table_n : 0);
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, hist, bucket_start, (int)(TB + 1), stream));
             CUDA_TRY(cudaMemcpyAsync(cursors, bucket_start, (size_t)(TB + 1) * 4, cudaMemcpyDeviceToDevice, stream));
-            k_digits<true><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, cursors, sorted);
+            k_digits<true><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, cursors, sorted, flat ? table_n : 0);
             count_launch(4);
         }
-        if (levels > 0) {
+        const uint32_t* gather_src = flat ? table : dense_bases;
+        if (levels > 0 && !flat) {
             ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
             k_densify_bases<<<(unsigned)((npoints + 255) / 256), 256, 0, stream>>>((const uint8_t*)d_points, stride, npoints, dense_bases);
             count_launch();
         }
-        for (uint32_t w0 = 0; w0 < (uint32_t)plan.nwin; w0 += gw) {
-            const uint32_t wn = (uint32_t)plan.nwin - w0 < gw ? (uint32_t)plan.nwin - w0 : gw;     // windows in this group
+        for (uint32_t w0 = 0; w0 < nwin_red; w0 += gw) {
+            const uint32_t wn = nwin_red - w0 < gw ? nwin_red - w0 : gw;                           // windows (bucket sets) in this group
             const uint32_t tb = wn * plan.nbuckets;
             const uint32_t* bs = bucket_start + (size_t)w0 * plan.nbuckets;                       // tb + 1 absolute offsets into `sorted`
-            const size_t entries = npoints * (size_t)wn;
+            const size_t entries = flat ? max_entries : npoints * (size_t)wn;
             size_t items_bound = 1;                                                                // ≥ item count of any single bucket
             const uint32_t* final_partial = nullptr;
             const uint32_t* final_start = nullptr;
@@ -530,7 +558,7 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
                 CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(tb + 1), stream));
                 count_launch(3);
                 const size_t group_items = (size_t)tb + entries / plan.cap + 1;
-                items_bound = npoints / plan.cap + 1;                   // a bucket belongs to one window: ≤ n entries
+                items_bound = bucket_cap / plan.cap + 1;                // a bucket belongs to one window: ≤ n entries
                 ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
                 k_bucket_accumulate<<<(unsigned)((group_items + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
                     (const uint8_t*)d_points, stride, sorted, bs, item_start, tb, plan.cap, partial);
@@ -559,7 +587,7 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
                     // level 0 reads absolute positions of `sorted` (off_in = bs); its outputs and all later levels are
                     // group-relative (the scans start at 0)
                     if (l == 0)
-                        k_pair_level<true><<<lgrid, 128, 0, stream>>>(dense_bases, sorted, nullptr, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
+                        k_pair_level<true><<<lgrid, 128, 0, stream>>>(gather_src, sorted, nullptr, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
                     else
                         k_pair_level<false><<<lgrid, 128, 0, stream>>>(nullptr, nullptr, dense_in, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
                     count_launch(4);
@@ -569,7 +597,7 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
                 k_items_from_offsets<<<(tb + 256) / 256, 256, 0, stream>>>(off_in, items, tb, plan.cap);
                 CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(tb + 1), stream));
                 const size_t group_items = (size_t)tb + bound / plan.cap + 1;
-                items_bound = ((npoints >> levels) + 1) / plan.cap + 1;
+                items_bound = ((bucket_cap >> levels) + 1) / plan.cap + 1;
                 k_bucket_accumulate_dense<<<(unsigned)((group_items + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
                     dense_in, off_in, item_start, tb, plan.cap, partial);
                 count_launch(4);
@@ -618,10 +646,48 @@ done:
     cudaFreeAsync(hist, stream); cudaFreeAsync(bucket_start, stream); cudaFreeAsync(cursors, stream);
     cudaFreeAsync(items, stream); cudaFreeAsync(item_start, stream); cudaFreeAsync(sorted, stream);
     cudaFreeAsync(off_a, stream); cudaFreeAsync(off_b, stream); cudaFreeAsync(dense_a, stream); cudaFreeAsync(dense_b, stream);
-    cudaFreeAsync(prefix, stream); cudaFreeAsync(dense_bases, stream);
+    cudaFreeAsync(prefix, stream); if (dense_bases) cudaFreeAsync(dense_bases, stream);
     cudaFreeAsync(partial2, stream); cudaFreeAsync(items2, stream);
     cudaFreeAsync(partial, stream); cudaFreeAsync(red_a, stream); cudaFreeAsync(red_b, stream); cudaFreeAsync(cub_tmp, stream);
     return rc;
+}
+
+int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const void* d_points, size_t stride,
+                           const void* d_scalars, size_t npoints, cudaStream_t stream) {
+    return msm_core(d_window_sums, plan, d_points, stride, nullptr, 0, d_scalars, npoints, stream);
+}
+
+MsmPlan msm_make_plan_precomputed(size_t npoints) {
+    MsmPlan p;
+    int lg = ceil_log2(npoints < 2 ? 2 : npoints);
+    // one bucket set for all windows ⇒ the bucket reduction is paid once and wide windows are cheap: c = 22 at 2^24
+    // (12 windows instead of 15).  Swept on a B200 with tools/tune_precomputed.py (profiles/tune_precomputed_r1.log).
+    int c = lg >= 24 ? 22 : lg >= 22 ? lg - 2 : lg >= 20 ? lg - 3 : lg >= 8 ? lg - 2 : 6;
+    if (const char* e = getenv("SNARKVM_B200_MSM_PRE_C")) { int v = atoi(e); if (v >= 2 && v <= 24) c = v; }
+    p.c = c;
+    p.nwin = 253 / c + 1;
+    p.nbuckets = 1u << (c - 1);
+    size_t total = npoints * (size_t)p.nwin;
+    size_t cap = total / 300000 + 1;
+    if (cap < 16) cap = 16;
+    p.cap = (uint32_t)cap;
+    int levels = lg >= 24 ? 3 : lg >= 22 ? 2 : 1;
+    if (const char* e = getenv("SNARKVM_B200_MSM_PRE_LEVELS")) { int v = atoi(e); if (v >= 1 && v <= 16) levels = v; }
+    p.levels = levels;
+    return p;
+}
+
+int msm_precompute_tables_device(uint32_t* d_table, const MsmPlan& plan, const void* d_points, size_t stride, size_t npoints,
+                                 cudaStream_t stream) {
+    if (stride < 104 || (stride & 7) || npoints == 0) return (int)cudaErrorInvalidValue;
+    k_precompute_tables<<<(unsigned)((npoints + 127) / 128), 128, 0, stream>>>((const uint8_t*)d_points, stride, npoints, plan.c, plan.nwin, d_table);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int msm_precomputed_sum_device(uint32_t* d_sum, const MsmPlan& plan, const uint32_t* d_table, size_t table_n, const void* d_scalars,
+                               size_t nscalars, cudaStream_t stream) {
+    return msm_core(d_sum, plan, nullptr, 0, d_table, table_n, d_scalars, nscalars, stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -40,6 +40,13 @@ MsmPlan msm_make_plan(size_t npoints);
 int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const void* d_points, size_t stride,
                            const void* d_scalars, size_t npoints, cudaStream_t stream);
 
+// Resident bases with precomputed tables 2^{c·w}·P_i (w < nwin; 128 B per record): all windows then share ONE bucket set, so
+// wide windows are cheap (c = 22, 12 windows at 2^24 instead of 17 / 15).  Table size: npoints · nwin · 128 B.
+MsmPlan msm_make_plan_precomputed(size_t npoints);
+int msm_precompute_tables_device(uint32_t* d_table, const MsmPlan& plan, const void* d_points, size_t stride, size_t npoints, cudaStream_t stream);
+// d_sum: ONE XYZZ point (192 B) = Σ scalars[i]·P_i over the first nscalars (≤ table_n) points
+int msm_precomputed_sum_device(uint32_t* d_sum, const MsmPlan& plan, const uint32_t* d_table, size_t table_n, const void* d_scalars, size_t nscalars, cudaStream_t stream);
+
 // Deterministic test/bench input: P_i = h(seed, i)·G with a 64-bit multiplier h
 // (every point is in the prime-order subgroup because G is).  Writes the reference
 // affine layout with the given stride.

@@ -129,6 +129,51 @@ def kzg_commit(powers: torch.Tensor, coeffs_mont: torch.Tensor, stride: int = AF
     return out
 
 
+class PrecomputedBases:
+    """A fixed base set with its tables 2^{c·w}·P_i resident in HBM (snarkvm_b200_msm_precompute_device): MSMs over it use one
+    bucket set for all windows.  `msm(scalars)` / `kzg_commit(coeffs_mont)` take the first len(scalars) bases, like
+    `&powers_of_beta_g[..len]` in KZG10::commit (kzg10/mod.rs:121-135)."""
+
+    def __init__(self, bases: torch.Tensor, stride: int = AFFINE_STRIDE):
+        npoints = _nbytes(bases) // stride
+        self.device = bases.device
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().snarkvm_b200_msm_precompute_device(ctypes.byref(h), _check(bases, "bases"), npoints, stride, _stream()))
+        self._h = h
+        n, c, nwin, tb = ctypes.c_size_t(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
+        _lib.check(_lib.lib().snarkvm_b200_msm_precomputed_info(h, ctypes.byref(n), ctypes.byref(c), ctypes.byref(nwin), ctypes.byref(tb)))
+        self.npoints, self.c, self.nwin, self.table_bytes = n.value, c.value, nwin.value, tb.value
+
+    def _run(self, fn, scalars: torch.Tensor) -> np.ndarray:
+        if self._h is None:
+            raise ValueError("PrecomputedBases was freed")
+        n = _nbytes(scalars) // 32
+        if n > self.npoints:
+            raise ValueError("more scalars than bases")
+        out = np.zeros(18, dtype=np.uint64)
+        with torch.cuda.device(self.device):
+            _lib.check(fn(out.ctypes.data, self._h, _check(scalars, "scalars") if n else None, n, _stream()))
+        return out
+
+    def msm(self, scalars: torch.Tensor) -> np.ndarray:
+        return self._run(_lib.lib().snarkvm_b200_msm_precomputed_device, scalars)
+
+    def kzg_commit(self, coeffs_mont: torch.Tensor) -> np.ndarray:
+        return self._run(_lib.lib().snarkvm_b200_kzg_commit_precomputed_device, coeffs_mont)
+
+    def free(self) -> None:
+        if self._h is not None:
+            _lib.check(_lib.lib().snarkvm_b200_msm_precomputed_free(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def fr_from_mont(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(x)
     with torch.cuda.device(x.device):

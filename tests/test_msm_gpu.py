@@ -328,3 +328,64 @@ def test_srs_decode_real_powers(oracle_cpu):
     assert g[12].tobytes() == py.affine_bytes(None)
     keep = [i for i in range(512) if i not in (5, 9, 12)]
     assert (g[keep] == affine_array(pts)[keep]).all()
+
+
+@pytest.mark.parametrize("n,pre_c,pre_levels", [(3000, 5, 1), (3000, 7, 3), (1 << 14, None, None), (1 << 17, None, None)])
+def test_precomputed_bases_vs_oracle(oracle_cpu, bases64k, monkeypatch, n, pre_c, pre_levels):
+    """Fixed-base tables 2^{c·w}·P_i (snarkvm_b200_msm_precompute_device): same group element as the oracle MSM, for full and
+    prefix lengths (kzg10/mod.rs:121-135 slices the powers), with the pair-level special cases in play (equal / opposite points,
+    ∞ bases, hot buckets — now ACROSS windows, since all windows share one bucket set)."""
+    from snarkvm_b200 import device
+    if pre_c is not None:
+        monkeypatch.setenv("SNARKVM_B200_MSM_PRE_C", str(pre_c))
+        monkeypatch.setenv("SNARKVM_B200_MSM_PRE_LEVELS", str(pre_levels))
+    if n <= (1 << 16):
+        bases = bases64k[:n].copy()
+        bases[48:64, 96] = 1
+        bases[100:301] = bases[400]
+        neg = affine_array([py.g1_neg(py.affine_from_bytes(bases[500].tobytes()))])[0]
+        bases[501:521:2] = neg; bases[502:522:2] = bases[500]
+        dbases = _dev(bases)
+    else:
+        dbases = device.generate_bases(n, seed=77)
+        bases = dbases.cpu().numpy()
+    pre = device.PrecomputedBases(dbases)
+    assert pre.npoints == n and pre.table_bytes == n * pre.nwin * 128
+    scal = random_canonical_fr(n, seed=60 + (pre_c or 0))
+    scal[0:16] = 0
+    scal[16:32] = scalars_from_ints([1])[0]
+    scal[32:48] = scalars_from_ints([py.R_MOD - 1])[0]
+    scal[100:301] = scal[400]
+    scal[500:522] = scal[500]
+    assert (pre.msm(_dev(scal)) == oracle_cpu.msm(bases, scal, 1)).all()
+    for m in (1, 2, 700, n - 1):
+        assert (pre.msm(_dev(scal[:m])) == oracle_cpu.msm(bases[:m], scal[:m], 1)).all(), m
+    same = np.tile(scal[700:701], (n, 1))
+    assert (pre.msm(_dev(same)) == oracle_cpu.msm(bases, same, 1)).all()
+    inf = np.frombuffer(py.projective_bytes_normalised(None), dtype=np.uint64)
+    assert (pre.msm(_dev(np.zeros((n, 4), dtype=np.uint64))) == inf).all()
+    assert (pre.msm(_dev(scal)[:0]) == inf).all()
+    # KZG commit over the table: Montgomery coefficients in, to_bigint on the device
+    coeffs = random_canonical_fr(n, seed=61)
+    assert (pre.kzg_commit(_dev(coeffs)) == oracle_cpu.msm(bases, oracle_cpu.fr_from_mont(coeffs), 1)).all()
+    with pytest.raises(ValueError):
+        pre.msm(_dev(random_canonical_fr(n + 1, seed=1)))
+    pre.free()
+
+
+def test_precomputed_bases_full_size(oracle_cpu):
+    """2^22 points through the closed form Σ s_i·k_i·G (bases are known multiples of G) and against the windowed path"""
+    from snarkvm_b200 import device
+    lg = 22
+    n = 1 << lg
+    seed = 2000 + lg
+    bases = device.generate_bases(n, seed)
+    pre = device.PrecomputedBases(bases)
+    scal = random_canonical_fr(n, seed=lg + 7)
+    got = pre.msm(_dev(scal))
+    ks = np.zeros((n, 4), dtype=np.uint64)
+    ks[:, 0] = generated_base_multipliers(seed, n)
+    g = affine_array([py.G1_GENERATOR])[0]
+    assert (got == oracle_cpu.g1_mul(g, oracle_cpu.fr_dot_canonical(scal, ks))).all()
+    assert (got == device.msm(bases, _dev(scal))).all()
+    pre.free()
