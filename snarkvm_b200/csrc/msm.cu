@@ -78,7 +78,7 @@ MsmPlan msm_make_plan(size_t npoints) {
     int lg = ceil_log2(npoints < 2 ? 2 : npoints);
     // Window bits from a sweep on B200 (tools/tune_msm.py, profiles/tune_msm_r1.log): wider windows mean fewer
     // bucket additions (n·W) but more buckets to reduce and shorter, more divergent bucket runs.
-    int c = lg <= 8 ? 4 : lg <= 12 ? lg - 4 : lg <= 18 ? 11 : lg <= 20 ? 16 : 17;
+    int c = lg <= 8 ? 4 : lg <= 12 ? lg - 4 : lg <= 18 ? 11 : lg == 19 ? 16 : lg == 20 ? 15 : lg <= 22 ? 16 : 17;
     if (const char* e = getenv("SNARKVM_B200_MSM_C")) { int v = atoi(e); if (v >= 2 && v <= 24) c = v; }
     p.c = c;
     p.nwin = 253 / c + 1;
@@ -91,8 +91,8 @@ MsmPlan msm_make_plan(size_t npoints) {
     if (const char* e = getenv("SNARKVM_B200_MSM_CAP")) { long v = atol(e); if (v >= 1) cap = (size_t)v; }
     p.cap = (uint32_t)cap;
     // Batched-affine pair levels before the XYZZ accumulation pay off only when every level still fills the
-    // GPU (same sweep): none up to 2^20 points, 2 at 2^21–2^22, 4 from 2^23, if the dense scratch fits.
-    int levels = lg >= 23 ? 4 : lg >= 21 ? 2 : 0;
+    // GPU (tools/ab_pair.py sweep after the CTA-shared inversion): none below 2^20 points, 1 at 2^20, 4 from 2^21.
+    int levels = lg >= 21 ? 4 : lg == 20 ? 1 : 0;
     while (levels > 0 && ((npoints >> (c - 1)) >> levels) < 2) levels--;
     if (const char* e = getenv("SNARKVM_B200_MSM_LEVELS")) { int v = atoi(e); if (v >= 0 && v <= 16) levels = v; }
     p.levels = levels;
@@ -263,6 +263,59 @@ __global__ void __launch_bounds__(128) k_precompute_tables(const uint8_t* __rest
     }
 }
 
+static constexpr int PAIR_THREADS = 128;
+FF_DEV Fq shfl_up_fq(const Fq& a, int d) {
+    Fq r;
+#pragma unroll
+    for (int j = 0; j < 12; j++) r.v[j] = __shfl_up_sync(0xffffffffu, a.v[j], d);
+    return r;
+}
+FF_DEV Fq shfl_down_fq(const Fq& a, int d) {
+    Fq r;
+#pragma unroll
+    for (int j = 0; j < 12; j++) r.v[j] = __shfl_down_sync(0xffffffffu, a.v[j], d);
+    return r;
+}
+FF_DEV Fq shfl_idx_fq(const Fq& a, int l) {
+    Fq r;
+#pragma unroll
+    for (int j = 0; j < 12; j++) r.v[j] = __shfl_sync(0xffffffffu, a.v[j], l);
+    return r;
+}
+// One Fermat inversion per CTA instead of one per warp-lane: the 128 running products (all non-zero) go through shared memory,
+// ONE warp multiplies them together (4 per lane, then a shuffle scan across lanes), inverts the total and unwinds.  In SIMT
+// time an inversion costs a warp ≈ 515 Fq mul whether 1 or 32 lanes need it, so the per-thread version spends 4 × 515 per
+// CTA and this one ≈ 540.  The inverting warp rotates with blockIdx so co-resident CTAs load different SM sub-partitions.
+__device__ __noinline__ Fq cta_shared_inverse(const Fq& run, uint32_t* sh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    run.store(sh + tid * 12);
+    __syncthreads();
+    if (warp == (int)(blockIdx.x & 3u)) {
+        uint32_t* mine = sh + lane * 48;
+        Fq a0 = Fq::load(mine), a1 = Fq::load(mine + 12), a2 = Fq::load(mine + 24), a3 = Fq::load(mine + 36);
+        Fq p1 = a0 * a1, p2 = p1 * a2, p3 = p2 * a3;
+        Fq incl = p3, suff = p3;                           // inclusive prefix / suffix products over lanes
+#pragma unroll 1
+        for (int d = 1; d < 32; d <<= 1) {
+            Fq up = shfl_up_fq(incl, d), dn = shfl_down_fq(suff, d);
+            if (lane >= d) incl = incl * up;
+            if (lane + d < 32) suff = suff * dn;
+        }
+        Fq tinv = shfl_idx_fq(incl, 31).inverse();
+        Fq before = shfl_up_fq(incl, 1), after = shfl_down_fq(suff, 1);
+        Fq ip3 = tinv;                                     // 1 / p3 of this lane = tinv · Π(other lanes)
+        if (lane > 0) ip3 = ip3 * before;
+        if (lane < 31) ip3 = ip3 * after;
+        Fq ip2 = ip3 * a3, ip1 = ip2 * a2;
+        (ip3 * p2).store(mine + 36);                       // 1/a3
+        (ip2 * p1).store(mine + 24);                       // 1/a2
+        (ip1 * a0).store(mine + 12);                       // 1/a1
+        (ip1 * a1).store(mine);                            // 1/a0
+    }
+    __syncthreads();
+    return Fq::load(sh + tid * 12);
+}
+
 enum PairKind { PAIR_COPY1 = 0, PAIR_COPY2 = 1, PAIR_INF = 2, PAIR_ADD = 3, PAIR_DBL = 4 };
 FF_DEV int classify_pair(const DensePoint& P, const DensePoint& Q, bool has2, Fq& d) {
     if (!has2 || Q.inf) return PAIR_COPY1;
@@ -276,18 +329,20 @@ FF_DEV int classify_pair(const DensePoint& P, const DensePoint& Q, bool has2, Fq
 }
 
 template <bool GATHER>
-__global__ void __launch_bounds__(128, 4) k_pair_level(const uint32_t* __restrict__ dense_bases,
+__global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair_level(const uint32_t* __restrict__ dense_bases,
                                                         const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ dense_in,
                                                         const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out,
                                                         uint32_t total_buckets, uint32_t T, uint32_t* __restrict__ prefix,
                                                         uint32_t* __restrict__ dense_out) {
+    __shared__ uint4 sh_inv4[PAIR_THREADS * 3];           // one Fq per thread for the CTA-wide shared inversion
+    uint32_t* sh_inv = reinterpret_cast<uint32_t*>(sh_inv4);
     const uint32_t total = off_out[total_buckets];
     const uint64_t o0_64 = (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * T;
-    if (o0_64 >= total) return;
-    const uint32_t o0 = (uint32_t)o0_64;
+    // threads past the end stay for the barriers of the shared inversion with an empty range
+    const uint32_t o0 = o0_64 < total ? (uint32_t)o0_64 : total;
     const uint32_t o1 = (o0_64 + T < total) ? o0 + T : total;
     uint32_t lo = 0, hi = total_buckets;                  // off_out[lo] <= o0 < off_out[hi]
-    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (off_out[mid] <= o0) lo = mid; else hi = mid; }
+    if (o0 < o1) while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (off_out[mid] <= o0) lo = mid; else hi = mid; }
     uint32_t b = lo;
 
     // ---- forward: running product of denominators (x coordinates only on the common path) ----
@@ -313,7 +368,7 @@ __global__ void __launch_bounds__(128, 4) k_pair_level(const uint32_t* __restric
         }
         run.store(prefix + (size_t)o * 12);
     }
-    Fq inv = run.inverse();
+    Fq inv = cta_shared_inverse(run, sh_inv);
     // ---- backward: one inverse per pair, then the affine addition / doubling ----
     for (uint32_t o = o1; o-- > o0;) {
         while (o < off_out[b]) b--;
