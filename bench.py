@@ -365,6 +365,36 @@ def run_product(args, rank, world, local_rank):
         kzg_ms = max_over_ranks(e0.elapsed_time(e1)) / 5
         kzg = {"metric": "kzg10_commit_coefficients_per_sec", "value": nk * world / (kzg_ms * 1e-3), "unit": "coefficients/s",
                "ms_per_commit": kzg_ms, "workload": f"2^{args.kzg_lg}-coefficient polynomial, powers resident in HBM, per GPU"}
+        # same commitment over precomputed tables 2^{c·w}·P_i of the powers (one bucket set for all windows)
+        t0 = time.perf_counter()
+        pre = device.PrecomputedBases(powers)
+        torch.cuda.synchronize()
+        pre_s = time.perf_counter() - t0
+        assert (pre.kzg_commit(coeffs) == device.kzg_commit(powers, coeffs)).all()
+        for _ in range(2):
+            pre.kzg_commit(coeffs)
+        barrier()
+        e0.record()
+        for _ in range(5):
+            pre.kzg_commit(coeffs)
+        e1.record()
+        barrier()
+        pre_ms = max_over_ranks(e0.elapsed_time(e1)) / 5
+        kzg["precomputed_tables"] = {"value": nk * world / (pre_ms * 1e-3), "unit": "coefficients/s", "ms_per_commit": pre_ms,
+                                     "window_bits": pre.c, "windows": pre.nwin, "table_bytes": pre.table_bytes,
+                                     "one_time_precompute_s": pre_s}
+        pre.free()
+        # UniversalParams::lagrange_basis: iFFT over G1 points (data_structures.rs:68-72)
+        ng = 1 << args.g1_ntt_lg
+        gp = powers.reshape(-1)[: ng * 104].contiguous()
+        device.lagrange_basis(gp)
+        barrier()
+        e0.record()
+        device.lagrange_basis(gp)
+        e1.record()
+        barrier()
+        kzg["lagrange_basis"] = {"ms": max_over_ranks(e0.elapsed_time(e1)), "workload": f"ifft of 2^{args.g1_ntt_lg} G1 points per GPU",
+                                 "unit": "ms"}
 
     if rank != 0:
         return
@@ -390,7 +420,7 @@ def run_product(args, rank, world, local_rank):
                                    "sample": f"one 2^{args.cpu_ntt_lg} forward fft_in_place ({ndt:.2f} s), best team size of 16/32/64/all"}
 
     plan = device.msm_plan(n)
-    plan_levels = 4 if args.lg >= 23 else 2 if args.lg >= 21 else 0      # msm_make_plan (csrc/msm.cu)
+    plan_levels = 4 if args.lg >= 21 else 1 if args.lg == 20 else 0      # msm_make_plan (csrc/msm.cu)
     line = {
         "metric": "bls12_377_g1_msm_points_per_sec", "value": value, "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -435,6 +465,7 @@ def main():
     ap.add_argument("--ref-lg", type=int, default=20, help="--impl reference: points per step")
     ap.add_argument("--ref-ntt-lg", type=int, default=22)
     ap.add_argument("--kzg-lg", type=int, default=22)
+    ap.add_argument("--g1-ntt-lg", type=int, default=12, help="size of the G1 iFFT (lagrange_basis) timed inside the KZG extra")
     ap.add_argument("--skip-kzg", action="store_true")
     ap.add_argument("--skip-ntt", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

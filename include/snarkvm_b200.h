@@ -122,6 +122,32 @@ SNARKVM_API int snarkvm_b200_msm_precomputed_device(void* out144, const void* ha
 SNARKVM_API int snarkvm_b200_kzg_commit_precomputed_device(void* out144, const void* handle, const void* d_coeffs_mont, size_t ncoeffs,
                                                            void* stream);
 
+/* KZG10::commit with hiding_bound = Some(_) (polycommit/kzg10/mod.rs:98-156): MSM(powers_of_beta_g, coeffs) +
+ * MSM(powers_of_beta_times_gamma_g, blinding coefficients).  The caller samples the blinding polynomial; all coefficient arrays are
+ * Montgomery Fr in HBM; nblinding = 0 gives the plain commitment. */
+SNARKVM_API int snarkvm_b200_kzg_commit_hiding_device(void* out144, const void* d_powers, size_t stride, const void* d_coeffs_mont,
+                                                      size_t ncoeffs, const void* d_gamma_powers, const void* d_blinding_mont,
+                                                      size_t nblinding, void* stream);
+/* `count` commitments against the same resident powers (one prover round, polycommit/sonic_pc/mod.rs:177-257).
+ * d_coeffs_mont / ncoeffs: HOST arrays of device pointers / lengths; out144s: count * 144 B of HOST memory. */
+SNARKVM_API int snarkvm_b200_kzg_commit_batch_device(void* out144s, const void* d_powers, size_t stride, const void* const* d_coeffs_mont,
+                                                     const size_t* ncoeffs, size_t count, void* stream);
+
+/* FFT over G1 points (EvaluationDomain::{fft,ifft} with T = G1Projective, fft/domain.rs:169-221): 2^lg affine points in, affine
+ * points out, natural order.  direction 1 = inverse, which is UniversalParams::lagrange_basis
+ * (polycommit/kzg10/data_structures.rs:68-72): the commitment key for commit_lagrange (kzg10/mod.rs:159-206). */
+SNARKVM_API int snarkvm_b200_g1_ntt_device(void* d_out, size_t out_stride, const void* d_in, size_t in_stride, uint32_t lg, int direction,
+                                           void* stream);
+
+/* batch_inversion_and_mul (fields/src/lib.rs:78-129): v_i <- coeff * v_i^{-1} in place, zeros stay zero.  coeff: 32 B HOST. */
+SNARKVM_API int snarkvm_b200_fr_batch_inversion_and_mul_device(void* d_v, size_t n, const void* coeff_mont_host, void* stream);
+/* DensePolynomial::divide_by_vanishing_poly (fft/polynomial/dense.rs:162-169): p (m coefficients) = q * (x^n - 1) + r;
+ * d_q receives max(m - n, 0) coefficients, d_r receives min(m, n) (neither trimmed). */
+SNARKVM_API int snarkvm_b200_poly_divide_by_vanishing_device(void* d_q, void* d_r, const void* d_p, size_t m, size_t n, void* stream);
+/* DensePolynomial::evaluate (fft/polynomial/dense.rs:98-114): out = sum c_i * point^i; out and point are 32-byte HOST buffers. */
+SNARKVM_API int snarkvm_b200_poly_evaluate_device(void* out_mont_host, const void* d_coeffs, size_t m, const void* point_mont_host,
+                                                  void* stream);
+
 /* Fr Montgomery <-> canonical, n elements in HBM (to_bigint / from_bigint, fields/src/fp_256.rs:362-413). */
 SNARKVM_API int snarkvm_b200_fr_from_mont_device(void* d_out, const void* d_in, size_t n, void* stream);
 SNARKVM_API int snarkvm_b200_fr_to_mont_device(void* d_out, const void* d_in, size_t n, void* stream);

@@ -192,3 +192,47 @@ def fr_dot_canonical(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     out = np.zeros(4, dtype=np.uint64)
     lib().oracle_fr_dot_canonical(_p(out), _p(a), _p(b), ctypes.c_size_t(a.shape[0]))
     return out
+
+
+# ---- next-row oracles (SURVEY §8 f1–f4) ----
+def g1_ifft(bases: np.ndarray) -> np.ndarray:
+    """UniversalParams::lagrange_basis (kzg10/data_structures.rs:68-72): group iFFT of n = 2^k affine points → affine [n, 104]."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8).reshape(-1, 104)
+    n = bases.shape[0]
+    lg = n.bit_length() - 1
+    assert 1 << lg == n
+    out = np.zeros_like(bases)
+    lib().oracle_g1_ifft.restype = ctypes.c_int
+    assert lib().oracle_g1_ifft(_p(out), _p(bases), ctypes.c_uint32(lg)) == 0
+    return out
+
+
+def fr_batch_inversion_and_mul(v: np.ndarray, coeff: np.ndarray) -> np.ndarray:
+    """fields/src/lib.rs:78-129 on Montgomery [n, 4] arrays (out of place); zeros stay zero."""
+    v = np.array(v, dtype=np.uint64, order="C", copy=True).reshape(-1, 4)
+    c = np.ascontiguousarray(coeff, dtype=np.uint64).reshape(4)
+    lib().oracle_fr_batch_inversion_and_mul(_p(v), ctypes.c_size_t(v.shape[0]), _p(c))
+    return v
+
+
+def poly_divide_by_vanishing(p: np.ndarray, n: int):
+    """DensePolynomial::divide_by_vanishing_poly (dense.rs:162-169): (q [max(m−n,0), 4], r [min(m,n), 4]), untrimmed."""
+    p = np.ascontiguousarray(p, dtype=np.uint64).reshape(-1, 4)
+    m = p.shape[0]
+    q = np.zeros((max(m - n, 0), 4), dtype=np.uint64)
+    r = np.zeros((min(m, n), 4), dtype=np.uint64)
+    qd = np.zeros((max(q.shape[0], 1), 4), dtype=np.uint64)
+    rd = np.zeros((max(r.shape[0], 1), 4), dtype=np.uint64)
+    lib().oracle_poly_divide_by_vanishing.restype = ctypes.c_size_t
+    lib().oracle_poly_divide_by_vanishing(_p(qd), _p(rd), _p(p), ctypes.c_size_t(m), ctypes.c_size_t(n))
+    q[:] = qd[:q.shape[0]]
+    r[:] = rd[:r.shape[0]]
+    return q, r
+
+
+def poly_evaluate(coeffs: np.ndarray, point: np.ndarray) -> np.ndarray:
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+    z = np.ascontiguousarray(point, dtype=np.uint64).reshape(4)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().oracle_poly_evaluate(_p(out), _p(coeffs), ctypes.c_size_t(coeffs.shape[0]), _p(z))
+    return out

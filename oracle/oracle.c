@@ -123,6 +123,7 @@ INL void fr_sub(fr_t *r, const fr_t *a, const fr_t *b) { fp_sub(r->l, a->l, b->l
 INL void fr_mul(fr_t *r, const fr_t *a, const fr_t *b) { fp_mul(r->l, a->l, b->l, FR_MOD, FR_INV, 4); }
 INL void fr_sqr(fr_t *r, const fr_t *a) { fp_mul(r->l, a->l, a->l, FR_MOD, FR_INV, 4); }
 static int fr_inverse(fr_t *r, const fr_t *a) { return fp_inverse(r->l, a->l, FR_MOD, FR_R2, 4); }
+INL int fr_is_zero(const fr_t *a) { return bn_is_zero(a->l, 4); }
 static fr_t fr_one(void) { fr_t o; memcpy(o.l, FR_R, 32); return o; }
 static fr_t fr_pow_u64(const fr_t *a, uint64_t e) {
     fr_t acc = fr_one(), b = *a;
@@ -754,6 +755,125 @@ API int oracle_polymul(uint64_t *out, size_t pcount, const uint64_t *const *poly
     ifft_in_place(acc, lg, 0);
     free(tmp);
     return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* Next-row oracles (SURVEY §8 f1–f4)                                  */
+/* ------------------------------------------------------------------ */
+/* Projective · Fr.  The reference routes `Projective * ScalarField` (projective.rs:488-504) through the curve's
+ * mul_projective (GLV for BLS12-377 G1); the group element is the same whichever ladder computes it, and every
+ * comparison is made on the affine image, so this is plain MSB-first double-and-add over scalar.to_bigint(). */
+static g1_proj_t proj_mul_fr(const g1_proj_t *p, const fr_t *scalar_mont) {
+    fr_t one = {{1, 0, 0, 0}}, s; fr_mul(&s, scalar_mont, &one);
+    g1_proj_t out = proj_zero();
+    int started = 0;
+    for (int bit = 255; bit >= 0; bit--) {
+        int b = (s.l[bit >> 6] >> (bit & 63)) & 1;
+        if (!started) { if (!b) continue; started = 1; }
+        proj_double(&out);
+        if (b) proj_add(&out, p);
+    }
+    return out;
+}
+static void proj_neg(g1_proj_t *p) { if (!fq_is_zero(&p->y)) { fq_t z = fq_zero(); fq_sub(&p->y, &z, &p->y); } }
+
+/* UniversalParams::lagrange_basis — polycommit/kzg10/data_structures.rs:68-72:
+ *   domain.ifft(powers_of_beta_g[0..n].to_projective()) then batch_normalization_into_affine.
+ * ifft over T = G1Projective is the generic in_order_ifft_in_place (domain.rs:403-422; the GPU branch needs
+ * size_of::<T>() == 32): derange → oi_helper (butterfly_fn_oi :659-664: hi *= root; neg = lo − hi; lo += hi; hi = neg)
+ * → every value *= size_inv. */
+API int oracle_g1_ifft(void *out104, const void *in104, uint32_t lg) {
+    if (lg > 30) return 1;
+    size_t n = (size_t)1 << lg;
+    g1_proj_t *x = (g1_proj_t *)malloc(n * sizeof *x);
+    for (size_t i = 0; i < n; i++) { g1_affine_t a; memcpy(&a, (const uint8_t *)in104 + i * 104, 104); a.inf = a.inf != 0; x[i] = aff_to_proj(&a); }
+    fr_t size_inv = fr_from_u64(n); fr_inverse(&size_inv, &size_inv);
+    if (n > 1) {
+        fr_t w = fr_root_of_unity(lg), wi; fr_inverse(&wi, &w);
+        fr_t *roots = roots_of_unity(&wi, n / 2);
+        for (size_t i = 1; i + 1 < n; i++) {                 /* derange */
+            size_t r = 0, v = i;
+            for (unsigned b = 0; b < lg; b++) { r = (r << 1) | (v & 1); v >>= 1; }
+            if (i < r) { g1_proj_t t = x[i]; x[i] = x[r]; x[r] = t; }
+        }
+        for (size_t gap = 1; gap < n; gap *= 2) {
+            size_t chunk = 2 * gap, num_chunks = n / chunk;
+#pragma omp parallel for schedule(dynamic, 16)
+            for (size_t b = 0; b < n / 2; b++) {
+                size_t ch = b / gap, k = b % gap;
+                g1_proj_t *lo = &x[ch * chunk + k], *hi = lo + gap;
+                g1_proj_t t = proj_mul_fr(hi, &roots[k * num_chunks]);
+                g1_proj_t neg = t; proj_neg(&neg);
+                g1_proj_t d = *lo; proj_add(&d, &neg);
+                proj_add(lo, &t);
+                *hi = d;
+            }
+        }
+        free(roots);
+    }
+#pragma omp parallel for schedule(dynamic, 16)
+    for (size_t i = 0; i < n; i++) {
+        g1_proj_t v = proj_mul_fr(&x[i], &size_inv);
+        g1_affine_t a = proj_to_affine(&v);
+        memcpy((uint8_t *)out104 + i * 104, &a, 104);
+    }
+    free(x);
+    return 0;
+}
+
+/* serial_batch_inversion_and_mul — fields/src/lib.rs:93-129: v_i ← coeff · v_i^{-1}, zeros stay zero */
+API void oracle_fr_batch_inversion_and_mul(uint64_t *v, size_t n, const uint64_t *coeff) {
+    fr_t *x = (fr_t *)v;
+    fr_t *prod = (fr_t *)malloc((n ? n : 1) * sizeof *prod);
+    size_t m = 0;
+    fr_t tmp = fr_one();
+    for (size_t i = 0; i < n; i++) if (!fr_is_zero(&x[i])) { fr_mul(&tmp, &tmp, &x[i]); prod[m++] = tmp; }
+    fr_inverse(&tmp, &tmp);
+    fr_mul(&tmp, &tmp, (const fr_t *)coeff);
+    for (size_t i = n; i-- > 0;) {
+        if (fr_is_zero(&x[i])) continue;
+        m--;
+        fr_t s = m ? prod[m - 1] : fr_one(), new_tmp;
+        fr_mul(&new_tmp, &tmp, &x[i]);
+        fr_mul(&x[i], &tmp, &s);
+        tmp = new_tmp;
+    }
+    free(prod);
+}
+
+/* DensePolynomial::divide_by_vanishing_poly — fft/polynomial/dense.rs:162-169 → divide_with_q_and_r
+ * (fft/polynomial/mod.rs:222-256) with the sparse divisor x^n − 1 (domain.rs vanishing_polynomial).
+ * p has m coefficients (trailing zeros allowed); q gets max(m − n, 0) and r gets min(m, n) coefficient slots
+ * (the caller trims leading-zero high coefficients as DensePolynomial does).  Returns the quotient length. */
+API size_t oracle_poly_divide_by_vanishing(uint64_t *q_out, uint64_t *r_out, const uint64_t *p, size_t m, size_t n) {
+    fr_t *rem = (fr_t *)malloc((m ? m : 1) * sizeof *rem);
+    memcpy(rem, p, m * 32);
+    size_t len = m;
+    while (len && fr_is_zero(&rem[len - 1])) len--;
+    size_t qlen = m > n ? m - n : 0;
+    fr_t *q = (fr_t *)q_out;
+    memset(q, 0, qlen * 32);
+    fr_t minus_one = fr_one(), zero = {{0, 0, 0, 0}}; fr_sub(&minus_one, &zero, &minus_one);
+    while (len && len - 1 >= n) {                                         /* remainder.degree() >= divisor.degree() */
+        fr_t cur = rem[len - 1];                                          /* × leading_coefficient^{-1} = 1 */
+        size_t d = len - 1 - n;
+        q[d] = cur;
+        fr_t t; fr_mul(&t, &cur, &minus_one); fr_sub(&rem[d], &rem[d], &t);   /* remainder[d + 0] −= cur·(−1) */
+        fr_sub(&rem[d + n], &rem[d + n], &cur);                               /* remainder[d + n] −= cur·1 */
+        while (len && fr_is_zero(&rem[len - 1])) len--;
+    }
+    size_t rl = m < n ? m : n;
+    memset(r_out, 0, rl * 32);
+    memcpy(r_out, rem, (len < rl ? len : rl) * 32);
+    free(rem);
+    return qlen;
+}
+
+/* DensePolynomial::evaluate — fft/polynomial/dense.rs:98-114: Σ c_i·z^i (Horner here; field results are canonical) */
+API void oracle_poly_evaluate(uint64_t *out, const uint64_t *coeffs, size_t m, const uint64_t *point) {
+    fr_t acc = {{0, 0, 0, 0}};
+    for (size_t i = m; i-- > 0;) { fr_mul(&acc, &acc, (const fr_t *)point); fr_add(&acc, &acc, (const fr_t *)(coeffs + 4 * i)); }
+    memcpy(out, acc.l, 32);
 }
 
 /* normalise: p.to_affine().to_projective() — the byte image the parity tests compare */

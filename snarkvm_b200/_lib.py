@@ -23,6 +23,8 @@ SYMBOLS = (
     "snarkvm_b200_srs_decode_device", "snarkvm_b200_register_bases", "snarkvm_b200_unregister_bases", "snarkvm_b200_profile_enable", "snarkvm_b200_profile_collect", "snarkvm_b200_generate_bases_device",
     "snarkvm_b200_msm_precompute_device", "snarkvm_b200_msm_precomputed_free", "snarkvm_b200_msm_precomputed_info",
     "snarkvm_b200_msm_precomputed_device", "snarkvm_b200_kzg_commit_precomputed_device",
+    "snarkvm_b200_kzg_commit_hiding_device", "snarkvm_b200_kzg_commit_batch_device", "snarkvm_b200_g1_ntt_device",
+    "snarkvm_b200_fr_batch_inversion_and_mul_device", "snarkvm_b200_poly_divide_by_vanishing_device", "snarkvm_b200_poly_evaluate_device",
 )
 
 
@@ -85,6 +87,12 @@ def lib():
     L.snarkvm_b200_msm_precomputed_info.argtypes = [vp, ctypes.POINTER(sz), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(sz)]
     L.snarkvm_b200_msm_precomputed_device.argtypes = [vp, vp, vp, sz, vp]
     L.snarkvm_b200_kzg_commit_precomputed_device.argtypes = [vp, vp, vp, sz, vp]
+    L.snarkvm_b200_kzg_commit_hiding_device.argtypes = [vp, vp, sz, vp, sz, vp, vp, sz, vp]
+    L.snarkvm_b200_kzg_commit_batch_device.argtypes = [vp, vp, sz, vp, vp, sz, vp]
+    L.snarkvm_b200_g1_ntt_device.argtypes = [vp, sz, vp, sz, u32, i32, vp]
+    L.snarkvm_b200_fr_batch_inversion_and_mul_device.argtypes = [vp, sz, vp, vp]
+    L.snarkvm_b200_poly_divide_by_vanishing_device.argtypes = [vp, vp, vp, sz, sz, vp]
+    L.snarkvm_b200_poly_evaluate_device.argtypes = [vp, vp, sz, vp, vp]
     for s in SYMBOLS[5:]:
         getattr(L, s).restype = i32
     L.snarkvm_b200_launch_count.restype = u64

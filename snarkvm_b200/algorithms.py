@@ -143,12 +143,80 @@ class PolyMultiplier:
 
 
 class KZG10:
-    """The MSM-bearing core of KZG10::commit (algorithms/src/polycommit/kzg10/mod.rs:98-156)."""
+    """The MSM-bearing parts of KZG10 (algorithms/src/polycommit/kzg10/mod.rs:98-206) on device-resident operands
+    (torch CUDA tensors; Montgomery coefficients, the reference's in-memory affine points)."""
 
     @staticmethod
-    def commit(powers_of_beta_g, coefficients_mont):
-        """commitment = VariableBase::msm(powers, to_bigint(coeffs)) with device-resident operands
-        (torch CUDA tensors).  Hiding-polynomial randomness (mod.rs:123-156) is a second, 3-term MSM the
-        caller adds; it is not on the hot path."""
+    def commit(powers_of_beta_g, coefficients_mont, powers_of_beta_times_gamma_g=None, blinding_mont=None):
+        """mod.rs:98-156: VariableBase::msm(powers, to_bigint(coeffs)) [+ msm(gamma powers, to_bigint(blinding)) when hiding;
+        the caller samples the blinding polynomial]."""
         from . import device
-        return device.kzg_commit(powers_of_beta_g, coefficients_mont)
+        if blinding_mont is None:
+            return device.kzg_commit(powers_of_beta_g, coefficients_mont)
+        return device.kzg_commit_hiding(powers_of_beta_g, coefficients_mont, powers_of_beta_times_gamma_g, blinding_mont)
+
+    @staticmethod
+    def commit_lagrange(lagrange_basis_at_beta_g, evaluations_mont, powers_of_beta_times_gamma_g=None, blinding_mont=None):
+        """mod.rs:159-206: the same MSM against the Lagrange basis; len(evaluations).next_power_of_two() must be the basis size."""
+        from . import device
+        n = evaluations_mont.shape[0]
+        size = lagrange_basis_at_beta_g.numel() * lagrange_basis_at_beta_g.element_size() // device.AFFINE_STRIDE
+        if n == 0 or (1 << (n - 1).bit_length()) != size:
+            raise ValueError("evaluations do not match the Lagrange basis size")            # mod.rs:166-169
+        return KZG10.commit(lagrange_basis_at_beta_g, evaluations_mont, powers_of_beta_times_gamma_g, blinding_mont)
+
+    @staticmethod
+    def batch_commit(powers_of_beta_g, polynomials_mont):
+        """all plain commitments of one round against the same powers (sonic_pc/mod.rs:177-257) → [count, 18] uint64"""
+        from . import device
+        return device.kzg_commit_batch(powers_of_beta_g, list(polynomials_mont))
+
+
+class UniversalParams:
+    """polycommit/kzg10/data_structures.rs:36-100, the part that computes: lagrange_basis."""
+
+    def __init__(self, powers_of_beta_g):
+        self.powers_of_beta_g = powers_of_beta_g
+
+    def lagrange_basis(self, domain: "EvaluationDomain"):
+        """data_structures.rs:68-72: domain.ifft(powers_of_beta_g[0..domain.size]) normalised to affine"""
+        from . import device
+        nbytes = domain.size * device.AFFINE_STRIDE
+        flat = self.powers_of_beta_g.reshape(-1).view(__import__("torch").uint8)
+        if flat.numel() < nbytes:
+            raise ValueError("not enough powers for this domain")
+        return device.lagrange_basis(flat[:nbytes].contiguous())
+
+
+class DensePolynomial:
+    """The device-resident subset of fft/polynomial/dense.rs used between transforms: coefficients are a CUDA tensor [m, 4] int64
+    (Montgomery Fr, low degree first)."""
+
+    def __init__(self, coeffs):
+        self.coeffs = coeffs
+
+    def evaluate(self, point_mont):
+        """dense.rs:98-114"""
+        from . import device
+        return device.poly_evaluate(self.coeffs, point_mont)
+
+    def divide_by_vanishing_poly(self, domain: "EvaluationDomain"):
+        """dense.rs:162-169 → (quotient, remainder) as DensePolynomial (not trimmed)"""
+        from . import device
+        q, r = device.poly_divide_by_vanishing(self.coeffs, domain.size)
+        return DensePolynomial(q), DensePolynomial(r)
+
+    def evaluate_over_domain(self, domain: "EvaluationDomain"):
+        """dense.rs:172-181 for degree < domain.size: zero-pad and FFT"""
+        import torch
+        if self.coeffs.shape[0] > domain.size:
+            raise ValueError("degree ≥ domain size is not supported on the device path")
+        x = torch.zeros((domain.size, 4), dtype=self.coeffs.dtype, device=self.coeffs.device)
+        x[: self.coeffs.shape[0]] = self.coeffs
+        return domain.fft_in_place(x)
+
+
+def batch_inversion_and_mul(v, coeff_mont):
+    """fields/src/lib.rs:78-129 on a CUDA tensor, in place"""
+    from . import device
+    return device.fr_batch_inversion_and_mul(v, coeff_mont)

@@ -15,6 +15,7 @@
 #include "host_ec.hpp"
 #include "msm.cuh"
 #include "ntt.cuh"
+#include "poly.cuh"
 
 using namespace b200;
 
@@ -362,6 +363,49 @@ int snarkvm_b200_kzg_commit_precomputed_device(void* out144, const void* handle,
     if (rc == 0) rc = snarkvm_b200_msm_precomputed_device(out144, handle, d_plain, ncoeffs, stream_v);
     if (d_plain) cudaFreeAsync(d_plain, stream);
     return rc;
+}
+
+// KZG10::commit with a hiding bound (polycommit/kzg10/mod.rs:98-156): commitment to the plaintext polynomial against
+// powers_of_beta_g plus the commitment to the blinding polynomial against powers_of_beta_times_gamma_g.  The caller samples the
+// blinding polynomial (KZGRandomness::rand, :129-140) and passes its Montgomery coefficients; nblinding = 0 is the non-hiding
+// commit.  Zero coefficients contribute nothing, so skip_leading_zeros_and_convert_to_bigints (:455-467) needs no special path.
+int snarkvm_b200_kzg_commit_hiding_device(void* out144, const void* d_powers, size_t stride, const void* d_coeffs_mont, size_t ncoeffs,
+                                          const void* d_gamma_powers, const void* d_blinding_mont, size_t nblinding, void* stream) {
+    if (!out144) return (int)cudaErrorInvalidValue;
+    uint64_t a[18], b[18];
+    int rc = snarkvm_b200_kzg_commit_device(a, d_powers, stride, d_coeffs_mont, ncoeffs, stream);
+    if (rc == 0) rc = snarkvm_b200_kzg_commit_device(b, d_gamma_powers, stride, d_blinding_mont, nblinding, stream);
+    if (rc != 0) return rc;
+    host::Xyzz sum = host::xyzz_from_projective(a);
+    host::xyzz_add(sum, host::xyzz_from_projective(b));
+    host::xyzz_to_normalised_projective(sum, (uint64_t*)out144);
+    return 0;
+}
+
+// All commitments of one prover round share powers_of_beta_g (sonic_pc/mod.rs:177-257): count polynomials, one call, the
+// bases stay where they are.  out144s: count × 144 B of HOST memory.
+int snarkvm_b200_kzg_commit_batch_device(void* out144s, const void* d_powers, size_t stride, const void* const* d_coeffs_mont,
+                                         const size_t* ncoeffs, size_t count, void* stream) {
+    if (count == 0) return 0;
+    if (!out144s || !d_coeffs_mont || !ncoeffs) return (int)cudaErrorInvalidValue;
+    for (size_t i = 0; i < count; i++) {
+        int rc = snarkvm_b200_kzg_commit_device((uint8_t*)out144s + i * 144, d_powers, stride, d_coeffs_mont[i], ncoeffs[i], stream);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}
+
+int snarkvm_b200_g1_ntt_device(void* d_out, size_t out_stride, const void* d_in, size_t in_stride, uint32_t lg, int direction, void* stream) {
+    return g1_ntt_device(d_out, out_stride, d_in, in_stride, lg, direction, (cudaStream_t)stream);
+}
+int snarkvm_b200_fr_batch_inversion_and_mul_device(void* d_v, size_t n, const void* coeff_mont_host, void* stream) {
+    return fr_batch_inversion_and_mul_device(d_v, n, coeff_mont_host, (cudaStream_t)stream);
+}
+int snarkvm_b200_poly_divide_by_vanishing_device(void* d_q, void* d_r, const void* d_p, size_t m, size_t n, void* stream) {
+    return poly_divide_by_vanishing_device(d_q, d_r, d_p, m, n, (cudaStream_t)stream);
+}
+int snarkvm_b200_poly_evaluate_device(void* out_mont_host, const void* d_coeffs, size_t m, const void* point_mont_host, void* stream) {
+    return poly_evaluate_device(out_mont_host, d_coeffs, m, point_mont_host, (cudaStream_t)stream);
 }
 
 int snarkvm_b200_fr_from_mont_device(void* d_out, const void* d_in, size_t n, void* stream) {

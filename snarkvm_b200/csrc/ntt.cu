@@ -18,6 +18,7 @@
 
 #include "ff.cuh"
 #include "msm.cuh"   // count_launch
+#include "poly.cuh"  // ntt_get_twiddles
 
 namespace b200 {
 
@@ -98,6 +99,13 @@ static int get_twiddles(int lg, const Fr** tw, int* lgN) {
     *tw = c.tw;
     *lgN = c.lgN;
     return 0;
+}
+
+int ntt_get_twiddles(int lg, const void** tw, int* lgN) {
+    const Fr* t = nullptr;
+    int rc = get_twiddles(lg, &t, lgN);
+    *tw = t;
+    return rc;
 }
 
 static int get_coset_tables(int lg, int inverse, CosetTables* out) {

@@ -1,0 +1,147 @@
+// Device-resident polynomial helpers around the NTT: the pieces of the Varuna prover that sit between
+// transforms and would otherwise force a PCIe round trip per polynomial.
+//
+//   fr_batch_inversion_and_mul_device  — fields/src/lib.rs:78-129 (batch_inversion_and_mul; used by
+//                                        snark/varuna/ahp/prover/round_functions/fourth.rs:203-211)
+//   poly_divide_by_vanishing_device    — fft/polynomial/dense.rs:162-169 → fft/polynomial/mod.rs:222-256 with the
+//                                        divisor x^n − 1
+//   poly_evaluate_device               — DensePolynomial::evaluate (fft/polynomial/dense.rs:98-114)
+//
+// Every result is a canonical Fr value, so any correct evaluation order is bit-identical to the reference's.
+#include "poly.cuh"
+
+#include "ff.cuh"
+#include "msm.cuh"   // count_launch, ensure_pool_configured
+
+namespace b200 {
+
+struct FrArg { uint32_t v[8]; };
+FF_DEV Fr fr_from_arg(const FrArg& a) { Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = a.v[i]; return r; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// v_i ← coeff · v_i^{-1}; zeros are skipped and stay zero (lib.rs:107, 121).  Montgomery's trick per thread over K
+// elements taken with a grid stride (coalesced), one Fermat inversion per K: ≈ 3 + 380/K multiplications per element.
+// ---------------------------------------------------------------------------------------------------------------------
+static constexpr int BINV_K = 8;
+__global__ void __launch_bounds__(128) k_fr_batch_inverse(uint32_t* __restrict__ v, size_t n, FrArg coeff_arg) {
+    const size_t T = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    Fr x[BINV_K], pre[BINV_K];
+    Fr run = Fr::one();
+#pragma unroll
+    for (int k = 0; k < BINV_K; k++) {
+        size_t i = (size_t)k * T + t;
+        x[k] = i < n ? Fr::load(v + i * 8) : Fr::zero();
+        pre[k] = run;                                      // product of the non-zero elements before k
+        if (!x[k].is_zero()) run = run * x[k];
+    }
+    Fr inv = run.inverse() * fr_from_arg(coeff_arg);       // run ≠ 0 (one if everything was zero)
+#pragma unroll
+    for (int k = BINV_K - 1; k >= 0; k--) {
+        size_t i = (size_t)k * T + t;
+        if (i < n && !x[k].is_zero()) {
+            (inv * pre[k]).store(v + i * 8);
+            inv = inv * x[k];
+        }
+    }
+}
+
+int fr_batch_inversion_and_mul_device(void* d_v, size_t n, const void* coeff_mont_host, cudaStream_t stream) {
+    if (n == 0) return 0;
+    if (!d_v || !coeff_mont_host) return (int)cudaErrorInvalidValue;
+    FrArg c;
+    memcpy(c.v, coeff_mont_host, 32);
+    size_t threads = (n + BINV_K - 1) / BINV_K;
+    k_fr_batch_inverse<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>((uint32_t*)d_v, n, c);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// p = q·(x^n − 1) + r  ⇒  q_i = Σ_{k ≥ 1} p_{i + k·n},  r_i = p_i + q_i  (q_i = 0 past its end).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void k_divide_by_vanishing(const uint32_t* __restrict__ p, size_t m, size_t n, uint32_t* __restrict__ q,
+                                      uint32_t* __restrict__ r) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t qlen = m > n ? m - n : 0, rlen = m < n ? m : n;
+    if (i >= qlen && i >= rlen) return;
+    Fr acc = Fr::zero();
+    for (size_t j = i + n; j < m; j += n) acc = acc + Fr::load_ldg(p + j * 8);
+    if (i < qlen) acc.store(q + i * 8);
+    if (i < rlen) (acc + Fr::load_ldg(p + i * 8)).store(r + i * 8);
+}
+
+int poly_divide_by_vanishing_device(void* d_q, void* d_r, const void* d_p, size_t m, size_t n, cudaStream_t stream) {
+    if (n == 0) return (int)cudaErrorInvalidValue;
+    if (m == 0) return 0;
+    const size_t qlen = m > n ? m - n : 0, rlen = m < n ? m : n, work = qlen > rlen ? qlen : rlen;
+    if (!d_p || !d_r || (qlen && !d_q)) return (int)cudaErrorInvalidValue;
+    k_divide_by_vanishing<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>((const uint32_t*)d_p, m, n, (uint32_t*)d_q, (uint32_t*)d_r);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Σ c_i z^i: a thread runs Horner over EVAL_K consecutive coefficients and shifts its partial by z^{first index}; the
+// CTA adds its 256 partials in shared memory; a second single-CTA launch adds the per-CTA sums.
+// ---------------------------------------------------------------------------------------------------------------------
+static constexpr int EVAL_K = 64, EVAL_THREADS = 256;
+FF_DEV Fr fr_pow_u64(Fr base, uint64_t e) {
+    Fr acc = Fr::one();
+    while (e) { if (e & 1) acc = acc * base; base = base.sqr(); e >>= 1; }
+    return acc;
+}
+FF_DEV Fr cta_sum(Fr mine, uint32_t* sh) {
+    mine.store(sh + threadIdx.x * 8);
+    __syncthreads();
+    for (int s = EVAL_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) (Fr::load(sh + threadIdx.x * 8) + Fr::load(sh + (threadIdx.x + s) * 8)).store(sh + threadIdx.x * 8);
+        __syncthreads();
+    }
+    return Fr::load(sh);
+}
+__global__ void __launch_bounds__(EVAL_THREADS) k_poly_eval_partial(const uint32_t* __restrict__ c, size_t m, FrArg z_arg,
+                                                                     uint32_t* __restrict__ partial) {
+    __shared__ uint4 sh4[EVAL_THREADS * 2];
+    const Fr z = fr_from_arg(z_arg);
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, i0 = t * EVAL_K;
+    Fr acc = Fr::zero();
+    if (i0 < m) {
+        const size_t i1 = i0 + EVAL_K < m ? i0 + EVAL_K : m;
+        for (size_t i = i1; i-- > i0;) acc = acc * z + Fr::load_ldg(c + i * 8);
+        acc = acc * fr_pow_u64(z, (uint64_t)i0);
+    }
+    Fr s = cta_sum(acc, reinterpret_cast<uint32_t*>(sh4));
+    if (threadIdx.x == 0) s.store(partial + (size_t)blockIdx.x * 8);
+}
+__global__ void __launch_bounds__(EVAL_THREADS) k_fr_sum(const uint32_t* __restrict__ in, size_t count, uint32_t* __restrict__ out) {
+    __shared__ uint4 sh4[EVAL_THREADS * 2];
+    Fr acc = Fr::zero();
+    for (size_t i = threadIdx.x; i < count; i += EVAL_THREADS) acc = acc + Fr::load_ldg(in + i * 8);
+    Fr s = cta_sum(acc, reinterpret_cast<uint32_t*>(sh4));
+    if (threadIdx.x == 0) s.store(out);
+}
+
+int poly_evaluate_device(void* out_mont_host, const void* d_coeffs, size_t m, const void* point_mont_host, cudaStream_t stream) {
+    if (!out_mont_host || !point_mont_host) return (int)cudaErrorInvalidValue;
+    if (m == 0) { memset(out_mont_host, 0, 32); return 0; }
+    if (!d_coeffs) return (int)cudaErrorInvalidValue;
+    ensure_pool_configured();
+    FrArg z;
+    memcpy(z.v, point_mont_host, 32);
+    const size_t threads = (m + EVAL_K - 1) / EVAL_K, blocks = (threads + EVAL_THREADS - 1) / EVAL_THREADS;
+    uint32_t* scratch = nullptr;
+    cudaError_t e = cudaMallocAsync(&scratch, (blocks + 1) * 32, stream);
+    if (e != cudaSuccess) return (int)e;
+    k_poly_eval_partial<<<(unsigned)blocks, EVAL_THREADS, 0, stream>>>((const uint32_t*)d_coeffs, m, z, scratch);
+    k_fr_sum<<<1, EVAL_THREADS, 0, stream>>>(scratch, blocks, scratch + blocks * 8);
+    count_launch(2);
+    int rc = (int)cudaGetLastError();
+    if (rc == 0) rc = (int)cudaMemcpyAsync(out_mont_host, scratch + blocks * 8, 32, cudaMemcpyDeviceToHost, stream);
+    cudaFreeAsync(scratch, stream);
+    if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
+    return rc;
+}
+
+}  // namespace b200

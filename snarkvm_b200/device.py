@@ -129,6 +129,92 @@ def kzg_commit(powers: torch.Tensor, coeffs_mont: torch.Tensor, stride: int = AF
     return out
 
 
+def kzg_commit_hiding(powers: torch.Tensor, coeffs_mont: torch.Tensor, gamma_powers: torch.Tensor, blinding_mont: torch.Tensor,
+                      stride: int = AFFINE_STRIDE) -> np.ndarray:
+    """KZG10::commit with hiding_bound = Some(_) (kzg10/mod.rs:98-156): Σ to_bigint(c_i)·powers_i + Σ to_bigint(b_j)·gamma_powers_j;
+    the caller samples the blinding polynomial b (KZGRandomness::rand)."""
+    n = _msm_args(powers, coeffs_mont, stride)
+    nb = _nbytes(blinding_mont) // 32
+    if nb > _nbytes(gamma_powers) // stride:
+        raise ValueError("hiding bound exceeds powers_of_beta_times_gamma_g")      # check_hiding_bound, mod.rs:134-137
+    out = np.zeros(18, dtype=np.uint64)
+    with torch.cuda.device(powers.device):
+        _lib.check(_lib.lib().snarkvm_b200_kzg_commit_hiding_device(
+            out.ctypes.data, _check(powers, "powers"), stride, _check(coeffs_mont, "coeffs"), n,
+            _check(gamma_powers, "gamma_powers"), _check(blinding_mont, "blinding"), nb, _stream()))
+    return out
+
+
+def kzg_commit_batch(powers: torch.Tensor, polys_mont: list, stride: int = AFFINE_STRIDE) -> np.ndarray:
+    """One call for all commitments of a round against the same resident powers (sonic_pc/mod.rs:177-257) → [count, 18] u64."""
+    count = len(polys_mont)
+    out = np.zeros((count, 18), dtype=np.uint64)
+    if count == 0:
+        return out
+    nb = _nbytes(powers) // stride
+    lens = [_nbytes(p) // 32 for p in polys_mont]
+    if max(lens) > nb:
+        raise ValueError("polynomial degree exceeds the number of powers")         # check_degree_is_too_large, mod.rs:105
+    ptrs = (ctypes.c_void_p * count)(*[_check(p, "poly") for p in polys_mont])
+    szs = (ctypes.c_size_t * count)(*lens)
+    with torch.cuda.device(powers.device):
+        _lib.check(_lib.lib().snarkvm_b200_kzg_commit_batch_device(out.ctypes.data, _check(powers, "powers"), stride, ptrs, szs, count, _stream()))
+    return out
+
+
+def g1_ntt(points: torch.Tensor, inverse: bool, stride: int = AFFINE_STRIDE) -> torch.Tensor:
+    """FFT / iFFT over 2^k G1 points (EvaluationDomain with T = G1Projective, fft/domain.rs:169-221) → affine points, same stride."""
+    n = _nbytes(points) // stride
+    if n == 0 or n & (n - 1):
+        raise ValueError("domain size must be a power of two")
+    out = torch.empty_like(points)
+    with torch.cuda.device(points.device):
+        _lib.check(_lib.lib().snarkvm_b200_g1_ntt_device(out.data_ptr(), stride, _check(points, "points"), stride, n.bit_length() - 1,
+                                                          1 if inverse else 0, _stream()))
+    return out
+
+
+def lagrange_basis(powers_of_beta_g: torch.Tensor, stride: int = AFFINE_STRIDE) -> torch.Tensor:
+    """UniversalParams::lagrange_basis (kzg10/data_structures.rs:68-72): ifft of the first n powers, normalised to affine."""
+    return g1_ntt(powers_of_beta_g, True, stride)
+
+
+def _fr_host(x) -> np.ndarray:
+    a = np.ascontiguousarray(x, dtype=np.uint64).reshape(4)
+    return a
+
+
+def fr_batch_inversion_and_mul(v: torch.Tensor, coeff_mont) -> torch.Tensor:
+    """fields/src/lib.rs:78-129, in place on a CUDA tensor of Montgomery Fr: v_i ← coeff·v_i^{-1}; zeros stay zero."""
+    c = _fr_host(coeff_mont)
+    with torch.cuda.device(v.device):
+        _lib.check(_lib.lib().snarkvm_b200_fr_batch_inversion_and_mul_device(_check(v, "v"), _nbytes(v) // 32, c.ctypes.data, _stream()))
+    return v
+
+
+def poly_divide_by_vanishing(p: torch.Tensor, domain_size: int):
+    """DensePolynomial::divide_by_vanishing_poly (fft/polynomial/dense.rs:162-169) → (quotient, remainder) CUDA tensors [.., 4] i64,
+    max(m − n, 0) and min(m, n) coefficients, not trimmed."""
+    m = _nbytes(p) // 32
+    q = torch.empty((max(m - domain_size, 0), 4), dtype=torch.int64, device=p.device)
+    r = torch.empty((min(m, domain_size), 4), dtype=torch.int64, device=p.device)
+    if m:
+        with torch.cuda.device(p.device):
+            _lib.check(_lib.lib().snarkvm_b200_poly_divide_by_vanishing_device(q.data_ptr() if q.numel() else None, r.data_ptr(),
+                                                                                _check(p, "p"), m, domain_size, _stream()))
+    return q, r
+
+
+def poly_evaluate(coeffs: torch.Tensor, point_mont) -> np.ndarray:
+    """DensePolynomial::evaluate (fft/polynomial/dense.rs:98-114) → Montgomery Fr as uint64[4] on the host."""
+    z = _fr_host(point_mont)
+    out = np.zeros(4, dtype=np.uint64)
+    m = _nbytes(coeffs) // 32
+    with torch.cuda.device(coeffs.device):
+        _lib.check(_lib.lib().snarkvm_b200_poly_evaluate_device(out.ctypes.data, _check(coeffs, "coeffs") if m else None, m, z.ctypes.data, _stream()))
+    return out
+
+
 class PrecomputedBases:
     """A fixed base set with its tables 2^{c·w}·P_i resident in HBM (snarkvm_b200_msm_precompute_device): MSMs over it use one
     bucket set for all windows.  `msm(scalars)` / `kzg_commit(coeffs_mont)` take the first len(scalars) bases, like

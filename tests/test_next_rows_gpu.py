@@ -1,0 +1,130 @@
+"""GPU parity for the rows after the hot path (SURVEY §8 f1–f4): hiding / batched / Lagrange KZG commitments, the group FFT behind
+UniversalParams::lagrange_basis, batch_inversion_and_mul, divide_by_vanishing_poly, DensePolynomial::evaluate — each against the
+oracle's restatement of the reference CPU code, bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bls12_377 as py
+
+from helpers import affine_array, fr_ints_to_mont_array, oracle_bases, random_canonical_fr, random_fr_mont
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _dev(x):
+    import torch
+    if x.dtype == np.uint64:
+        x = x.view(np.int64)
+    return torch.from_numpy(x.copy()).cuda()
+
+
+def _host_u64(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+@pytest.mark.parametrize("lg", [0, 1, 2, 3, 6, 9])
+def test_g1_ifft_vs_oracle(oracle_cpu, lg):
+    from snarkvm_b200 import device
+    n = 1 << lg
+    bases = oracle_bases(oracle_cpu, max(n, 4), seed=20 + lg)[:n].copy()
+    if n >= 8:
+        bases[5, 96] = 1                                       # an ∞ input
+        bases[6] = bases[2]                                    # a repeated point (sum doubles, difference cancels)
+    got = device.g1_ntt(_dev(bases), inverse=True).cpu().numpy()
+    assert (got == oracle_cpu.g1_ifft(bases)).all()
+    # forward transform undoes it (fft ∘ ifft = id on the group elements); ∞ comes back in the canonical (0, 1, ∞) image
+    back = device.g1_ntt(_dev(got), inverse=False).cpu().numpy()
+    want = bases.copy()
+    if n >= 8:
+        want[5] = affine_array([None])[0]
+    assert (back == want).all()
+
+
+def test_lagrange_basis_real_srs_and_commit_lagrange(oracle_cpu):
+    """lagrange_basis of the real powers-of-beta (kzg10/data_structures.rs:68-72); then commit_lagrange(evals) == commit(ifft(evals)):
+    the two commitment keys commit to the same polynomial (kzg10/mod.rs:98-206)."""
+    from snarkvm_b200.algorithms import KZG10, EvaluationDomain, UniversalParams
+    n = 256
+    blob = open(os.path.join(HERE, "golden", "powers_of_beta_15_first512.usrs"), "rb").read()
+    powers = affine_array(py.parse_usrs_points(blob, n))
+    dpowers = _dev(powers)
+    domain = EvaluationDomain.new(n)
+    basis = UniversalParams(dpowers).lagrange_basis(domain)
+    assert (basis.cpu().numpy().reshape(n, 104) == oracle_cpu.g1_ifft(powers)).all()
+    evals = random_fr_mont(n, seed=77)
+    c_lagrange = KZG10.commit_lagrange(basis, _dev(evals))
+    coeffs = oracle_cpu.ntt(evals, oracle_cpu.INVERSE)
+    assert (c_lagrange == oracle_cpu.msm(powers, oracle_cpu.fr_from_mont(coeffs), 0)).all()
+    assert (c_lagrange == KZG10.commit(dpowers, _dev(coeffs))).all()
+    with pytest.raises(ValueError):
+        KZG10.commit_lagrange(basis, _dev(evals[:100]))       # next_power_of_two(100) != 256
+
+
+def test_kzg_commit_hiding_and_batch(oracle_cpu):
+    from snarkvm_b200.algorithms import KZG10
+    from snarkvm_b200 import device
+    n = 1 << 12
+    powers = device.generate_bases(n, seed=41)
+    gamma = device.generate_bases(8, seed=42)
+    hp, hg = powers.cpu().numpy(), gamma.cpu().numpy()
+    coeffs = random_fr_mont(n, seed=1)
+    coeffs[:37] = 0                                            # leading zeros (skip_leading_zeros_and_convert_to_bigints, mod.rs:455-467)
+    blind = random_fr_mont(3, seed=2)                          # hiding_bound = Some(1) ⇒ degree-2 blinding polynomial
+    got = KZG10.commit(powers, _dev(coeffs), gamma, _dev(blind))
+    plain = oracle_cpu.msm(hp, oracle_cpu.fr_from_mont(coeffs), 0)
+    rnd = oracle_cpu.msm(hg, oracle_cpu.fr_from_mont(blind), 0)
+    assert (got == oracle_cpu.g1_add(plain, rnd)).all()
+    with pytest.raises(ValueError):
+        KZG10.commit(powers, _dev(coeffs), gamma, _dev(random_fr_mont(9, seed=3)))
+    polys = [random_fr_mont(m, seed=10 + i) for i, m in enumerate((n, 1000, 1, n - 1))]
+    batch = KZG10.batch_commit(powers, [_dev(p) for p in polys])
+    for row, p in zip(batch, polys):
+        assert (row == oracle_cpu.msm(hp, oracle_cpu.fr_from_mont(p), 0)).all()
+    assert KZG10.batch_commit(powers, []).shape == (0, 18)
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 1000, 100003])
+def test_batch_inversion_and_mul(oracle_cpu, n):
+    from snarkvm_b200.algorithms import batch_inversion_and_mul
+    v = random_fr_mont(n, seed=n)
+    v[::5] = 0
+    coeff = random_fr_mont(1, seed=99)[0]
+    got = _host_u64(batch_inversion_and_mul(_dev(v), coeff))
+    assert (got == oracle_cpu.fr_batch_inversion_and_mul(v, coeff)).all()
+    one = fr_ints_to_mont_array([1])[0]
+    back = _host_u64(batch_inversion_and_mul(_dev(got), one))   # (c/v)^{-1} = v/c
+    cinv = oracle_cpu.fr_batch_inversion_and_mul(coeff.reshape(1, 4), one)[0]
+    want = np.array([oracle_cpu.fr_mul(x, cinv) for x in v[:16]])
+    assert (back[:16] == want).all()
+
+
+@pytest.mark.parametrize("m,n", [(5, 8), (8, 8), (9, 8), (40, 8), (4096, 1024), (3 * 4096 - 5, 4096), (100, 4), (1, 1)])
+def test_divide_by_vanishing_poly_and_evaluate(oracle_cpu, m, n):
+    from snarkvm_b200.algorithms import DensePolynomial, EvaluationDomain
+    p = random_fr_mont(m, seed=m + n)
+    if m == 40:
+        p[-3:] = 0
+    poly = DensePolynomial(_dev(p))
+    q, r = poly.divide_by_vanishing_poly(EvaluationDomain.new(n))
+    wq, wr = oracle_cpu.poly_divide_by_vanishing(p, n)
+    assert (_host_u64(q.coeffs).reshape(-1, 4) == wq).all() and (_host_u64(r.coeffs).reshape(-1, 4) == wr).all()
+    for seed in (1, 2):
+        z = random_fr_mont(1, seed=seed)[0]
+        assert (poly.evaluate(z) == oracle_cpu.poly_evaluate(p, z)).all()
+    zero = np.zeros(4, dtype=np.uint64)
+    assert (poly.evaluate(zero) == p[0]).all()                 # dense.rs:101-102
+
+
+def test_evaluate_large_and_over_domain(oracle_cpu):
+    from snarkvm_b200.algorithms import DensePolynomial, EvaluationDomain
+    m = (1 << 18) + 12345
+    p = random_fr_mont(m, seed=5)
+    z = random_fr_mont(1, seed=6)[0]
+    assert (DensePolynomial(_dev(p)).evaluate(z) == oracle_cpu.poly_evaluate(p, z)).all()
+    small = random_fr_mont(300, seed=7)
+    ev = DensePolynomial(_dev(small)).evaluate_over_domain(EvaluationDomain.new(512))
+    padded = np.zeros((512, 4), dtype=np.uint64); padded[:300] = small
+    assert (_host_u64(ev).reshape(-1, 4) == oracle_cpu.ntt(padded, oracle_cpu.FORWARD)).all()
