@@ -37,6 +37,8 @@ snarkvm_error_t make_error(int code) {
 struct ThreadCtx {
     cudaStream_t stream[64] = {};
     bool have[64] = {};
+    cudaStream_t copy_stream[64] = {};
+    bool have_copy[64] = {};
     ~ThreadCtx() {}
 };
 thread_local ThreadCtx t_ctx;
@@ -53,6 +55,21 @@ int thread_stream(cudaStream_t* out) {
         t_ctx.have[dev] = true;
     }
     *out = t_ctx.stream[dev];
+    return 0;
+}
+
+// second stream of the calling thread: uploads that overlap the kernels of the first
+int thread_copy_stream(cudaStream_t* out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    dev &= 63;
+    if (!t_ctx.have_copy[dev]) {
+        e = cudaStreamCreateWithFlags(&t_ctx.copy_stream[dev], cudaStreamNonBlocking);
+        if (e != cudaSuccess) return (int)e;
+        t_ctx.have_copy[dev] = true;
+    }
+    *out = t_ctx.copy_stream[dev];
     return 0;
 }
 
@@ -209,6 +226,39 @@ snarkvm_error_t snarkvm_polymul(void* out, size_t pcount, const void* polynomial
     return make_error(rc ? rc : rs);
 }
 
+// Large host-buffer MSMs are cut into point ranges: range k+1 crosses PCIe on the thread's copy stream while range k is in
+// the Pippenger kernels (an MSM is a sum over points: every range is a complete MSM with its own plan and the results add).
+// 2^24 points: 2.28 GB of upload, ≈ 40 ms, of which only the first range's share stays exposed — so the first range is small
+// (1/8 of the points), then 3/8, then 1/2.  SNARKVM_B200_MSM_CHUNKS = "1", "2" (equal parts) or weights like "1:3:4".
+static std::vector<size_t> msm_ranges(size_t npoints) {
+    std::vector<size_t> w;
+    if (npoints >= ((size_t)1 << 23)) w = {1, 3, 4};
+    if (const char* e = getenv("SNARKVM_B200_MSM_CHUNKS")) {
+        std::vector<size_t> v;
+        for (const char* p = e; *p;) {
+            char* end = nullptr;
+            long x = strtol(p, &end, 10);
+            if (end == p || x < 1 || x > 1024) { v.clear(); break; }
+            v.push_back((size_t)x);
+            p = *end == ':' ? end + 1 : end;
+            if (*end && *end != ':') { v.clear(); break; }
+        }
+        if (v.size() == 1) v.assign(v[0] <= 64 ? v[0] : 64, 1);            // "k" = k equal parts
+        if (!v.empty()) w = v;
+    }
+    size_t total = 0;
+    for (size_t x : w) total += x;
+    std::vector<size_t> bounds{0};                                        // range k = [bounds[k], bounds[k+1])
+    size_t acc = 0;
+    for (size_t x : w) {
+        acc += x;
+        size_t b = (size_t)((unsigned __int128)npoints * acc / total);
+        if (b > bounds.back()) bounds.push_back(b);                       // empty ranges are dropped
+    }
+    if (bounds.back() != npoints) bounds.push_back(npoints);
+    return bounds;
+}
+
 snarkvm_error_t snarkvm_msm(void* out, const void* points, size_t npoints, const void* scalars, size_t ffi_affine_sz) {
     if (!out) return make_error((int)cudaErrorInvalidValue);
     if (npoints == 0) { write_infinity(out); return make_error(0); }
@@ -219,12 +269,58 @@ snarkvm_error_t snarkvm_msm(void* out, const void* points, size_t npoints, const
     void *d_points = nullptr, *d_scalars = nullptr;
     ResidentBases rb;
     const bool resident = find_resident(points, npoints, ffi_affine_sz, &rb);
+    std::vector<size_t> bounds{0, npoints};
+    if (!resident) bounds = msm_ranges(npoints);
+    const int chunks = (int)bounds.size() - 1;
     if (!resident) rc = (int)cudaMallocAsync(&d_points, npoints * ffi_affine_sz, stream);
     if (rc == 0) rc = (int)cudaMallocAsync(&d_scalars, npoints * 32, stream);
-    if (rc == 0) rc = (int)cudaMemcpyAsync(d_scalars, scalars, npoints * 32, cudaMemcpyHostToDevice, stream);
-    if (rc == 0 && !resident) rc = (int)cudaMemcpyAsync(d_points, points, npoints * ffi_affine_sz, cudaMemcpyHostToDevice, stream);
     uint64_t result[18];
-    if (rc == 0) rc = msm_device_impl(result, resident ? rb.d_ptr : d_points, npoints, d_scalars, ffi_affine_sz, stream);
+    if (chunks == 1) {
+        if (rc == 0) rc = (int)cudaMemcpyAsync(d_scalars, scalars, npoints * 32, cudaMemcpyHostToDevice, stream);
+        if (rc == 0 && !resident) rc = (int)cudaMemcpyAsync(d_points, points, npoints * ffi_affine_sz, cudaMemcpyHostToDevice, stream);
+        if (rc == 0) rc = msm_device_impl(result, resident ? rb.d_ptr : d_points, npoints, d_scalars, ffi_affine_sz, stream);
+    } else {
+        cudaStream_t copy = nullptr;
+        if (rc == 0) rc = thread_copy_stream(&copy);
+        std::vector<MsmPlan> plans;
+        std::vector<size_t> sum_off{0};                                   // in XYZZ points
+        for (int k = 0; k < chunks; k++) {
+            plans.push_back(msm_make_plan(bounds[k + 1] - bounds[k]));
+            sum_off.push_back(sum_off.back() + (size_t)plans.back().nwin);
+        }
+        std::vector<cudaEvent_t> ev((size_t)chunks + 1, nullptr);
+        for (auto& e : ev) if (rc == 0) rc = (int)cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        uint32_t* d_sums = nullptr;
+        if (rc == 0) rc = (int)cudaMallocAsync((void**)&d_sums, sum_off.back() * 192, stream);
+        // the pool allocations above are ordered on `stream`; the copy stream may touch them only after this point
+        if (rc == 0) rc = (int)cudaEventRecord(ev[chunks], stream);
+        if (rc == 0) rc = (int)cudaStreamWaitEvent(copy, ev[chunks], 0);
+        for (int k = 0; k < chunks && rc == 0; k++) {
+            const size_t i0 = bounds[k], cn = bounds[k + 1] - i0;
+            rc = (int)cudaMemcpyAsync((uint8_t*)d_scalars + i0 * 32, (const uint8_t*)scalars + i0 * 32, cn * 32, cudaMemcpyHostToDevice, copy);
+            if (rc == 0) rc = (int)cudaMemcpyAsync((uint8_t*)d_points + i0 * ffi_affine_sz, (const uint8_t*)points + i0 * ffi_affine_sz,
+                                                   cn * ffi_affine_sz, cudaMemcpyHostToDevice, copy);
+            if (rc == 0) rc = (int)cudaEventRecord(ev[k], copy);
+        }
+        for (int k = 0; k < chunks && rc == 0; k++) {
+            const size_t i0 = bounds[k], cn = bounds[k + 1] - i0;
+            rc = (int)cudaStreamWaitEvent(stream, ev[k], 0);
+            if (rc == 0) rc = msm_window_sums_device(d_sums + sum_off[k] * 48, plans[k], (const uint8_t*)d_points + i0 * ffi_affine_sz,
+                                                     ffi_affine_sz, (const uint8_t*)d_scalars + i0 * 32, cn, stream);
+        }
+        std::vector<host::Xyzz> sums(sum_off.back());
+        if (rc == 0) rc = (int)cudaMemcpyAsync(sums.data(), d_sums, sums.size() * 192, cudaMemcpyDeviceToHost, stream);
+        if (d_sums) cudaFreeAsync(d_sums, stream);
+        // on any failure the copy stream may still be writing: drain it before the buffers go back to the pool
+        if (copy) { int rs = (int)cudaStreamSynchronize(copy); if (rc == 0) rc = rs; }
+        if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (rc == 0) {
+            host::Xyzz total = host::xyzz_inf();
+            for (int k = 0; k < chunks; k++) host::xyzz_add(total, host::horner_windows(sums.data() + sum_off[k], plans[k].nwin, plans[k].c));
+            host::xyzz_to_normalised_projective(total, result);
+        }
+    }
     if (d_points) cudaFreeAsync(d_points, stream);
     if (d_scalars) cudaFreeAsync(d_scalars, stream);
     int rs = (int)cudaStreamSynchronize(stream);

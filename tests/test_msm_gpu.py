@@ -389,3 +389,16 @@ def test_precomputed_bases_full_size(oracle_cpu):
     assert (got == oracle_cpu.g1_mul(g, oracle_cpu.fr_dot_canonical(scal, ks))).all()
     assert (got == device.msm(bases, _dev(scal))).all()
     pre.free()
+
+
+@pytest.mark.parametrize("chunks,n", [("2", 3001), ("3", 1 << 14), ("16", 20), ("5", 4), ("1:3:4", 1 << 14), ("7:1", 1000)])
+def test_msm_ffi_chunked_upload(oracle_cpu, bases64k, monkeypatch, chunks, n):
+    """snarkvm_msm cuts big host buffers into point ranges whose upload overlaps the previous range's kernels
+    (default: 1/8, 3/8, 1/2 of the points from 2^23); forced here on small inputs, including ranges of one point."""
+    from snarkvm_b200.algorithms import VariableBase
+    monkeypatch.setenv("SNARKVM_B200_MSM_CHUNKS", str(chunks))
+    scal = random_canonical_fr(n, seed=len(chunks) + n)
+    scal[0] = 0
+    bases = bases64k[:n].copy()
+    bases[1, 96] = 1
+    assert (VariableBase.msm(bases, scal) == oracle_cpu.msm(bases, scal, 1)).all()
