@@ -144,6 +144,9 @@ SNARKVM_API int snarkvm_b200_fr_batch_inversion_and_mul_device(void* d_v, size_t
 /* DensePolynomial::divide_by_vanishing_poly (fft/polynomial/dense.rs:162-169): p (m coefficients) = q * (x^n - 1) + r;
  * d_q receives max(m - n, 0) coefficients, d_r receives min(m, n) (neither trimmed). */
 SNARKVM_API int snarkvm_b200_poly_divide_by_vanishing_device(void* d_q, void* d_r, const void* d_p, size_t m, size_t n, void* stream);
+/* KZG10::compute_witness_polynomial (polycommit/kzg10/mod.rs:220-241): quotient of p (m coefficients) / (x - point); d_q receives
+ * m - 1 coefficients; the remainder p(point) is dropped as in the reference.  point: 32 B Montgomery, HOST. */
+SNARKVM_API int snarkvm_b200_poly_divide_by_linear_device(void* d_q, const void* d_p, size_t m, const void* point_mont_host, void* stream);
 /* DensePolynomial::evaluate (fft/polynomial/dense.rs:98-114): out = sum c_i * point^i; out and point are 32-byte HOST buffers. */
 SNARKVM_API int snarkvm_b200_poly_evaluate_device(void* out_mont_host, const void* d_coeffs, size_t m, const void* point_mont_host,
                                                   void* stream);

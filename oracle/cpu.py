@@ -236,3 +236,14 @@ def poly_evaluate(coeffs: np.ndarray, point: np.ndarray) -> np.ndarray:
     out = np.zeros(4, dtype=np.uint64)
     lib().oracle_poly_evaluate(_p(out), _p(coeffs), ctypes.c_size_t(coeffs.shape[0]), _p(z))
     return out
+
+
+def poly_divide_by_linear(p: np.ndarray, point: np.ndarray) -> np.ndarray:
+    """compute_witness_polynomial (kzg10/mod.rs:220-241): quotient of p / (x − point) → [max(m − 1, 0), 4], untrimmed."""
+    p = np.ascontiguousarray(p, dtype=np.uint64).reshape(-1, 4)
+    z = np.ascontiguousarray(point, dtype=np.uint64).reshape(4)
+    m = p.shape[0]
+    q = np.zeros((max(m - 1, 1), 4), dtype=np.uint64)
+    lib().oracle_poly_divide_by_linear.restype = ctypes.c_size_t
+    lib().oracle_poly_divide_by_linear(_p(q), _p(p), ctypes.c_size_t(m), _p(z))
+    return q[:max(m - 1, 0)]

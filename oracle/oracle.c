@@ -876,6 +876,32 @@ API void oracle_poly_evaluate(uint64_t *out, const uint64_t *coeffs, size_t m, c
     memcpy(out, acc.l, 32);
 }
 
+/* compute_witness_polynomial — polycommit/kzg10/mod.rs:220-241: `polynomial / &divisor` with divisor = x − point, i.e. the
+ * quotient of divide_with_q_and_r (fft/polynomial/mod.rs:222-256) against the dense divisor [−point, 1]; the remainder p(point)
+ * is dropped.  p has m coefficient slots; q_out gets max(m − 1, 0) slots (zero above the true degree).  Returns that length. */
+API size_t oracle_poly_divide_by_linear(uint64_t *q_out, const uint64_t *p, size_t m, const uint64_t *point_mont) {
+    size_t qslots = m ? m - 1 : 0;
+    memset(q_out, 0, qslots * 32);
+    fr_t *rem = (fr_t *)malloc((m ? m : 1) * sizeof *rem);
+    memcpy(rem, p, m * 32);
+    size_t len = m;
+    while (len && fr_is_zero(&rem[len - 1])) len--;
+    fr_t zero = {{0, 0, 0, 0}}, neg_point, lead_inv = fr_one();
+    fr_sub(&neg_point, &zero, (const fr_t *)point_mont);
+    fr_inverse(&lead_inv, &lead_inv);                                     /* divisor.leading_coefficient().inverse() = 1 */
+    fr_t *q = (fr_t *)q_out;
+    while (len && len - 1 >= 1) {
+        fr_t cur; fr_mul(&cur, &rem[len - 1], &lead_inv);
+        size_t d = len - 1 - 1;
+        q[d] = cur;
+        fr_t t; fr_mul(&t, &cur, &neg_point); fr_sub(&rem[d], &rem[d], &t);
+        fr_t one = fr_one(); fr_mul(&t, &cur, &one); fr_sub(&rem[d + 1], &rem[d + 1], &t);
+        while (len && fr_is_zero(&rem[len - 1])) len--;
+    }
+    free(rem);
+    return qslots;
+}
+
 /* normalise: p.to_affine().to_projective() — the byte image the parity tests compare */
 static void write_normalised(uint64_t *out144, const g1_proj_t *p) {
     g1_affine_t a = proj_to_affine(p); g1_proj_t q = aff_to_proj(&a); memcpy(out144, &q, 144);

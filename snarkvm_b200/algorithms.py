@@ -166,6 +166,31 @@ class KZG10:
         return KZG10.commit(lagrange_basis_at_beta_g, evaluations_mont, powers_of_beta_times_gamma_g, blinding_mont)
 
     @staticmethod
+    def compute_witness_polynomial(polynomial_mont, point_mont, blinding_mont=None):
+        """mod.rs:220-241: (p / (x − point), blinding / (x − point) or None), quotients only"""
+        from . import device
+        w = device.poly_divide_by_linear(polynomial_mont, point_mont)
+        rw = device.poly_divide_by_linear(blinding_mont, point_mont) if blinding_mont is not None else None
+        return w, rw
+
+    @staticmethod
+    def open_with_witness_polynomial(powers_of_beta_g, point_mont, witness_mont, powers_of_beta_times_gamma_g=None,
+                                     blinding_mont=None, hiding_witness_mont=None):
+        """mod.rs:243-277 → (w as normalised projective uint64[18], random_v as Montgomery uint64[4] or None):
+        w = msm(powers, witness) [+ msm(gamma powers, hiding witness)], random_v = blinding.evaluate(point)"""
+        from . import device
+        if hiding_witness_mont is None:
+            return device.kzg_commit(powers_of_beta_g, witness_mont), None
+        w = device.kzg_commit_hiding(powers_of_beta_g, witness_mont, powers_of_beta_times_gamma_g, hiding_witness_mont)
+        return w, device.poly_evaluate(blinding_mont, point_mont)
+
+    @staticmethod
+    def open(powers_of_beta_g, polynomial_mont, point_mont, powers_of_beta_times_gamma_g=None, blinding_mont=None):
+        """mod.rs:303-321: compute_witness_polynomial then open_with_witness_polynomial"""
+        w, rw = KZG10.compute_witness_polynomial(polynomial_mont, point_mont, blinding_mont)
+        return KZG10.open_with_witness_polynomial(powers_of_beta_g, point_mont, w, powers_of_beta_times_gamma_g, blinding_mont, rw)
+
+    @staticmethod
     def batch_commit(powers_of_beta_g, polynomials_mont):
         """all plain commitments of one round against the same powers (sonic_pc/mod.rs:177-257) → [count, 18] uint64"""
         from . import device

@@ -500,6 +500,9 @@ int snarkvm_b200_fr_batch_inversion_and_mul_device(void* d_v, size_t n, const vo
 int snarkvm_b200_poly_divide_by_vanishing_device(void* d_q, void* d_r, const void* d_p, size_t m, size_t n, void* stream) {
     return poly_divide_by_vanishing_device(d_q, d_r, d_p, m, n, (cudaStream_t)stream);
 }
+int snarkvm_b200_poly_divide_by_linear_device(void* d_q, const void* d_p, size_t m, const void* point_mont_host, void* stream) {
+    return poly_divide_by_linear_device(d_q, d_p, m, point_mont_host, (cudaStream_t)stream);
+}
 int snarkvm_b200_poly_evaluate_device(void* out_mont_host, const void* d_coeffs, size_t m, const void* point_mont_host, void* stream) {
     return poly_evaluate_device(out_mont_host, d_coeffs, m, point_mont_host, (cudaStream_t)stream);
 }

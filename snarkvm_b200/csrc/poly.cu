@@ -144,4 +144,86 @@ int poly_evaluate_device(void* out_mont_host, const void* d_coeffs, size_t m, co
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Quotient of p / (x − z) — the KZG witness polynomial (polycommit/kzg10/mod.rs:220-241).  q_{L−1} = p_L, q_{i−1} = p_i + z·q_i
+// (L = m − 1) is a first-order linear recurrence; it is cut into chunks of LIN_K coefficients:
+//   pass 1: each chunk's value at its low end assuming a zero carry-in (A_k),
+//   pass 2: one CTA chains the chunks, C_k = A_k + z^{len_k}·C_{k+1}, two levels deep, and leaves every chunk's carry-in,
+//   pass 3: each chunk reruns its recurrence from the true carry-in and writes q.
+// 2 Fr multiplications per coefficient.
+// ---------------------------------------------------------------------------------------------------------------------
+static constexpr int LIN_K = 64, LIN_THREADS = 256;
+__global__ void k_lin_local(const uint32_t* __restrict__ p, size_t L, FrArg z_arg, uint32_t* __restrict__ A) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x, bot = k * LIN_K;
+    if (bot >= L) return;
+    const size_t top = bot + LIN_K < L ? bot + LIN_K : L;
+    const Fr z = fr_from_arg(z_arg);
+    Fr acc = Fr::zero();
+    for (size_t i = top; i-- > bot;) acc = acc * z + Fr::load_ldg(p + (i + 1) * 8);
+    acc.store(A + k * 8);
+}
+__global__ void __launch_bounds__(LIN_THREADS) k_lin_carry(const uint32_t* __restrict__ A, size_t nchunks, size_t L, FrArg z_arg,
+                                                            uint32_t* __restrict__ cin) {
+    __shared__ uint4 shB4[LIN_THREADS * 2], shW4[LIN_THREADS * 2];
+    uint32_t* shB = reinterpret_cast<uint32_t*>(shB4);
+    uint32_t* shW = reinterpret_cast<uint32_t*>(shW4);
+    const Fr z = fr_from_arg(z_arg);
+    const Fr zK = fr_pow_u64(z, LIN_K);
+    const Fr zlast = fr_pow_u64(z, (uint64_t)(L - (nchunks - 1) * LIN_K));      // the highest chunk may be short
+    const size_t per = (nchunks + LIN_THREADS - 1) / LIN_THREADS;
+    const size_t k0 = (size_t)threadIdx.x * per, k1 = k0 + per < nchunks ? k0 + per : nchunks;
+    Fr B = Fr::zero(), W = Fr::one();
+    for (size_t k = k1; k-- > k0 && k0 < nchunks;) {
+        const Fr zl = (k == nchunks - 1) ? zlast : zK;
+        B = Fr::load_ldg(A + k * 8) + zl * B;
+        W = W * zl;
+    }
+    B.store(shB + threadIdx.x * 8);
+    W.store(shW + threadIdx.x * 8);
+    __syncthreads();
+    if (threadIdx.x == 0) {                                  // D_t = value entering super-chunk t from above
+        Fr D = Fr::zero();
+        for (int t = LIN_THREADS - 1; t >= 0; t--) {
+            Fr Bt = Fr::load(shB + t * 8), Wt = Fr::load(shW + t * 8);
+            D.store(shB + t * 8);                            // carry-in of super-chunk t
+            D = Bt + Wt * D;
+        }
+    }
+    __syncthreads();
+    Fr C = Fr::load(shB + threadIdx.x * 8);
+    for (size_t k = k1; k-- > k0 && k0 < nchunks;) {
+        C.store(cin + k * 8);
+        const Fr zl = (k == nchunks - 1) ? zlast : zK;
+        C = Fr::load_ldg(A + k * 8) + zl * C;
+    }
+}
+__global__ void k_lin_final(const uint32_t* __restrict__ p, size_t L, FrArg z_arg, const uint32_t* __restrict__ cin, uint32_t* __restrict__ q) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x, bot = k * LIN_K;
+    if (bot >= L) return;
+    const size_t top = bot + LIN_K < L ? bot + LIN_K : L;
+    const Fr z = fr_from_arg(z_arg);
+    Fr acc = Fr::load_ldg(cin + k * 8);
+    for (size_t i = top; i-- > bot;) { acc = acc * z + Fr::load_ldg(p + (i + 1) * 8); acc.store(q + i * 8); }
+}
+
+int poly_divide_by_linear_device(void* d_q, const void* d_p, size_t m, const void* point_mont_host, cudaStream_t stream) {
+    if (m <= 1) return 0;
+    if (!d_q || !d_p || !point_mont_host) return (int)cudaErrorInvalidValue;
+    ensure_pool_configured();
+    FrArg z;
+    memcpy(z.v, point_mont_host, 32);
+    const size_t L = m - 1, nchunks = (L + LIN_K - 1) / LIN_K;
+    uint32_t* scratch = nullptr;                             // A[nchunks] then cin[nchunks]
+    cudaError_t e = cudaMallocAsync(&scratch, nchunks * 64, stream);
+    if (e != cudaSuccess) return (int)e;
+    const unsigned grid = (unsigned)((nchunks + 127) / 128);
+    k_lin_local<<<grid, 128, 0, stream>>>((const uint32_t*)d_p, L, z, scratch);
+    k_lin_carry<<<1, LIN_THREADS, 0, stream>>>(scratch, nchunks, L, z, scratch + nchunks * 8);
+    k_lin_final<<<grid, 128, 0, stream>>>((const uint32_t*)d_p, L, z, scratch + nchunks * 8, (uint32_t*)d_q);
+    count_launch(3);
+    int rc = (int)cudaGetLastError();
+    cudaFreeAsync(scratch, stream);
+    return rc;
+}
+
 }  // namespace b200

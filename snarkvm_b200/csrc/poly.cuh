@@ -12,6 +12,9 @@ int fr_batch_inversion_and_mul_device(void* d_v, size_t n, const void* coeff_mon
 // p (m coefficients) = q·(x^n − 1) + r:  d_q gets max(m − n, 0) coefficients, d_r gets min(m, n).
 int poly_divide_by_vanishing_device(void* d_q, void* d_r, const void* d_p, size_t m, size_t n, cudaStream_t stream);
 
+// quotient of p (m coefficients) / (x − point): d_q gets m − 1 coefficients (the KZG witness polynomial, kzg10/mod.rs:220-241)
+int poly_divide_by_linear_device(void* d_q, const void* d_p, size_t m, const void* point_mont_host, cudaStream_t stream);
+
 // out = Σ c_i·point^i (Montgomery in and out; out and point are 32-byte HOST buffers; synchronises the stream)
 int poly_evaluate_device(void* out_mont_host, const void* d_coeffs, size_t m, const void* point_mont_host, cudaStream_t stream);
 

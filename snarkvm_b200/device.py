@@ -205,6 +205,17 @@ def poly_divide_by_vanishing(p: torch.Tensor, domain_size: int):
     return q, r
 
 
+def poly_divide_by_linear(p: torch.Tensor, point_mont) -> torch.Tensor:
+    """Quotient of p / (x − point), the KZG witness polynomial (kzg10/mod.rs:220-241) → CUDA tensor [m − 1, 4] i64, not trimmed."""
+    z = _fr_host(point_mont)
+    m = _nbytes(p) // 32
+    q = torch.empty((max(m - 1, 0), 4), dtype=torch.int64, device=p.device)
+    if m > 1:
+        with torch.cuda.device(p.device):
+            _lib.check(_lib.lib().snarkvm_b200_poly_divide_by_linear_device(q.data_ptr(), _check(p, "p"), m, z.ctypes.data, _stream()))
+    return q
+
+
 def poly_evaluate(coeffs: torch.Tensor, point_mont) -> np.ndarray:
     """DensePolynomial::evaluate (fft/polynomial/dense.rs:98-114) → Montgomery Fr as uint64[4] on the host."""
     z = _fr_host(point_mont)

@@ -128,3 +128,38 @@ def test_evaluate_large_and_over_domain(oracle_cpu):
     ev = DensePolynomial(_dev(small)).evaluate_over_domain(EvaluationDomain.new(512))
     padded = np.zeros((512, 4), dtype=np.uint64); padded[:300] = small
     assert (_host_u64(ev).reshape(-1, 4) == oracle_cpu.ntt(padded, oracle_cpu.FORWARD)).all()
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 64, 65, 66, 4097, 64 * 256 + 1, 64 * 256 * 3 + 17, (1 << 20) + 5])
+def test_divide_by_linear_vs_oracle(oracle_cpu, m):
+    """compute_witness_polynomial (kzg10/mod.rs:220-241): chunk boundaries of the three-pass recurrence, zero / one / random points"""
+    from snarkvm_b200 import device
+    p = random_fr_mont(m, seed=m)
+    if m > 3:
+        p[-2:] = 0                                             # true degree below the slot count
+    dp = _dev(p)
+    points = [np.zeros(4, dtype=np.uint64), fr_ints_to_mont_array([1])[0], random_fr_mont(1, seed=3)[0]]
+    for z in points[: 3 if m < (1 << 20) else 1] + points[2:]:
+        got = _host_u64(device.poly_divide_by_linear(dp, z)).reshape(-1, 4)
+        assert (got == oracle_cpu.poly_divide_by_linear(p, z)).all()
+
+
+def test_kzg_open(oracle_cpu):
+    """KZG10::open (kzg10/mod.rs:220-321), hiding and not: w = commit(p / (x − z)) [+ commit_γ(blinding / (x − z))], random_v = blinding(z)"""
+    from snarkvm_b200.algorithms import KZG10
+    from snarkvm_b200 import device
+    n = 1 << 11
+    powers = device.generate_bases(n, seed=51)
+    gamma = device.generate_bases(4, seed=52)
+    hp, hg = powers.cpu().numpy(), gamma.cpu().numpy()
+    poly = random_fr_mont(n, seed=4)
+    blind = random_fr_mont(3, seed=5)
+    z = random_fr_mont(1, seed=6)[0]
+    wq = oracle_cpu.poly_divide_by_linear(poly, z)
+    bq = oracle_cpu.poly_divide_by_linear(blind, z)
+    w_plain = oracle_cpu.msm(hp, oracle_cpu.fr_from_mont(wq), 0)
+    w, v = KZG10.open(powers, _dev(poly), z)
+    assert v is None and (w == w_plain).all()
+    w, v = KZG10.open(powers, _dev(poly), z, gamma, _dev(blind))
+    assert (w == oracle_cpu.g1_add(w_plain, oracle_cpu.msm(hg, oracle_cpu.fr_from_mont(bq), 0))).all()
+    assert (v == oracle_cpu.poly_evaluate(blind, z)).all()

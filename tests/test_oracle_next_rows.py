@@ -76,3 +76,22 @@ def test_divide_by_vanishing_and_evaluate(oracle_cpu):
         z = rnd.randrange(py.R_MOD)
         want = sum(c * pow(z, i, py.R_MOD) for i, c in enumerate(p)) % py.R_MOD
         assert mont_array_to_fr_ints(oracle_cpu.poly_evaluate(fr_ints_to_mont_array(p), fr_ints_to_mont_array([z])[0]).reshape(1, 4)) == [want]
+
+
+def test_divide_by_linear(oracle_cpu):
+    """witness polynomial: p(x) = q(x)·(x − z) + p(z)"""
+    rnd = random.Random(8)
+    for m in (1, 2, 3, 17, 200):
+        p = [rnd.randrange(py.R_MOD) for _ in range(m)]
+        if m == 17:
+            p[-2:] = [0, 0]
+        for z in (0, 1, rnd.randrange(py.R_MOD)):
+            q = mont_array_to_fr_ints(oracle_cpu.poly_divide_by_linear(fr_ints_to_mont_array(p), fr_ints_to_mont_array([z])[0]))
+            assert len(q) == m - 1
+            pz = sum(c * pow(z, i, py.R_MOD) for i, c in enumerate(p)) % py.R_MOD
+            back = [0] * m
+            for i, c in enumerate(q):
+                back[i + 1] = (back[i + 1] + c) % py.R_MOD
+                back[i] = (back[i] - c * z) % py.R_MOD
+            back[0] = (back[0] + pz) % py.R_MOD
+            assert back == p, (m, z)
