@@ -147,6 +147,11 @@ SNARKVM_API int snarkvm_b200_poly_divide_by_vanishing_device(void* d_q, void* d_
 /* KZG10::compute_witness_polynomial (polycommit/kzg10/mod.rs:220-241): quotient of p (m coefficients) / (x - point); d_q receives
  * m - 1 coefficients; the remainder p(point) is dropped as in the reference.  point: 32 B Montgomery, HOST. */
 SNARKVM_API int snarkvm_b200_poly_divide_by_linear_device(void* d_q, const void* d_p, size_t m, const void* point_mont_host, void* stream);
+/* z_M = M * (public || private) for a sparse R1CS matrix (inner_product, snark/varuna/ahp/prover/round_functions/mod.rs:169-189,
+ * called per row of A, B, C at :128-152).  CSR in HBM: row_ptr = nrows + 1 u32, cols = u32 indices into d_x (nvars Montgomery Fr),
+ * vals = Montgomery Fr.  A column >= nvars makes the call return cudaErrorInvalidValue. */
+SNARKVM_API int snarkvm_b200_sparse_matvec_device(void* d_out, const void* d_row_ptr, const void* d_cols, const void* d_vals, size_t nrows,
+                                                  const void* d_x, size_t nvars, void* stream);
 /* DensePolynomial::evaluate (fft/polynomial/dense.rs:98-114): out = sum c_i * point^i; out and point are 32-byte HOST buffers. */
 SNARKVM_API int snarkvm_b200_poly_evaluate_device(void* out_mont_host, const void* d_coeffs, size_t m, const void* point_mont_host,
                                                   void* stream);

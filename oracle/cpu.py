@@ -247,3 +247,16 @@ def poly_divide_by_linear(p: np.ndarray, point: np.ndarray) -> np.ndarray:
     lib().oracle_poly_divide_by_linear.restype = ctypes.c_size_t
     lib().oracle_poly_divide_by_linear(_p(q), _p(p), ctypes.c_size_t(m), _p(z))
     return q[:max(m - 1, 0)]
+
+
+def sparse_matvec(row_ptr, cols, vals, public_vars, private_vars) -> np.ndarray:
+    """inner_product per row (varuna/ahp/prover/round_functions/mod.rs:169-189) for a CSR matrix → [nrows, 4]."""
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint32)
+    cols = np.ascontiguousarray(cols, dtype=np.uint32)
+    vals = np.ascontiguousarray(vals, dtype=np.uint64).reshape(-1, 4)
+    pub = np.ascontiguousarray(public_vars, dtype=np.uint64).reshape(-1, 4)
+    prv = np.ascontiguousarray(private_vars, dtype=np.uint64).reshape(-1, 4)
+    nrows = row_ptr.shape[0] - 1
+    out = np.zeros((max(nrows, 1), 4), dtype=np.uint64)
+    lib().oracle_sparse_matvec(_p(out), _p(row_ptr), _p(cols), _p(vals), ctypes.c_size_t(nrows), _p(pub), ctypes.c_size_t(pub.shape[0]), _p(prv))
+    return out[:nrows]

@@ -902,6 +902,26 @@ API size_t oracle_poly_divide_by_linear(uint64_t *q_out, const uint64_t *p, size
     return qslots;
 }
 
+/* z_M = M·(public ‖ private) row by row — inner_product, snark/varuna/ahp/prover/round_functions/mod.rs:169-189
+ * (called for A, B, C at :128-152).  CSR: row r owns entries [row_ptr[r], row_ptr[r+1]) of (vals, cols). */
+API void oracle_sparse_matvec(uint64_t *out, const uint32_t *row_ptr, const uint32_t *cols, const uint64_t *vals, size_t nrows,
+                              const uint64_t *public_vars, size_t num_public, const uint64_t *private_vars) {
+    fr_t one = fr_one();
+#pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < nrows; r++) {
+        fr_t result = {{0, 0, 0, 0}};
+        for (uint32_t e = row_ptr[r]; e < row_ptr[r + 1]; e++) {
+            size_t i = cols[e];
+            const fr_t *variable = i < num_public ? (const fr_t *)(public_vars + 4 * i) : (const fr_t *)(private_vars + 4 * (i - num_public));
+            const fr_t *coefficient = (const fr_t *)(vals + 4 * e);
+            fr_t t;
+            if (memcmp(coefficient, &one, 32) == 0) t = *variable; else fr_mul(&t, variable, coefficient);
+            fr_add(&result, &result, &t);
+        }
+        memcpy(out + 4 * r, &result, 32);
+    }
+}
+
 /* normalise: p.to_affine().to_projective() — the byte image the parity tests compare */
 static void write_normalised(uint64_t *out144, const g1_proj_t *p) {
     g1_affine_t a = proj_to_affine(p); g1_proj_t q = aff_to_proj(&a); memcpy(out144, &q, 144);

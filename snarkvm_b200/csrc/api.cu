@@ -503,6 +503,10 @@ int snarkvm_b200_poly_divide_by_vanishing_device(void* d_q, void* d_r, const voi
 int snarkvm_b200_poly_divide_by_linear_device(void* d_q, const void* d_p, size_t m, const void* point_mont_host, void* stream) {
     return poly_divide_by_linear_device(d_q, d_p, m, point_mont_host, (cudaStream_t)stream);
 }
+int snarkvm_b200_sparse_matvec_device(void* d_out, const void* d_row_ptr, const void* d_cols, const void* d_vals, size_t nrows, const void* d_x,
+                                      size_t nvars, void* stream) {
+    return sparse_matvec_device(d_out, d_row_ptr, d_cols, d_vals, nrows, d_x, nvars, (cudaStream_t)stream);
+}
 int snarkvm_b200_poly_evaluate_device(void* out_mont_host, const void* d_coeffs, size_t m, const void* point_mont_host, void* stream) {
     return poly_evaluate_device(out_mont_host, d_coeffs, m, point_mont_host, (cudaStream_t)stream);
 }

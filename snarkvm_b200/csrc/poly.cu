@@ -226,4 +226,42 @@ int poly_divide_by_linear_device(void* d_q, const void* d_p, size_t m, const voi
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// z_M = M·z for a sparse R1CS matrix in CSR form — inner_product (snark/varuna/ahp/prover/round_functions/mod.rs:169-189),
+// the per-row loop the prover runs for A, B and C (:128-152).  One thread per row (rows hold a handful of entries).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void k_sparse_matvec(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ cols, const uint32_t* __restrict__ vals,
+                                size_t nrows, const uint32_t* __restrict__ x, size_t nvars, uint32_t* __restrict__ out, int* __restrict__ bad) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    Fr acc = Fr::zero();
+    for (uint32_t e = row_ptr[r]; e < row_ptr[r + 1]; e++) {
+        const uint32_t c = cols[e];
+        if (c >= nvars) { *bad = 1; continue; }              // out-of-range column: reported, never read
+        acc = acc + Fr::load_ldg(x + (size_t)c * 8) * Fr::load_ldg(vals + (size_t)e * 8);
+    }
+    acc.store(out + r * 8);
+}
+
+int sparse_matvec_device(void* d_out, const void* d_row_ptr, const void* d_cols, const void* d_vals, size_t nrows, const void* d_x,
+                         size_t nvars, cudaStream_t stream) {
+    if (nrows == 0) return 0;
+    if (!d_out || !d_row_ptr || !d_x) return (int)cudaErrorInvalidValue;
+    ensure_pool_configured();
+    int* bad = nullptr;
+    cudaError_t e = cudaMallocAsync(&bad, sizeof(int), stream);
+    if (e != cudaSuccess) return (int)e;
+    int rc = (int)cudaMemsetAsync(bad, 0, sizeof(int), stream);
+    k_sparse_matvec<<<(unsigned)((nrows + 127) / 128), 128, 0, stream>>>((const uint32_t*)d_row_ptr, (const uint32_t*)d_cols, (const uint32_t*)d_vals,
+                                                                         nrows, (const uint32_t*)d_x, nvars, (uint32_t*)d_out, bad);
+    count_launch();
+    if (rc == 0) rc = (int)cudaGetLastError();
+    int h_bad = 0;
+    if (rc == 0) rc = (int)cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    cudaFreeAsync(bad, stream);
+    if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
+    if (rc == 0 && h_bad) rc = (int)cudaErrorInvalidValue;
+    return rc;
+}
+
 }  // namespace b200

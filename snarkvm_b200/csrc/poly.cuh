@@ -18,6 +18,11 @@ int poly_divide_by_linear_device(void* d_q, const void* d_p, size_t m, const voi
 // out = Σ c_i·point^i (Montgomery in and out; out and point are 32-byte HOST buffers; synchronises the stream)
 int poly_evaluate_device(void* out_mont_host, const void* d_coeffs, size_t m, const void* point_mont_host, cudaStream_t stream);
 
+// out[r] = Σ_e vals[e]·x[cols[e]] over e ∈ [row_ptr[r], row_ptr[r+1]) — CSR sparse matrix × vector over Fr (Montgomery);
+// row_ptr: nrows + 1 u32, cols: u32.  A column ≥ nvars returns cudaErrorInvalidValue.  Synchronises the stream.
+int sparse_matvec_device(void* d_out, const void* d_row_ptr, const void* d_cols, const void* d_vals, size_t nrows, const void* d_x,
+                         size_t nvars, cudaStream_t stream);
+
 // Group FFT over G1 (DomainCoeff = G1Projective, fft/domain.rs:169-221 generic path): n = 2^lg affine points in, affine points
 // out (natural order both sides).  direction 1 = inverse (includes n^{-1}): UniversalParams::lagrange_basis
 // (polycommit/kzg10/data_structures.rs:68-72).

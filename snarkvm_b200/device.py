@@ -205,6 +205,22 @@ def poly_divide_by_vanishing(p: torch.Tensor, domain_size: int):
     return q, r
 
 
+def sparse_matvec(row_ptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """z_M = M·x for a CSR matrix over Fr (inner_product per row, varuna/ahp/prover/round_functions/mod.rs:130-189).
+    row_ptr: int32 [nrows + 1], cols: int32 [nnz], vals: [nnz, 4] i64 Montgomery, x: [nvars, 4] i64 Montgomery → [nrows, 4] i64."""
+    if row_ptr.dtype != torch.int32 or cols.dtype != torch.int32:
+        raise TypeError("row_ptr and cols must be int32 tensors")
+    nrows = row_ptr.numel() - 1
+    out = torch.empty((max(nrows, 0), 4), dtype=torch.int64, device=x.device)
+    if nrows > 0:
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().snarkvm_b200_sparse_matvec_device(out.data_ptr(), _check(row_ptr, "row_ptr"),
+                                                                     _check(cols, "cols") if cols.numel() else None,
+                                                                     _check(vals, "vals") if vals.numel() else None, nrows, _check(x, "x"),
+                                                                     _nbytes(x) // 32, _stream()))
+    return out
+
+
 def poly_divide_by_linear(p: torch.Tensor, point_mont) -> torch.Tensor:
     """Quotient of p / (x − point), the KZG witness polynomial (kzg10/mod.rs:220-241) → CUDA tensor [m − 1, 4] i64, not trimmed."""
     z = _fr_host(point_mont)

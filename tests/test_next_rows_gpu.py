@@ -163,3 +163,25 @@ def test_kzg_open(oracle_cpu):
     w, v = KZG10.open(powers, _dev(poly), z, gamma, _dev(blind))
     assert (w == oracle_cpu.g1_add(w_plain, oracle_cpu.msm(hg, oracle_cpu.fr_from_mont(bq), 0))).all()
     assert (v == oracle_cpu.poly_evaluate(blind, z)).all()
+
+
+def test_sparse_matvec_vs_oracle(oracle_cpu):
+    """z_A = A·z as the Varuna prover computes it (round_functions/mod.rs:130-189), CSR on the device"""
+    import torch
+    from snarkvm_b200 import CudaError, device
+    rng = np.random.default_rng(3)
+    nrows, npub, nprv = 5000, 17, 4000
+    counts = rng.integers(0, 9, size=nrows)
+    counts[7] = 0
+    row_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
+    nnz = int(row_ptr[-1])
+    cols = rng.integers(0, npub + nprv, size=nnz).astype(np.uint32)
+    vals = random_fr_mont(nnz, seed=1)
+    vals[::3] = fr_ints_to_mont_array([1])[0]
+    pub, prv = random_fr_mont(npub, seed=2), random_fr_mont(nprv, seed=3)
+    x = np.concatenate([pub, prv])
+    got = device.sparse_matvec(torch.from_numpy(row_ptr.view(np.int32)).cuda(), torch.from_numpy(cols.view(np.int32)).cuda(), _dev(vals), _dev(x))
+    assert (_host_u64(got).reshape(-1, 4) == oracle_cpu.sparse_matvec(row_ptr, cols, vals, pub, prv)).all()
+    bad = cols.copy(); bad[5] = npub + nprv
+    with pytest.raises(CudaError):
+        device.sparse_matvec(torch.from_numpy(row_ptr.view(np.int32)).cuda(), torch.from_numpy(bad.view(np.int32)).cuda(), _dev(vals), _dev(x))

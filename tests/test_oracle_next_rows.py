@@ -95,3 +95,21 @@ def test_divide_by_linear(oracle_cpu):
                 back[i] = (back[i] - c * z) % py.R_MOD
             back[0] = (back[0] + pz) % py.R_MOD
             assert back == p, (m, z)
+
+
+def test_sparse_matvec(oracle_cpu):
+    rnd = random.Random(9)
+    nrows, npub, nprv = 40, 5, 30
+    pub = [rnd.randrange(py.R_MOD) for _ in range(npub)]
+    prv = [rnd.randrange(py.R_MOD) for _ in range(nprv)]
+    row_ptr, cols, vals = [0], [], []
+    for r in range(nrows):
+        for _ in range(rnd.randrange(0, 6)):
+            cols.append(rnd.randrange(npub + nprv))
+            vals.append(1 if rnd.random() < 0.3 else rnd.randrange(py.R_MOD))      # coefficient.is_one() shortcut (mod.rs:186)
+        row_ptr.append(len(cols))
+    got = mont_array_to_fr_ints(oracle_cpu.sparse_matvec(row_ptr, cols, fr_ints_to_mont_array(vals) if vals else np.zeros((0, 4), np.uint64),
+                                                         fr_ints_to_mont_array(pub), fr_ints_to_mont_array(prv)))
+    x = pub + prv
+    want = [sum(vals[e] * x[cols[e]] for e in range(row_ptr[r], row_ptr[r + 1])) % py.R_MOD for r in range(nrows)]
+    assert got == want
