@@ -232,12 +232,16 @@ class DensePolynomial:
         return DensePolynomial(q), DensePolynomial(r)
 
     def evaluate_over_domain(self, domain: "EvaluationDomain"):
-        """dense.rs:172-181 for degree < domain.size: zero-pad and FFT"""
+        """dense.rs:172-181 → polynomial/mod.rs:266-290: zero-pad and FFT; when degree ≥ domain.size the reference FFTs every
+        domain-sized chunk of coefficients and adds the results — the same values as one FFT of the coefficients folded
+        modulo x^n − 1, which is the remainder of divide_by_vanishing_poly."""
         import torch
-        if self.coeffs.shape[0] > domain.size:
-            raise ValueError("degree ≥ domain size is not supported on the device path")
-        x = torch.zeros((domain.size, 4), dtype=self.coeffs.dtype, device=self.coeffs.device)
-        x[: self.coeffs.shape[0]] = self.coeffs
+        from . import device
+        coeffs = self.coeffs
+        if coeffs.shape[0] > domain.size:
+            _, coeffs = device.poly_divide_by_vanishing(coeffs, domain.size)
+        x = torch.zeros((domain.size, 4), dtype=coeffs.dtype, device=coeffs.device)
+        x[: coeffs.shape[0]] = coeffs
         return domain.fft_in_place(x)
 
 

@@ -128,6 +128,15 @@ def test_evaluate_large_and_over_domain(oracle_cpu):
     ev = DensePolynomial(_dev(small)).evaluate_over_domain(EvaluationDomain.new(512))
     padded = np.zeros((512, 4), dtype=np.uint64); padded[:300] = small
     assert (_host_u64(ev).reshape(-1, 4) == oracle_cpu.ntt(padded, oracle_cpu.FORWARD)).all()
+    # degree ≥ domain size (polynomial/mod.rs:277-288): per-chunk FFTs added up, restated here with the oracle
+    big = random_fr_mont(1300, seed=8)
+    ev = DensePolynomial(_dev(big)).evaluate_over_domain(EvaluationDomain.new(512))
+    acc = np.zeros((512, 4), dtype=np.uint64)
+    for c0 in range(0, 1300, 512):
+        chunk = np.zeros((512, 4), dtype=np.uint64); chunk[: min(512, 1300 - c0)] = big[c0:c0 + 512]
+        e = oracle_cpu.ntt(chunk, oracle_cpu.FORWARD)
+        acc = np.array([oracle_cpu.fr_add(a, b) for a, b in zip(acc, e)])
+    assert (_host_u64(ev).reshape(-1, 4) == acc).all()
 
 
 @pytest.mark.parametrize("m", [1, 2, 3, 64, 65, 66, 4097, 64 * 256 + 1, 64 * 256 * 3 + 17, (1 << 20) + 5])
