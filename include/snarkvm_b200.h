@@ -152,6 +152,12 @@ SNARKVM_API int snarkvm_b200_poly_divide_by_linear_device(void* d_q, const void*
  * vals = Montgomery Fr.  A column >= nvars makes the call return cudaErrorInvalidValue. */
 SNARKVM_API int snarkvm_b200_sparse_matvec_device(void* d_out, const void* d_row_ptr, const void* d_cols, const void* d_vals, size_t nrows,
                                                   const void* d_x, size_t nvars, void* stream);
+/* Elementwise Fr arithmetic on HBM vectors (the zip loops between transforms, e.g. polycommit/kzg10/mod.rs:292-297,
+ * fft/evaluations.rs:49-74): op 0 = a + b, 1 = a - b, 2 = a * b; out may alias an input; the scalar form takes a 32-byte HOST scalar. */
+SNARKVM_API int snarkvm_b200_fr_vec_op_device(void* d_out, const void* d_a, const void* d_b, size_t n, int op, void* stream);
+SNARKVM_API int snarkvm_b200_fr_vec_scalar_op_device(void* d_out, const void* d_a, const void* scalar_mont_host, size_t n, int op, void* stream);
+/* EvaluationDomain::elements (fft/domain.rs:307-309): d_out[i] = group_gen^i, i < 2^lg, Montgomery. */
+SNARKVM_API int snarkvm_b200_domain_elements_device(void* d_out, uint32_t lg, void* stream);
 /* DensePolynomial::evaluate (fft/polynomial/dense.rs:98-114): out = sum c_i * point^i; out and point are 32-byte HOST buffers. */
 SNARKVM_API int snarkvm_b200_poly_evaluate_device(void* out_mont_host, const void* d_coeffs, size_t m, const void* point_mont_host,
                                                   void* stream);

@@ -26,6 +26,7 @@ SYMBOLS = (
     "snarkvm_b200_kzg_commit_hiding_device", "snarkvm_b200_kzg_commit_batch_device", "snarkvm_b200_g1_ntt_device",
     "snarkvm_b200_fr_batch_inversion_and_mul_device", "snarkvm_b200_poly_divide_by_vanishing_device", "snarkvm_b200_poly_evaluate_device",
     "snarkvm_b200_poly_divide_by_linear_device", "snarkvm_b200_sparse_matvec_device",
+    "snarkvm_b200_fr_vec_op_device", "snarkvm_b200_fr_vec_scalar_op_device", "snarkvm_b200_domain_elements_device",
 )
 
 
@@ -96,6 +97,9 @@ def lib():
     L.snarkvm_b200_poly_evaluate_device.argtypes = [vp, vp, sz, vp, vp]
     L.snarkvm_b200_poly_divide_by_linear_device.argtypes = [vp, vp, sz, vp, vp]
     L.snarkvm_b200_sparse_matvec_device.argtypes = [vp, vp, vp, vp, sz, vp, sz, vp]
+    L.snarkvm_b200_fr_vec_op_device.argtypes = [vp, vp, vp, sz, i32, vp]
+    L.snarkvm_b200_fr_vec_scalar_op_device.argtypes = [vp, vp, vp, sz, i32, vp]
+    L.snarkvm_b200_domain_elements_device.argtypes = [vp, u32, vp]
     for s in SYMBOLS[5:]:
         getattr(L, s).restype = i32
     L.snarkvm_b200_launch_count.restype = u64

@@ -142,6 +142,21 @@ class PolyMultiplier:
                             [np.ascontiguousarray(e) for e in self.evaluations])
 
 
+_R_MOD = 8444461749428370424248824938781546531375899335154063827935233455917409239041   # curves/src/bls12_377/fr.rs:138-145
+
+
+def _fr_mont_to_int(x) -> int:
+    """host-side to_bigint of one Montgomery Fr (uint64[4]) — only for argument checks such as `point ∉ domain`"""
+    limbs = np.ascontiguousarray(x, dtype=np.uint64).reshape(4)
+    m = sum(int(v) << (64 * i) for i, v in enumerate(limbs))
+    return m * pow(1 << 256, -1, _R_MOD) % _R_MOD
+
+
+def _fr_int_to_mont(v: int) -> np.ndarray:
+    m = (v << 256) % _R_MOD
+    return np.array([(m >> (64 * i)) & (2**64 - 1) for i in range(4)], dtype=np.uint64)
+
+
 class KZG10:
     """The MSM-bearing parts of KZG10 (algorithms/src/polycommit/kzg10/mod.rs:98-206) on device-resident operands
     (torch CUDA tensors; Montgomery coefficients, the reference's in-memory affine points)."""
@@ -189,6 +204,23 @@ class KZG10:
         """mod.rs:303-321: compute_witness_polynomial then open_with_witness_polynomial"""
         w, rw = KZG10.compute_witness_polynomial(polynomial_mont, point_mont, blinding_mont)
         return KZG10.open_with_witness_polynomial(powers_of_beta_g, point_mont, w, powers_of_beta_times_gamma_g, blinding_mont, rw)
+
+    @staticmethod
+    def open_lagrange(lagrange_basis_at_beta_g, domain: "EvaluationDomain", evaluations_mont, point_mont, evaluation_at_point_mont):
+        """mod.rs:272-301: witness evaluations (eval_i − y)/(ω^i − point) committed against the Lagrange basis; the point must not
+        lie in the domain and len(evaluations) must equal the domain (= basis) size."""
+        from . import device
+        n = evaluations_mont.shape[0]
+        if (1 << max(n - 1, 0).bit_length()) != domain.size or n != domain.size:
+            raise ValueError("`evaluations.len()` must equal `domain.size()`")                # mod.rs:286-290, 294
+        z = _fr_mont_to_int(point_mont)
+        if pow(z, domain.size, _R_MOD) == 1:
+            raise ValueError("Point cannot be in the domain")                                  # mod.rs:283-285
+        divisor = device.fr_vec_op(device.domain_elements(domain.log_size_of_group, evaluations_mont.device), point_mont, device.FR_SUB)
+        device.fr_batch_inversion_and_mul(divisor, _fr_int_to_mont(1))                         # batch_inversion, mod.rs:293
+        num = device.fr_vec_op(evaluations_mont, evaluation_at_point_mont, device.FR_SUB)
+        device.fr_vec_op(divisor, num, device.FR_MUL, out=divisor)
+        return KZG10.commit_lagrange(lagrange_basis_at_beta_g, divisor), None
 
     @staticmethod
     def batch_commit(powers_of_beta_g, polynomials_mont):

@@ -507,6 +507,15 @@ int snarkvm_b200_sparse_matvec_device(void* d_out, const void* d_row_ptr, const 
                                       size_t nvars, void* stream) {
     return sparse_matvec_device(d_out, d_row_ptr, d_cols, d_vals, nrows, d_x, nvars, (cudaStream_t)stream);
 }
+int snarkvm_b200_fr_vec_op_device(void* d_out, const void* d_a, const void* d_b, size_t n, int op, void* stream) {
+    return fr_vec_op_device(d_out, d_a, d_b, n, op, (cudaStream_t)stream);
+}
+int snarkvm_b200_fr_vec_scalar_op_device(void* d_out, const void* d_a, const void* scalar_mont_host, size_t n, int op, void* stream) {
+    return fr_vec_scalar_op_device(d_out, d_a, scalar_mont_host, n, op, (cudaStream_t)stream);
+}
+int snarkvm_b200_domain_elements_device(void* d_out, uint32_t lg, void* stream) {
+    return domain_elements_device(d_out, lg, (cudaStream_t)stream);
+}
 int snarkvm_b200_poly_evaluate_device(void* out_mont_host, const void* d_coeffs, size_t m, const void* point_mont_host, void* stream) {
     return poly_evaluate_device(out_mont_host, d_coeffs, m, point_mont_host, (cudaStream_t)stream);
 }

@@ -264,4 +264,55 @@ int sparse_matvec_device(void* d_out, const void* d_row_ptr, const void* d_cols,
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Elementwise Fr arithmetic on HBM vectors (the `cfg_iter_mut!(..).zip(..)` loops between transforms, e.g.
+// polycommit/kzg10/mod.rs:292-297, fft/evaluations.rs:49-74) and the domain's elements (fft/domain.rs:307-309, 980-988).
+// op: 0 = a + b, 1 = a − b, 2 = a · b.  out may alias a or b.
+// ---------------------------------------------------------------------------------------------------------------------
+FF_DEV Fr fr_apply(int op, const Fr& a, const Fr& b) { return op == 0 ? a + b : op == 1 ? a - b : a * b; }
+__global__ void k_fr_vec_op(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n, int op) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fr_apply(op, Fr::load(a + i * 8), Fr::load(b + i * 8)).store(out + i * 8);
+}
+__global__ void k_fr_vec_scalar_op(uint32_t* out, const uint32_t* a, FrArg s_arg, size_t n, int op) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fr_apply(op, Fr::load(a + i * 8), fr_from_arg(s_arg)).store(out + i * 8);
+}
+// out[i] = ω_n^i from the NTT's table ω_N^j (j < N/2): ω_n^i = ω_N^{i·N/n}, and ω^{i} = −ω^{i − n/2} in the upper half
+__global__ void k_domain_elements(uint32_t* __restrict__ out, int lg, const uint32_t* __restrict__ tw, int lgN) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)1 << lg, half = n >> 1;
+    if (i >= n) return;
+    if (lg == 0) { Fr::one().store(out); return; }
+    const size_t j = i < half ? i : i - half;
+    Fr w = Fr::load_ldg(tw + (j << (lgN - lg)) * 8);
+    (i < half ? w : w.neg()).store(out + i * 8);
+}
+
+int fr_vec_op_device(void* d_out, const void* d_a, const void* d_b, size_t n, int op, cudaStream_t stream) {
+    if (n == 0) return 0;
+    if (!d_out || !d_a || !d_b || op < 0 || op > 2) return (int)cudaErrorInvalidValue;
+    k_fr_vec_op<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((uint32_t*)d_out, (const uint32_t*)d_a, (const uint32_t*)d_b, n, op);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+int fr_vec_scalar_op_device(void* d_out, const void* d_a, const void* scalar_mont_host, size_t n, int op, cudaStream_t stream) {
+    if (n == 0) return 0;
+    if (!d_out || !d_a || !scalar_mont_host || op < 0 || op > 2) return (int)cudaErrorInvalidValue;
+    FrArg sc;
+    memcpy(sc.v, scalar_mont_host, 32);
+    k_fr_vec_scalar_op<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((uint32_t*)d_out, (const uint32_t*)d_a, sc, n, op);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+int domain_elements_device(void* d_out, uint32_t lg, cudaStream_t stream) {
+    if (!d_out || lg > 30) return (int)cudaErrorInvalidValue;
+    const void* tw = nullptr;
+    int lgN = 0, rc = 0;
+    if (lg > 0 && (rc = ntt_get_twiddles((int)lg, &tw, &lgN)) != 0) return rc;
+    const size_t n = (size_t)1 << lg;
+    k_domain_elements<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((uint32_t*)d_out, (int)lg, (const uint32_t*)tw, lgN);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 }  // namespace b200

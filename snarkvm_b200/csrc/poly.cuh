@@ -23,6 +23,12 @@ int poly_evaluate_device(void* out_mont_host, const void* d_coeffs, size_t m, co
 int sparse_matvec_device(void* d_out, const void* d_row_ptr, const void* d_cols, const void* d_vals, size_t nrows, const void* d_x,
                          size_t nvars, cudaStream_t stream);
 
+// elementwise on n Montgomery Fr in HBM: op 0 = a + b, 1 = a − b, 2 = a·b; the scalar form takes a 32-byte HOST scalar
+int fr_vec_op_device(void* d_out, const void* d_a, const void* d_b, size_t n, int op, cudaStream_t stream);
+int fr_vec_scalar_op_device(void* d_out, const void* d_a, const void* scalar_mont_host, size_t n, int op, cudaStream_t stream);
+// out[i] = ω_n^i, i < n = 2^lg (EvaluationDomain::elements, fft/domain.rs:307-309)
+int domain_elements_device(void* d_out, uint32_t lg, cudaStream_t stream);
+
 // Group FFT over G1 (DomainCoeff = G1Projective, fft/domain.rs:169-221 generic path): n = 2^lg affine points in, affine points
 // out (natural order both sides).  direction 1 = inverse (includes n^{-1}): UniversalParams::lagrange_basis
 // (polycommit/kzg10/data_structures.rs:68-72).

@@ -205,6 +205,32 @@ def poly_divide_by_vanishing(p: torch.Tensor, domain_size: int):
     return q, r
 
 
+FR_ADD, FR_SUB, FR_MUL = 0, 1, 2
+
+
+def fr_vec_op(a: torch.Tensor, b, op: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Elementwise a (op) b on Montgomery Fr vectors in HBM; b is a tensor of the same length or one 32-byte host scalar."""
+    out = torch.empty_like(a) if out is None else out
+    n = _nbytes(a) // 32
+    with torch.cuda.device(a.device):
+        if isinstance(b, torch.Tensor):
+            if _nbytes(b) != _nbytes(a):
+                raise ValueError("length mismatch")
+            _lib.check(_lib.lib().snarkvm_b200_fr_vec_op_device(out.data_ptr(), _check(a, "a"), _check(b, "b"), n, op, _stream()))
+        else:
+            s = _fr_host(b)
+            _lib.check(_lib.lib().snarkvm_b200_fr_vec_scalar_op_device(out.data_ptr(), _check(a, "a"), s.ctypes.data, n, op, _stream()))
+    return out
+
+
+def domain_elements(lg: int, device="cuda") -> torch.Tensor:
+    """EvaluationDomain::elements (fft/domain.rs:307-309): [2^lg, 4] i64, element i = group_gen^i (Montgomery)."""
+    out = torch.empty((1 << lg, 4), dtype=torch.int64, device=device)
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().snarkvm_b200_domain_elements_device(out.data_ptr(), lg, _stream()))
+    return out
+
+
 def sparse_matvec(row_ptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     """z_M = M·x for a CSR matrix over Fr (inner_product per row, varuna/ahp/prover/round_functions/mod.rs:130-189).
     row_ptr: int32 [nrows + 1], cols: int32 [nnz], vals: [nnz, 4] i64 Montgomery, x: [nvars, 4] i64 Montgomery → [nrows, 4] i64."""

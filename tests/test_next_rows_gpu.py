@@ -194,3 +194,59 @@ def test_sparse_matvec_vs_oracle(oracle_cpu):
     bad = cols.copy(); bad[5] = npub + nprv
     with pytest.raises(CudaError):
         device.sparse_matvec(torch.from_numpy(row_ptr.view(np.int32)).cuda(), torch.from_numpy(bad.view(np.int32)).cuda(), _dev(vals), _dev(x))
+
+
+def test_fr_vec_ops_and_domain_elements(oracle_cpu):
+    from snarkvm_b200 import device
+    n = 1000
+    a, b = random_fr_mont(n, seed=1), random_fr_mont(n, seed=2)
+    s = random_fr_mont(1, seed=3)[0]
+    for op, f in ((device.FR_ADD, oracle_cpu.fr_add), (device.FR_SUB, oracle_cpu.fr_sub), (device.FR_MUL, oracle_cpu.fr_mul)):
+        got = _host_u64(device.fr_vec_op(_dev(a), _dev(b), op)).reshape(-1, 4)
+        assert (got == np.array([f(x, y) for x, y in zip(a, b)])).all(), op
+        got = _host_u64(device.fr_vec_op(_dev(a), s, op)).reshape(-1, 4)
+        assert (got == np.array([f(x, s) for x in a])).all(), op
+    da = _dev(a)
+    device.fr_vec_op(da, da, device.FR_MUL, out=da)           # aliasing: a ← a·a
+    assert (_host_u64(da).reshape(-1, 4) == np.array([oracle_cpu.fr_mul(x, x) for x in a])).all()
+    for lg in (0, 1, 3, 10):
+        # elements = FFT of the polynomial X (the reference's domain KAT, circuit_0/domain/*.txt, is the lg = 3 case)
+        m = 1 << lg
+        x = np.zeros((m, 4), dtype=np.uint64)
+        if m > 1:
+            x[1] = fr_ints_to_mont_array([1])[0]
+            want = oracle_cpu.ntt(x, oracle_cpu.FORWARD)
+        else:
+            want = fr_ints_to_mont_array([1])
+        assert (_host_u64(device.domain_elements(lg)).reshape(-1, 4) == want).all(), lg
+
+
+def test_kzg_open_lagrange(oracle_cpu):
+    """KZG10::open_lagrange (kzg10/mod.rs:272-301) against the oracle pieces, and against open() on the coefficient form:
+    both prove the same evaluation, so the witness commitments are the same group element."""
+    from snarkvm_b200.algorithms import KZG10, EvaluationDomain, UniversalParams
+    from snarkvm_b200 import device
+    n = 128
+    powers = device.generate_bases(n, seed=61)
+    domain = EvaluationDomain.new(n)
+    basis = UniversalParams(powers).lagrange_basis(domain)
+    coeffs = random_fr_mont(n, seed=1)
+    evals = oracle_cpu.ntt(coeffs, oracle_cpu.FORWARD)
+    z = random_fr_mont(1, seed=2)[0]
+    y = oracle_cpu.poly_evaluate(coeffs, z)
+    w, v = KZG10.open_lagrange(basis, domain, _dev(evals), z, y)
+    assert v is None
+    # oracle: (eval_i − y)·(ω^i − z)^{-1} committed against the oracle's own Lagrange basis
+    x = np.zeros((n, 4), dtype=np.uint64); x[1] = fr_ints_to_mont_array([1])[0]
+    elems = oracle_cpu.ntt(x, oracle_cpu.FORWARD)
+    div = np.array([oracle_cpu.fr_sub(e, z) for e in elems])
+    div = oracle_cpu.fr_batch_inversion_and_mul(div, fr_ints_to_mont_array([1])[0])
+    wit = np.array([oracle_cpu.fr_mul(d, oracle_cpu.fr_sub(e, y)) for d, e in zip(div, evals)])
+    hbasis = oracle_cpu.g1_ifft(powers.cpu().numpy())
+    assert (w == oracle_cpu.msm(hbasis, oracle_cpu.fr_from_mont(wit), 0)).all()
+    w2, _ = KZG10.open(powers, _dev(coeffs), z)
+    assert (w == w2).all()
+    with pytest.raises(ValueError):
+        KZG10.open_lagrange(basis, domain, _dev(evals), elems[5], y)      # a point of the domain
+    with pytest.raises(ValueError):
+        KZG10.open_lagrange(basis, domain, _dev(evals[:100]), z, y)
