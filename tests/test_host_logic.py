@@ -97,3 +97,29 @@ def test_sharded_msm_exchange_gloo_world2(tmp_path, oracle_cpu):
     mp.spawn(_gloo_worker, args=(2, port, 200, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert np.load(tmp_path / f"ok_{r}.npy")[0] == 1
+
+
+def test_kzg_argument_checks_need_no_gpu():
+    """the reference's argument checks run before any device call (kzg10/mod.rs:134-137,166-169,283-290)"""
+    import torch
+    from snarkvm_b200 import algorithms as alg
+    from snarkvm_b200.algorithms import KZG10, EvaluationDomain
+    # host-side Montgomery helpers against the big-int root of trust
+    rnd = random.Random(1)
+    for _ in range(20):
+        v = rnd.randrange(py.R_MOD)
+        m = alg._fr_int_to_mont(v)
+        assert sum(int(x) << (64 * i) for i, x in enumerate(m)) == py.fr_to_mont(v)
+        assert alg._fr_mont_to_int(m) == v
+    assert alg._R_MOD == py.R_MOD
+    domain = EvaluationDomain.new(8)
+    basis = torch.zeros(8 * 104, dtype=torch.uint8)
+    evals = torch.zeros((8, 4), dtype=torch.int64)
+    w = py.fr_root_of_unity(8)
+    in_domain = alg._fr_int_to_mont(pow(w, 3, py.R_MOD))
+    with pytest.raises(ValueError, match="Point cannot be in the domain"):
+        KZG10.open_lagrange(basis, domain, evals, in_domain, alg._fr_int_to_mont(0))
+    with pytest.raises(ValueError, match="must equal"):
+        KZG10.open_lagrange(basis, domain, evals[:5], alg._fr_int_to_mont(5), alg._fr_int_to_mont(0))
+    with pytest.raises(ValueError, match="Lagrange basis size"):
+        KZG10.commit_lagrange(basis, evals[:3])                 # next_power_of_two(3) = 4 ≠ 8
