@@ -178,6 +178,9 @@ SNARKVM_API int snarkvm_b200_srs_decode_device(void* d_out, size_t stride, const
  * passes the same slice to every commitment.  The caller must not mutate the slice while it is registered. */
 SNARKVM_API int snarkvm_b200_register_bases(const void* host_points, size_t npoints, size_t stride);
 SNARKVM_API int snarkvm_b200_unregister_bases(const void* host_points);
+/* As snarkvm_b200_register_bases, and also builds the fixed-base tables (snarkvm_b200_msm_precompute_device) of the uploaded copy:
+ * snarkvm_msm calls on this slice then run over the tables (npoints * nwin * 128 B of HBM, seconds of one-off set-up). */
+SNARKVM_API int snarkvm_b200_register_bases_precomputed(const void* host_points, size_t npoints, size_t stride);
 
 /* Per-kernel CUDA-event timing on the launching stream (off by default).  kind: 0 = MSM bucket sort
  * (digit histogram + scatter), 1 = MSM bucket accumulation, 2 = MSM bucket reduction, 3 = NTT passes.

@@ -27,6 +27,7 @@ SYMBOLS = (
     "snarkvm_b200_fr_batch_inversion_and_mul_device", "snarkvm_b200_poly_divide_by_vanishing_device", "snarkvm_b200_poly_evaluate_device",
     "snarkvm_b200_poly_divide_by_linear_device", "snarkvm_b200_sparse_matvec_device",
     "snarkvm_b200_fr_vec_op_device", "snarkvm_b200_fr_vec_scalar_op_device", "snarkvm_b200_domain_elements_device",
+    "snarkvm_b200_register_bases_precomputed",
 )
 
 
@@ -81,6 +82,7 @@ def lib():
     L.snarkvm_b200_srs_decode_device.argtypes = [vp, sz, vp, sz, vp, vp]
     L.snarkvm_b200_register_bases.argtypes = [vp, sz, sz]
     L.snarkvm_b200_unregister_bases.argtypes = [vp]
+    L.snarkvm_b200_register_bases_precomputed.argtypes = [vp, sz, sz]
     L.snarkvm_b200_profile_enable.argtypes = [i32]
     L.snarkvm_b200_profile_collect.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
     L.snarkvm_b200_generate_bases_device.argtypes = [vp, sz, sz, u64, vp]

@@ -76,7 +76,7 @@ int thread_copy_stream(cudaStream_t* out) {
 // Registered (resident) bases: the SRS powers of a proving key are constant, and the reference re-passes the same
 // host slice on every commitment (kzg10/mod.rs:119,149).  A caller may register that slice once; snarkvm_msm then
 // recognises the pointer and skips the 104 B/point upload.  Opt-in: the caller promises not to mutate the slice.
-struct ResidentBases { void* d_ptr; size_t npoints; size_t stride; int device; };
+struct ResidentBases { void* d_ptr; size_t npoints; size_t stride; int device; void* tables; /* PrecomputedBases* or null */ };
 std::mutex g_bases_mu;
 std::map<const void*, ResidentBases> g_bases;
 
@@ -278,7 +278,8 @@ snarkvm_error_t snarkvm_msm(void* out, const void* points, size_t npoints, const
     if (chunks == 1) {
         if (rc == 0) rc = (int)cudaMemcpyAsync(d_scalars, scalars, npoints * 32, cudaMemcpyHostToDevice, stream);
         if (rc == 0 && !resident) rc = (int)cudaMemcpyAsync(d_points, points, npoints * ffi_affine_sz, cudaMemcpyHostToDevice, stream);
-        if (rc == 0) rc = msm_device_impl(result, resident ? rb.d_ptr : d_points, npoints, d_scalars, ffi_affine_sz, stream);
+        if (rc == 0 && resident && rb.tables) rc = snarkvm_b200_msm_precomputed_device(result, rb.tables, d_scalars, npoints, stream);
+        else if (rc == 0) rc = msm_device_impl(result, resident ? rb.d_ptr : d_points, npoints, d_scalars, ffi_affine_sz, stream);
     } else {
         cudaStream_t copy = nullptr;
         if (rc == 0) rc = thread_copy_stream(&copy);
@@ -542,8 +543,8 @@ int snarkvm_b200_register_bases(const void* host_points, size_t npoints, size_t 
     if ((e = cudaMemcpy(d, host_points, npoints * stride, cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d); return (int)e; }
     std::lock_guard<std::mutex> lock(g_bases_mu);
     auto it = g_bases.find(host_points);
-    if (it != g_bases.end()) { cudaFree(it->second.d_ptr); g_bases.erase(it); }
-    g_bases[host_points] = ResidentBases{d, npoints, stride, dev};
+    if (it != g_bases.end()) { cudaFree(it->second.d_ptr); if (it->second.tables) snarkvm_b200_msm_precomputed_free(it->second.tables); g_bases.erase(it); }
+    g_bases[host_points] = ResidentBases{d, npoints, stride, dev, nullptr};
     return 0;
 }
 int snarkvm_b200_unregister_bases(const void* host_points) {
@@ -551,7 +552,29 @@ int snarkvm_b200_unregister_bases(const void* host_points) {
     auto it = g_bases.find(host_points);
     if (it == g_bases.end()) return (int)cudaErrorInvalidValue;
     cudaFree(it->second.d_ptr);
+    if (it->second.tables) snarkvm_b200_msm_precomputed_free(it->second.tables);
     g_bases.erase(it);
+    return 0;
+}
+// register + build the fixed-base tables (snarkvm_b200_msm_precompute_device) from the uploaded copy: later snarkvm_msm calls
+// on this slice run over the tables (one bucket set, wider windows).  Costs npoints·nwin·128 B of HBM and seconds of set-up.
+int snarkvm_b200_register_bases_precomputed(const void* host_points, size_t npoints, size_t stride) {
+    int rc = snarkvm_b200_register_bases(host_points, npoints, stride);
+    if (rc != 0) return rc;
+    void* d = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_bases_mu);
+        d = g_bases[host_points].d_ptr;
+    }
+    cudaStream_t stream;
+    if ((rc = thread_stream(&stream)) != 0) return rc;
+    void* tables = nullptr;
+    rc = snarkvm_b200_msm_precompute_device(&tables, d, npoints, stride, stream);
+    if (rc != 0) { snarkvm_b200_unregister_bases(host_points); return rc; }
+    std::lock_guard<std::mutex> lock(g_bases_mu);
+    auto it = g_bases.find(host_points);
+    if (it == g_bases.end() || it->second.d_ptr != d) { snarkvm_b200_msm_precomputed_free(tables); return (int)cudaErrorInvalidValue; }   // raced with unregister
+    it->second.tables = tables;
     return 0;
 }
 

@@ -97,5 +97,12 @@ def register_bases(points: np.ndarray) -> None:
     _lib.check(_lib.lib().snarkvm_b200_register_bases(points.ctypes.data, points.shape[0], points.shape[1]))
 
 
+def register_bases_precomputed(points: np.ndarray) -> None:
+    """register_bases plus the fixed-base tables 2^{c·w}·P_i of the uploaded copy: `msm` on this array then runs over the tables."""
+    if points.dtype != np.uint8 or points.ndim != 2 or not points.flags.c_contiguous:
+        raise TypeError("points must be a C-contiguous uint8 array [n, stride]")
+    _lib.check(_lib.lib().snarkvm_b200_register_bases_precomputed(points.ctypes.data, points.shape[0], points.shape[1]))
+
+
 def unregister_bases(points: np.ndarray) -> None:
     _lib.check(_lib.lib().snarkvm_b200_unregister_bases(points.ctypes.data))

@@ -402,3 +402,19 @@ def test_msm_ffi_chunked_upload(oracle_cpu, bases64k, monkeypatch, chunks, n):
     bases = bases64k[:n].copy()
     bases[1, 96] = 1
     assert (VariableBase.msm(bases, scal) == oracle_cpu.msm(bases, scal, 1)).all()
+
+
+def test_registered_bases_precomputed(oracle_cpu, bases64k):
+    """snarkvm_b200_register_bases_precomputed: snarkvm_msm on the registered slice runs over the fixed-base tables — same group
+    element, also for a prefix of the slice (fewer scalars than registered points)."""
+    from snarkvm_b200 import cuda
+    n = 5000
+    bases = np.ascontiguousarray(bases64k[:n])
+    scal = random_canonical_fr(n, seed=88)
+    cuda.register_bases_precomputed(bases)
+    try:
+        assert (cuda.msm(bases, scal) == oracle_cpu.msm(bases, scal, 0)).all()
+        assert (cuda.msm(bases, scal[:1234]) == oracle_cpu.msm(bases[:1234], scal[:1234], 0)).all()
+    finally:
+        cuda.unregister_bases(bases)
+    assert (cuda.msm(bases, scal) == oracle_cpu.msm(bases, scal, 0)).all()      # plain path again after unregistering
