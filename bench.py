@@ -305,20 +305,27 @@ def run_product(args, rank, world, local_rank):
         shim.unregister_bases(b_np)
         e2e_resident = {"value": n / (r_ms * 1e-3), "unit": "points/s", "ms_per_step": r_ms, "h2d_bytes_per_step": n * 32,
                         "d2h_bytes_per_step": 144, "api": "snarkvm_msm after snarkvm_b200_register_bases (bases resident)"}
-        # and with the fixed-base tables of the registered slice built once (snarkvm_b200_register_bases_precomputed)
-        t0 = time.perf_counter()
-        shim.register_bases_precomputed(b_np)
-        setup_s = time.perf_counter() - t0
-        assert (shim.msm(b_np, s_np) == first).all()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            shim.msm(b_np, s_np)
-        torch.cuda.synchronize()
-        p_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-        shim.unregister_bases(b_np)
-        e2e_resident["precomputed_tables"] = {"value": n / (p_ms * 1e-3), "unit": "points/s", "ms_per_step": p_ms, "one_time_setup_s": setup_s,
-                                              "api": "snarkvm_msm after snarkvm_b200_register_bases_precomputed"}
+        # and with the fixed-base tables of the registered slice built once (snarkvm_b200_register_bases_precomputed);
+        # an extra, never the headline: a failure here (e.g. not enough HBM for the tables) is reported, not fatal
+        try:
+            t0 = time.perf_counter()
+            shim.register_bases_precomputed(b_np)
+            setup_s = time.perf_counter() - t0
+            try:
+                assert (shim.msm(b_np, s_np) == first).all()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    shim.msm(b_np, s_np)
+                torch.cuda.synchronize()
+                p_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+            finally:
+                shim.unregister_bases(b_np)
+            e2e_resident["precomputed_tables"] = {"value": n / (p_ms * 1e-3), "unit": "points/s", "ms_per_step": p_ms,
+                                                  "one_time_setup_s": setup_s,
+                                                  "api": "snarkvm_msm after snarkvm_b200_register_bases_precomputed"}
+        except Exception as exc:  # noqa: BLE001
+            e2e_resident["precomputed_tables"] = {"error": repr(exc)}
 
     # ---- secondary metric: Fr NTT elements/s (per-GPU replicas; BASELINE config 3) ----
     ntt = None
