@@ -450,7 +450,7 @@ def run_product(args, rank, world, local_rank):
         "config": {"workload": f"bls12_377_g1_msm_2^{args.lg}_points_per_gpu", "points_per_gpu": n, "scalars": "uniform < 2^252",
                    "bases": "h(seed,i)*G, affine 104 B stride", "window_bits": plan["c"], "windows": plan["nwin"],
                    "parallelism": f"points sharded over {world} GPU(s); one all-gather of window sums" if world > 1 else "single GPU",
-                   "l2": "inputs (2.2 GB/step) larger than the 126 MB L2 — no flush needed"},
+                   "l2": f"inputs ({n * 136 / 1e9:.2f} GB/step) plus {n * plan['nwin'] * 4 / 1e9:.2f} GB of sorted entries and the dense pair-level scratch stream through the 126 MB L2 every step — no flush needed"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * (104 + 32) * world,
                 "d2h_bytes_per_step": 144 * world, "ms_per_step": e2e_ms, "steps": e2e_steps,
