@@ -7,11 +7,16 @@
 One "step" = one pass of the hot path over one batch of synthetic input:
   * product arm: one 2^lg-point VariableBase::msm per GPU (weak scaling: every rank owns 2^lg points;
     at N > 1 the per-rank window sums are all-gathered over NCCL and added on the device) — `value` is
-    measured with bases and scalars resident in HBM, `e2e` through the reference-facing C-ABI symbol
-    `snarkvm_msm` with pinned HOST buffers (H2D of points + scalars and D2H of the result inside the
-    timed region).
+    measured with bases and scalars resident in HBM; `e2e` goes through the reference-facing C ABI with
+    PAGEABLE host buffers (what a Rust Vec is): H2D of points + scalars and D2H of the result inside the
+    timed region (`e2e_pinned`: the same call on pinned buffers).
   * reference arm: the CPU restatement of batched::msm (oracle/oracle.c, OpenMP over all host cores) on a
     bounded sample of the same workload — the Rust reference cannot be built here (no cargo/rustc).
+
+Every timed result is CHECKED outside the timed region: the bases are h(seed, i)·G, so
+Σ s_i·P_i = (Σ s_i·h_i mod r)·G — one dot product and one scalar multiplication by the oracle — for the
+single-GPU MSM, the sharded result at every N, the 2^26-total sharded run and the KZG commitment; the NTT
+output is compared with the oracle's fft_in_place element by element.  `checked` in the JSON line says so.
 
 Prints ONE JSON line on rank 0.  Timing: CUDA events on the launching stream, barrier + synchronize on
 both sides, max over ranks; inputs (≥ 2.2 GB per step) are far larger than L2 so no flush is needed.
@@ -33,8 +38,10 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 ALGO_BYTES_PER_POINT = 128      # 96 B affine (x, y) + 32 B scalar, each touched once
-ALGO_BYTES_PER_ELEMENT = 64     # NTT: 32 B read + 32 B write per element per transform
+ALGO_BYTES_PER_ELEMENT = 64     # NTT: 32 B read + 32 B write per element per TRANSFORM
 FALLBACK_HBM_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md
+R_MOD = 8444461749428370424248824938781546531375899335154063827935233455917409239041
+R_LIMBS = np.array([(R_MOD >> (64 * i)) & (2**64 - 1) for i in range(4)], dtype=np.uint64)
 
 
 def load_peak():
@@ -56,10 +63,67 @@ def load_traffic(key):
 
 
 def random_scalars(n, seed):
+    """Uniform integers in [0, r): draw 4 limbs, clear the top REPR_SHAVE_BITS = 3 bits, reject ≥ r — the reference's own
+    sampler (fields/src/macros.rs:40-56).  Also used for Montgomery images (any value < r is one)."""
     rng = np.random.default_rng(seed)
-    s = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
-    s[:, 3] &= np.uint64((1 << 60) - 1)          # < r (r ≈ 2^252.1): uniform below 2^252
-    return s
+    out = np.empty((n, 4), dtype=np.uint64)
+    todo = np.arange(n)
+    while todo.size:
+        x = rng.integers(0, 2**64, size=(todo.size, 4), dtype=np.uint64)
+        x[:, 3] &= np.uint64((1 << 61) - 1)
+        lt = np.zeros(todo.size, dtype=bool)
+        eq = np.ones(todo.size, dtype=bool)
+        for i in (3, 2, 1, 0):
+            lt |= eq & (x[:, i] < R_LIMBS[i])
+            eq &= x[:, i] == R_LIMBS[i]
+        out[todo[lt]] = x[lt]
+        todo = todo[~lt]
+    return out
+
+
+def base_multipliers(seed, n):
+    """h(seed, i) of snarkvm_b200_generate_bases_device (csrc/msm.cu): P_i = h·G, as canonical uint64 [n, 4]."""
+    def sm(x):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+    with np.errstate(over="ignore"):
+        k = sm(np.uint64(seed & ((1 << 64) - 1)) ^ sm(np.arange(n, dtype=np.uint64)))
+    k[k == 0] = 1
+    ks = np.zeros((n, 4), dtype=np.uint64)
+    ks[:, 0] = k
+    return ks
+
+
+def limbs_to_int(a):
+    return sum(int(v) << (64 * i) for i, v in enumerate(np.asarray(a).reshape(-1)[:4]))
+
+
+def int_to_limbs(v):
+    return np.array([(v >> (64 * i)) & (2**64 - 1) for i in range(4)], dtype=np.uint64)
+
+
+class Checker:
+    """The oracle used as the CHECKER, outside every timed region (never as the thing measured)."""
+
+    def __init__(self):
+        from oracle import bls12_377 as py, cpu
+        cpu.build()
+        try:
+            cpu.set_num_threads(len(os.sched_getaffinity(0)))     # torchrun exports OMP_NUM_THREADS=1
+        except AttributeError:
+            cpu.set_num_threads(os.cpu_count() or 1)
+        self.cpu, self.py = cpu, py
+        self.g = np.frombuffer(py.affine_bytes(py.G1_GENERATOR), dtype=np.uint8).copy()
+
+    def dot(self, scalars, seed):
+        """Σ s_i·h(seed, i) mod r as a Python int (scalars canonical)"""
+        return limbs_to_int(self.cpu.fr_dot_canonical(scalars, base_multipliers(seed, scalars.shape[0])))
+
+    def point(self, k):
+        """(k mod r)·G as the normalised projective image uint64[18]"""
+        return self.cpu.g1_mul(self.g, int_to_limbs(k % R_MOD))
 
 
 class ClockSampler:
@@ -111,26 +175,26 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def workload_config(args, world):
+    """The workload both arms name (identical dict in the product and the reference line)."""
+    return {"workload": f"bls12_377_g1_msm_2^{args.lg}_points_per_gpu", "points_per_gpu": 1 << args.lg,
+            "scalars": "uniform in [0, r)", "bases": "h(seed,i)*G, affine 104 B stride",
+            "parallelism": f"points sharded over {world} GPU(s); one all-gather of window sums" if world > 1 else "single GPU"}
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle (CPU restatement of the reference algorithms)
 # ------------------------------------------------------------------------------------------------
-def cpu_msm_points_per_s(lg_sample, bases_host, reps=1):
-    from oracle import cpu
-    n = 1 << lg_sample
-    scal = random_scalars(n, 777)
-    best = None
-    for _ in range(reps):
-        t = time.perf_counter()
-        cpu.msm(bases_host[:n], scal, cpu.BATCHED)
-        dt = time.perf_counter() - t
-        best = dt if best is None else min(best, dt)
-    return n / best, best
+def cpu_msm_points_per_s(cpu, bases_host, scal):
+    t = time.perf_counter()
+    cpu.msm(bases_host, scal, cpu.BATCHED)
+    dt = time.perf_counter() - t
+    return scal.shape[0] / dt, dt
 
 
-def cpu_ntt_elements_per_s(lg_sample):
+def cpu_ntt_elements_per_s(cpu, lg_sample):
     """Best over a few OpenMP team sizes: the port's per-stage parallel-for (standing in for rayon's chunked
     butterflies, fft/domain.rs:667-688) stops scaling — and can slow down — on very wide hosts."""
-    from oracle import cpu
     x = random_scalars(1 << lg_sample, 778)
     allc = cpu.num_threads()
     best = None
@@ -163,32 +227,28 @@ def cpu_bases(n):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    from oracle import cpu
-    cpu.build()
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it may run on (rayon's default)
-    try:
-        cpu.set_num_threads(len(os.sched_getaffinity(0)))
-    except AttributeError:
-        cpu.set_num_threads(os.cpu_count() or 1)
+    chk = Checker()
+    cpu = chk.cpu
     lg = args.ref_lg
     bases = cpu_bases(1 << lg)
     threads = cpu.num_threads()
-    for _ in range(args.warmup):
-        cpu_msm_points_per_s(min(lg, 16), bases)
     scal = random_scalars(1 << lg, 777)
+    for _ in range(args.warmup):
+        cpu.msm(bases[: 1 << min(lg, 16)], scal[: 1 << min(lg, 16)], cpu.BATCHED)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu.msm(bases, scal, cpu.BATCHED)
     dt = (time.perf_counter() - t0) / args.steps
     value = (1 << lg) / dt
-    ntt_v, ntt_dt, ntt_th = cpu_ntt_elements_per_s(args.ref_ntt_lg)
-    sample = f"2^{lg}-point batched::msm per step on {threads} OpenMP threads (one task per window, as rayon in batched.rs:400-401)"
+    ntt_v, ntt_dt, ntt_th = cpu_ntt_elements_per_s(cpu, args.ref_ntt_lg)
+    sample = (f"each step = one 2^{lg}-point batched::msm (a bounded sample of the 2^{args.lg}-point workload: points/s of this algorithm "
+              f"grows only slowly with n) on {threads} OpenMP threads, one task per window as rayon in batched.rs:400-401")
     line = {
         "impl": "reference", "metric": "bls12_377_g1_msm_points_per_sec", "value": value, "unit": "points/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (CPU)", "data": "synthetic",
-        "config": {"workload": f"bls12_377_g1_msm_2^{args.lg}_points_per_gpu", "sample": sample,
-                   "note": "C restatement of the reference CPU (rayon) path — Rust toolchain unavailable"},
+        "config": workload_config(args, world),
+        "note": "C restatement of the reference CPU (rayon) path — Rust toolchain unavailable",
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ntt": {"metric": "fr_ntt_elements_per_sec", "value": ntt_v, "unit": "elements/s",
@@ -212,6 +272,8 @@ def run_product(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     n = 1 << args.lg
     peak, peak_src = load_peak()
+    chk = Checker()
+    checks = {}
 
     def barrier():
         if world > 1:
@@ -225,197 +287,270 @@ def run_product(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- inputs: per-rank shard, generated in HBM; host copies in pinned memory for the e2e leg ----
-    bases = device.generate_bases(n, seed=0xB200 + rank, device=dev)
-    scal_host = torch.from_numpy(random_scalars(n, 1234 + rank).view(np.int64)).pin_memory()
-    scalars = scal_host.to(dev)
+    def sum_over_ranks_mod_r(v):
+        """Σ over ranks of a Python int, mod r (the closed-form dot products of the shards)"""
+        if world == 1:
+            return v % R_MOD
+        objs = [None] * world
+        dist.all_gather_object(objs, int(v))
+        return sum(objs) % R_MOD
+
+    def timed(fn, steps, collect=None):
+        """K calls of fn bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks → ms per step;
+        `collect` (if given) turns what the K calls returned into results INSIDE the timed region"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        outs = [fn() for _ in range(steps)]
+        if collect is not None:
+            outs = [collect(o) for o in outs]
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, outs
+
+    def wall_timed(fn, steps):
+        barrier()
+        t0 = time.perf_counter()
+        outs = [fn() for _ in range(steps)]
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        return max_over_ranks(ms) / steps, outs
+
+    # ---- inputs: per-rank shard, generated in HBM ----
+    seed = 0xB200 + rank
+    bases = device.generate_bases(n, seed=seed, device=dev)
+    scal_np = random_scalars(n, 1234 + rank)
+    scalars = torch.from_numpy(scal_np.view(np.int64)).to(dev)
     torch.cuda.synchronize()
+    expect = chk.point(sum_over_ranks_mod_r(chk.dot(scal_np, seed)))          # closed form of the whole job's sum
 
-    def step_device():
-        return sharded.msm_sharded(bases, scalars) if world > 1 else device.msm(bases, scalars)
+    if world > 1:
+        def step_device():
+            return sharded.msm_sharded_async(bases, scalars, plan_npoints=n)
+        collect = lambda p: p.result()                                         # noqa: E731
+    else:
+        def step_device():
+            return device.msm(bases, scalars)
+        collect = None
 
-    # ---- correctness guard on the timed configuration (closed form: bases are known multiples of G) ----
     first = step_device()
+    first = collect(first) if collect else first
+    checks["msm_value"] = bool((first == expect).all())
+    assert checks["msm_value"], "device-resident MSM differs from the closed form (Σ s_i·h_i)·G"
 
-    # ---- `value`: device-resident MSM, K steps, CUDA events on the launching stream ----
+    # ---- `value`: device-resident MSM, K steps ----
     for _ in range(args.warmup):
-        step_device()
+        o = step_device()
+        if collect:
+            collect(o)
     _lib.profile_enable(True)
     for k in (0, 1, 2, 3):
         _lib.profile_collect(k)
     sampler = ClockSampler(local_rank)
     launches0 = _lib.launch_count()
-    barrier()
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = step_device()
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step, outs = timed(step_device, args.steps, collect)
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.launch_count() - launches0
     acc_ms, acc_n = _lib.profile_collect(_lib.PROF_MSM_ACCUMULATE)
     sort_ms, _ = _lib.profile_collect(_lib.PROF_MSM_SORT)
     red_ms, _ = _lib.profile_collect(_lib.PROF_MSM_REDUCE)
     _lib.profile_enable(False)
-    assert (out == first).all(), "MSM result changed between steps"
-    ms_per_step = ms_total / args.steps
+    assert all((o == expect).all() for o in outs), "MSM result changed between steps"
+    ms_total = ms_per_step * args.steps
     value = n * world / (ms_per_step * 1e-3)
-    acc_ms_per_launch = acc_ms / max(1, args.steps)        # the whole accumulation phase of one MSM (several kernels)
-    achieved = ALGO_BYTES_PER_POINT * n / (acc_ms_per_launch * 1e-3) / 1e9
+    acc_ms_per_step = acc_ms / max(1, args.steps)           # the whole accumulation phase of one MSM (several kernels)
+    achieved = ALGO_BYTES_PER_POINT * n / (acc_ms_per_step * 1e-3) / 1e9
 
-    # ---- `e2e`: through the drop-in C-ABI symbol with pinned HOST buffers (H2D + D2H inside the timing) ----
-    bases_host = torch.empty((n, 104), dtype=torch.uint8).pin_memory()
-    bases_host.copy_(bases)
+    # ---- `e2e`: through the reference-facing call with HOST buffers (H2D + D2H inside the timing) ----
+    # pageable = what a Rust Vec<G1Affine> / Vec<BigInteger256> is; pinned = the best a caller could do
+    bases_pin = torch.empty((n, 104), dtype=torch.uint8).pin_memory()
+    bases_pin.copy_(bases)
     torch.cuda.synchronize()
-    b_np, s_np = bases_host.numpy(), scal_host.numpy().view(np.uint64)
+    scal_pin = torch.from_numpy(scal_np.view(np.int64)).pin_memory()
+    b_pin, s_pin = bases_pin.numpy(), scal_pin.numpy().view(np.uint64)
+    b_page = np.empty((n, 104), dtype=np.uint8); b_page[:] = b_pin       # plain malloc'd arrays
+    s_page = np.empty((n, 4), dtype=np.uint64); s_page[:] = scal_np
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
 
-    def step_e2e():
+    def make_e2e(bh, sh):
         if world == 1:
-            return shim.msm(b_np, s_np)                     # snarkvm_msm: H2D points+scalars, MSM, D2H 144 B
-        db = bases_host.to(dev, non_blocking=True)           # sharded public API: same copies, then the NCCL exchange
-        ds = scal_host.to(dev, non_blocking=True)
-        return sharded.msm_sharded(db, ds)
+            return (lambda: shim.msm(bh, sh)), None                       # snarkvm_msm: H2D points+scalars, MSM, D2H 144 B
+        return (lambda: sharded.msm_sharded_async(bh, sh, plan_npoints=n, dev=dev)), (lambda p: p.result())
 
-    r_e2e = step_e2e()
-    assert (r_e2e == first).all(), "e2e result differs from the device-resident result"
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    e2e = {}
+    for name, bh, sh in (("pageable", b_page, s_page), ("pinned", b_pin, s_pin)):
+        fn, col = make_e2e(bh, sh)
+        r = fn(); r = col(r) if col else r
+        ok = bool((r == expect).all())
+        checks[f"msm_e2e_{name}"] = ok
+        assert ok, f"e2e ({name}) result differs from the closed form"
+        ms, _ = wall_timed((lambda: col(fn())) if col else fn, e2e_steps)
+        e2e[name] = ms
+    e2e_ms = e2e["pageable"]
     e2e_value = n * world / (e2e_ms * 1e-3)
+    del b_page, s_page
     e2e_resident = None
-    if world == 1:
+    if world == 1 and not args.skip_registered:
         # same call, SRS-style usage: the bases slice was registered once (snarkvm_b200_register_bases), only the
         # 32 B/point scalars cross PCIe per call
-        shim.register_bases(b_np)
-        assert (shim.msm(b_np, s_np) == first).all()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            shim.msm(b_np, s_np)
-        torch.cuda.synchronize()
-        r_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-        shim.unregister_bases(b_np)
+        shim.register_bases(b_pin)
+        assert (shim.msm(b_pin, s_pin) == expect).all()
+        r_ms, _ = wall_timed(lambda: shim.msm(b_pin, s_pin), e2e_steps)
+        shim.unregister_bases(b_pin)
         e2e_resident = {"value": n / (r_ms * 1e-3), "unit": "points/s", "ms_per_step": r_ms, "h2d_bytes_per_step": n * 32,
                         "d2h_bytes_per_step": 144, "api": "snarkvm_msm after snarkvm_b200_register_bases (bases resident)"}
         # and with the fixed-base tables of the registered slice built once (snarkvm_b200_register_bases_precomputed);
         # an extra, never the headline: a failure here (e.g. not enough HBM for the tables) is reported, not fatal
         try:
             t0 = time.perf_counter()
-            shim.register_bases_precomputed(b_np)
+            shim.register_bases_precomputed(b_pin)
             setup_s = time.perf_counter() - t0
             try:
-                assert (shim.msm(b_np, s_np) == first).all()
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for _ in range(e2e_steps):
-                    shim.msm(b_np, s_np)
-                torch.cuda.synchronize()
-                p_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+                assert (shim.msm(b_pin, s_pin) == expect).all()
+                p_ms, _ = wall_timed(lambda: shim.msm(b_pin, s_pin), e2e_steps)
             finally:
-                shim.unregister_bases(b_np)
+                shim.unregister_bases(b_pin)
             e2e_resident["precomputed_tables"] = {"value": n / (p_ms * 1e-3), "unit": "points/s", "ms_per_step": p_ms,
                                                   "one_time_setup_s": setup_s,
                                                   "api": "snarkvm_msm after snarkvm_b200_register_bases_precomputed"}
         except Exception as exc:  # noqa: BLE001
             e2e_resident["precomputed_tables"] = {"error": repr(exc)}
+    del bases_pin, b_pin
+
+    # ---- BASELINE config 5a: 2^total_lg points sharded over the N GPUs (strong scaling: total work fixed) ----
+    strong = None
+    if args.total_lg and not args.skip_strong:
+        tn = 1 << args.total_lg
+        lo, hi = sharded.shard_range(tn, rank, world)
+        shard_n = hi - lo
+        plan_n = (tn + world - 1) // world
+        sseed = 0x5A00 + rank
+        sb = bases if shard_n == n else device.generate_bases(shard_n, seed=sseed, device=dev)
+        if shard_n == n:
+            sseed = seed
+        ssc_np = scal_np if shard_n == n else random_scalars(shard_n, 4321 + rank)
+        ssc = scalars if shard_n == n else torch.from_numpy(ssc_np.view(np.int64)).to(dev)
+        sexpect = chk.point(sum_over_ranks_mod_r(chk.dot(ssc_np, sseed)))
+        sfn = lambda: sharded.msm_sharded_async(sb, ssc, plan_npoints=plan_n)      # noqa: E731
+        got = sfn().result()
+        checks["msm_sharded_total"] = bool((got == sexpect).all())
+        assert checks["msm_sharded_total"], "sharded 2^total MSM differs from the closed form"
+        ssteps = max(2, min(args.steps, 5))
+        s_ms, souts = timed(sfn, ssteps, lambda p: p.result())
+        assert all((o == sexpect).all() for o in souts)
+        strong = {"metric": "bls12_377_g1_msm_points_per_sec", "value": tn / (s_ms * 1e-3), "unit": "points/s", "scaling": "strong",
+                  "workload": f"2^{args.total_lg} points in total, ⌈n/N⌉ per GPU, NCCL all-gather of window sums + device point-reduce",
+                  "points_per_gpu": shard_n, "ms_per_step": s_ms, "steps": ssteps, "checked": True}
+        del sb, ssc
 
     # ---- secondary metric: Fr NTT elements/s (per-GPU replicas; BASELINE config 3) ----
     ntt = None
     if not args.skip_ntt:
         from snarkvm_b200.cuda import NTTDirection, NTTType
         nn = 1 << args.ntt_lg
-        x = torch.from_numpy(random_scalars(nn, 99 + rank).view(np.int64)).to(dev)
+        x_np = random_scalars(nn, 99 + rank)
+        x = torch.from_numpy(x_np.view(np.int64)).to(dev)
         scratch = torch.empty_like(x)
+        y = device.ntt_(x.clone(), NTTDirection.Forward, NTTType.Standard, scratch)
+        if rank == 0:
+            checks["ntt_vs_oracle"] = bool((y.cpu().numpy().view(np.uint64) == chk.cpu.ntt(x_np, chk.cpu.FORWARD, chk.cpu.STANDARD)).all())
+            assert checks["ntt_vs_oracle"], "NTT output differs from the oracle's fft_in_place"
+        back = device.ntt_(y.clone(), NTTDirection.Inverse, NTTType.Standard, scratch)
+        checks["ntt_round_trip"] = bool(torch.equal(back, x))
+        assert checks["ntt_round_trip"]
+        del y, back
         for _ in range(3):
             device.ntt_(x, NTTDirection.Forward, NTTType.Standard, scratch)
         _lib.profile_enable(True)
         _lib.profile_collect(_lib.PROF_NTT_PASS)
-        barrier()
         reps = 10
-        e0.record()
-        for _ in range(reps):
-            device.ntt_(x, NTTDirection.Forward, NTTType.Standard, scratch)
-        e1.record()
-        barrier()
-        ntt_ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+        ntt_ms, _ = timed(lambda: device.ntt_(x, NTTDirection.Forward, NTTType.Standard, scratch), reps)
         pass_ms, pass_n = _lib.profile_collect(_lib.PROF_NTT_PASS)
         _lib.profile_enable(False)
-        x_h = torch.from_numpy(random_scalars(nn, 5).view(np.int64)).pin_memory()
-        xs = x_h.numpy().view(np.uint64)
-        shim.NTT(nn, xs, shim.NTTInputOutputOrder.NN, shim.NTTDirection.Forward, shim.NTTType.Standard)
-        barrier()
-        t0 = time.perf_counter()
-        shim.NTT(nn, xs, shim.NTTInputOutputOrder.NN, shim.NTTDirection.Forward, shim.NTTType.Standard)
-        barrier()
-        ntt_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        xs_page = np.empty((nn, 4), dtype=np.uint64); xs_page[:] = random_scalars(nn, 5)
+        xs_pin_t = torch.from_numpy(xs_page.view(np.int64).copy()).pin_memory()
+        xs_pin = xs_pin_t.numpy().view(np.uint64)
+        ntt_e2e = {}
+        for name, buf in (("pageable", xs_page), ("pinned", xs_pin)):
+            shim.NTT(nn, buf, shim.NTTInputOutputOrder.NN, shim.NTTDirection.Forward, shim.NTTType.Standard)
+            ms, _ = wall_timed(lambda: shim.NTT(nn, buf, shim.NTTInputOutputOrder.NN, shim.NTTDirection.Forward, shim.NTTType.Standard), 2)
+            ntt_e2e[name] = ms
         per_pass_ms = pass_ms / max(1, pass_n)
+        npass = pass_n // reps if reps else None
+        ach = ALGO_BYTES_PER_ELEMENT * nn / (ntt_ms * 1e-3) / 1e9
         ntt = {
             "metric": "fr_ntt_elements_per_sec", "value": nn * world / (ntt_ms * 1e-3), "unit": "elements/s",
             "workload": f"forward NN NTT of 2^{args.ntt_lg} Fr elements per GPU (replicas, no collective)",
-            "ms_per_transform": ntt_ms, "passes_per_transform": pass_n // reps if reps else None,
-            "e2e": {"value": nn * world / (ntt_e2e_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": nn * 32,
-                    "d2h_bytes_per_step": nn * 32, "api": "snarkvm_ntt (host buffer, pinned)"},
-            "roofline": {"bound": "hbm", "kernel": "k_ntt_pass", "achieved": ALGO_BYTES_PER_ELEMENT * nn / (per_pass_ms * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": ALGO_BYTES_PER_ELEMENT * nn / (per_pass_ms * 1e-3) / 1e9 / peak,
-                         "traffic": load_traffic("k_ntt_pass"), "per_launch_ms": per_pass_ms,
-                         "note": "per pass: 64 B/element algorithmic; a transform is %d passes" % (pass_n // reps)},
+            "ms_per_transform": ntt_ms, "passes_per_transform": npass,
+            "e2e": {"value": nn * world / (ntt_e2e["pageable"] * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": nn * 32,
+                    "d2h_bytes_per_step": nn * 32, "ms_per_step": ntt_e2e["pageable"], "api": "snarkvm_ntt (pageable host buffer)"},
+            "e2e_pinned": {"value": nn * world / (ntt_e2e["pinned"] * 1e-3), "unit": "elements/s", "ms_per_step": ntt_e2e["pinned"]},
+            "roofline": {"bound": "hbm", "kernel": "k_ntt_pass x%d (one transform)" % (npass or 0), "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": load_traffic("ntt_transform"), "per_launch_ms": ntt_ms,
+                         "per_pass": {"ms": per_pass_ms, "achieved": ALGO_BYTES_PER_ELEMENT * nn / (per_pass_ms * 1e-3) / 1e9},
+                         "note": "SURVEY §8(d): 64 B per element per TRANSFORM over the whole transform's duration; the butterflies are "
+                                 "bound by the INT32 multiplier (1 Fr mul each), not by HBM"},
         }
+        del x, scratch
 
-    # ---- BASELINE config 4: KZG10 commit core at 2^22 coefficients (Montgomery → canonical → MSM), operands resident ----
+    # ---- BASELINE config 4: KZG10 commit at 2^22 coefficients with hiding_bound = Some(1), operands resident ----
     kzg = None
     if not args.skip_kzg:
         nk = 1 << args.kzg_lg
-        coeffs = torch.from_numpy(random_scalars(nk, 4242 + rank).view(np.int64)).to(dev)
-        powers = bases[:nk] if nk <= n else device.generate_bases(nk, seed=0xB200 + rank, device=dev)
-        for _ in range(3):
-            device.kzg_commit(powers, coeffs)
-        barrier()
-        e0.record()
-        for _ in range(5):
-            device.kzg_commit(powers, coeffs)
-        e1.record()
-        barrier()
-        kzg_ms = max_over_ranks(e0.elapsed_time(e1)) / 5
-        kzg = {"metric": "kzg10_commit_coefficients_per_sec", "value": nk * world / (kzg_ms * 1e-3), "unit": "coefficients/s",
-               "ms_per_commit": kzg_ms, "workload": f"2^{args.kzg_lg}-coefficient polynomial, powers resident in HBM, per GPU"}
-        # same commitment over precomputed tables 2^{c·w}·P_i of the powers (one bucket set for all windows)
-        t0 = time.perf_counter()
-        pre = device.PrecomputedBases(powers)
-        torch.cuda.synchronize()
-        pre_s = time.perf_counter() - t0
-        assert (pre.kzg_commit(coeffs) == device.kzg_commit(powers, coeffs)).all()
+        c_np = random_scalars(nk, 4242 + rank)                                   # Montgomery images of random coefficients
+        b_np2 = random_scalars(3, 4343 + rank)                                   # blinding polynomial: degree hiding_bound + 1
+        coeffs = torch.from_numpy(c_np.view(np.int64)).to(dev)
+        blind = torch.from_numpy(b_np2.view(np.int64)).to(dev)
+        powers = bases[:nk] if nk <= n else device.generate_bases(nk, seed=seed, device=dev)
+        gseed = 0x6A00 + rank
+        gamma = device.generate_bases(8, seed=gseed, device=dev)
+        kexpect = chk.point(chk.dot(chk.cpu.fr_from_mont(c_np), seed) + chk.dot(chk.cpu.fr_from_mont(b_np2), gseed))
+        kfn = lambda: device.kzg_commit_hiding(powers, coeffs, gamma, blind)     # noqa: E731
+        checks["kzg_commit_hiding"] = bool((kfn() == kexpect).all())
+        assert checks["kzg_commit_hiding"], "KZG hiding commitment differs from the closed form"
         for _ in range(2):
-            pre.kzg_commit(coeffs)
-        barrier()
-        e0.record()
-        for _ in range(5):
-            pre.kzg_commit(coeffs)
-        e1.record()
-        barrier()
-        pre_ms = max_over_ranks(e0.elapsed_time(e1)) / 5
-        kzg["precomputed_tables"] = {"value": nk * world / (pre_ms * 1e-3), "unit": "coefficients/s", "ms_per_commit": pre_ms,
-                                     "window_bits": pre.c, "windows": pre.nwin, "table_bytes": pre.table_bytes,
-                                     "one_time_precompute_s": pre_s}
-        pre.free()
+            kfn()
+        kzg_ms, _ = timed(kfn, 5)
+        kzg = {"metric": "kzg10_commit_coefficients_per_sec", "value": nk * world / (kzg_ms * 1e-3), "unit": "coefficients/s",
+               "ms_per_commit": kzg_ms, "checked": True,
+               "workload": f"KZG10::commit of a 2^{args.kzg_lg}-coefficient polynomial, hiding_bound = Some(1) (3 blinding terms in the same pass), "
+                           f"powers resident in HBM, per GPU"}
+        # a round of 8 commitments of 2^20 coefficients in ONE pass (sonic_pc/mod.rs:177-257)
+        nb = 1 << 20
+        if nb <= nk:
+            polys = [coeffs[i * (nk // 8): i * (nk // 8) + nb] if (i * (nk // 8) + nb) <= nk else coeffs[:nb] for i in range(8)]
+            polys = [p.contiguous() for p in polys]
+            want0 = device.kzg_commit(powers, polys[0])
+            got = device.kzg_commit_batch(powers, polys)
+            checks["kzg_batch_vs_single"] = bool((got[0] == want0).all() and (got[7] == device.kzg_commit(powers, polys[7])).all())
+            assert checks["kzg_batch_vs_single"]
+            b_ms, _ = timed(lambda: device.kzg_commit_batch(powers, polys), 5)
+            o_ms, _ = timed(lambda: device.kzg_commit(powers, polys[0]), 5)
+            kzg["round_batch"] = {"value": 8 * nb * world / (b_ms * 1e-3), "unit": "coefficients/s", "ms_per_round": b_ms,
+                                  "workload": "8 polynomials × 2^20 coefficients, one pass over the resident powers",
+                                  "one_by_one_ms": 8 * o_ms, "single_2^20_ms": o_ms}
+        if not args.skip_precomputed:
+            t0 = time.perf_counter()
+            pre = device.PrecomputedBases(powers)
+            torch.cuda.synchronize()
+            pre_s = time.perf_counter() - t0
+            assert (pre.kzg_commit(coeffs) == device.kzg_commit(powers, coeffs)).all()
+            for _ in range(2):
+                pre.kzg_commit(coeffs)
+            pre_ms, _ = timed(lambda: pre.kzg_commit(coeffs), 5)
+            kzg["precomputed_tables"] = {"value": nk * world / (pre_ms * 1e-3), "unit": "coefficients/s", "ms_per_commit": pre_ms,
+                                         "window_bits": pre.c, "windows": pre.nwin, "table_bytes": pre.table_bytes,
+                                         "one_time_precompute_s": pre_s, "note": "plain (non-hiding) commitment over the tables"}
+            pre.free()
         # UniversalParams::lagrange_basis: iFFT over G1 points (data_structures.rs:68-72)
         ng = 1 << args.g1_ntt_lg
         gp = powers.reshape(-1)[: ng * 104].contiguous()
         device.lagrange_basis(gp)
-        barrier()
-        e0.record()
-        device.lagrange_basis(gp)
-        e1.record()
-        barrier()
-        kzg["lagrange_basis"] = {"ms": max_over_ranks(e0.elapsed_time(e1)), "workload": f"ifft of 2^{args.g1_ntt_lg} G1 points per GPU",
-                                 "unit": "ms"}
+        lb_ms, _ = timed(lambda: device.lagrange_basis(gp), 1)
+        kzg["lagrange_basis"] = {"ms": lb_ms, "workload": f"ifft of 2^{args.g1_ntt_lg} G1 points per GPU", "unit": "ms"}
 
     if rank != 0:
         return
@@ -423,48 +558,48 @@ def run_product(args, rank, world, local_rank):
     # ---- cpu_baseline: the oracle port on this box's host cores, bounded sample (N = 1 only) ----
     cpu_baseline = None
     if world == 1 and not args.skip_cpu:
-        from oracle import cpu
-        cpu.build()
-        try:
-            cpu.set_num_threads(len(os.sched_getaffinity(0)))
-        except AttributeError:
-            cpu.set_num_threads(os.cpu_count() or 1)
-        lg_s = args.cpu_lg
-        hb = b_np[: 1 << lg_s]
-        v, dt = cpu_msm_points_per_s(lg_s, hb)
+        cpu = chk.cpu
+        lg_s = min(args.cpu_lg, args.lg)
+        hb = bases[: 1 << lg_s].cpu().numpy()
+        v, dt = cpu_msm_points_per_s(cpu, hb, scal_np[: 1 << lg_s])
         cpu_baseline = {"value": v, "unit": "points/s", "cores": cpu.num_threads(), "kind": "port",
-                        "sample": f"one 2^{lg_s}-point batched::msm ({dt:.1f} s) — C restatement of the reference CPU path, "
-                                  f"OpenMP task per window"}
+                        "sample": f"one 2^{lg_s}-point batched::msm ({dt:.1f} s) on the first 2^{lg_s} points and scalars of the GPU's input — "
+                                  f"C restatement of the reference CPU path, OpenMP task per window"}
         if ntt is not None:
-            nv, ndt, nth = cpu_ntt_elements_per_s(args.cpu_ntt_lg)
+            nv, ndt, nth = cpu_ntt_elements_per_s(cpu, args.cpu_ntt_lg)
             ntt["cpu_baseline"] = {"value": nv, "unit": "elements/s", "cores": nth, "kind": "port",
                                    "sample": f"one 2^{args.cpu_ntt_lg} forward fft_in_place ({ndt:.2f} s), best team size of 16/32/64/all"}
 
     plan = device.msm_plan(n)
     plan_levels = 4 if args.lg >= 21 else 1 if args.lg == 20 else 0      # msm_make_plan (csrc/msm.cu)
+    cfg = workload_config(args, world)
     line = {
         "metric": "bls12_377_g1_msm_points_per_sec", "value": value, "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (Montgomery integer arithmetic, IMAD pipe)",
-        "data": "synthetic",
-        "config": {"workload": f"bls12_377_g1_msm_2^{args.lg}_points_per_gpu", "points_per_gpu": n, "scalars": "uniform < 2^252",
-                   "bases": "h(seed,i)*G, affine 104 B stride", "window_bits": plan["c"], "windows": plan["nwin"],
-                   "parallelism": f"points sharded over {world} GPU(s); one all-gather of window sums" if world > 1 else "single GPU",
-                   "l2": f"inputs ({n * 136 / 1e9:.2f} GB/step) plus {n * plan['nwin'] * 4 / 1e9:.2f} GB of sorted entries and the dense pair-level scratch stream through the 126 MB L2 every step — no flush needed"},
+        "data": "synthetic", "config": cfg,
+        "plan": {"window_bits": plan["c"], "windows": plan["nwin"], "pair_levels": plan_levels,
+                 "l2": f"inputs ({n * 136 / 1e9:.2f} GB/step) plus {n * plan['nwin'] * 4 / 1e9:.2f} GB of sorted entries and the dense pair-level "
+                       f"scratch stream through the 126 MB L2 every step — no flush needed"},
+        "checked": all(checks.values()), "checks": checks,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * (104 + 32) * world,
-                "d2h_bytes_per_step": 144 * world, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "api": "snarkvm_msm (drop-in C-ABI, pinned host buffers)" if world == 1 else "sharded.msm_sharded after H2D"},
+                "d2h_bytes_per_step": (144 if world == 1 else plan["nwin"] * 192) * world, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "host_memory": "pageable (plain malloc, what a Rust Vec is); staged through the library's pinned ring",
+                "api": "snarkvm_msm (drop-in C-ABI)" if world == 1 else "sharded.msm_sharded_async on host buffers (snarkvm_b200_msm_window_sums_host + NCCL)"},
+        "e2e_pinned": {"value": n * world / (e2e["pinned"] * 1e-3), "unit": "points/s", "ms_per_step": e2e["pinned"],
+                       "host_memory": "pinned (cudaHostAlloc)"},
         "e2e_registered_bases": e2e_resident,
+        "sharded_total": strong,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "bucket accumulation phase: k_densify_bases + k_pair_level x%d + k_bucket_accumulate%s" % (
+        "roofline": {"bound": "hbm", "kernel": "bucket accumulation phase: k_densify_bases + k_pair_level2 x%d + k_bucket_accumulate%s" % (
                          plan_levels, "_dense" if plan_levels else ""),
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": load_traffic("msm_bucket_accumulation_phase") if args.lg == 24 else None,
-                     "peak_source": peak_src, "per_launch_ms": acc_ms_per_launch,
+                     "peak_source": peak_src, "per_launch_ms": acc_ms_per_step,
                      "share_of_step": {"sort": sort_ms / ms_total, "accumulate": acc_ms / ms_total, "reduce": red_ms / ms_total},
-                     "note": "algorithmic 128 B/point over the phase's duration; the phase is bound by the INT32 multiplier (fmaheavy pipe "
-                             "65-87 % active, profiles/r1_msm_metrics.csv), not by HBM"},
+                     "note": "algorithmic 128 B/point over the phase's duration; the phase is bound by the INT32 multiplier (fmaheavy pipe, "
+                             "profiles/), not by HBM"},
         "cpu_baseline": cpu_baseline,
         "ntt": ntt,
         "kzg_commit": kzg,
@@ -479,17 +614,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lg", type=int, default=24, help="log2 points per GPU (BASELINE configs[1]: 2^20/2^22/2^24)")
+    ap.add_argument("--total-lg", type=int, default=26, help="BASELINE config 5a: total points of the strong-scaling sharded MSM (0 = skip)")
     ap.add_argument("--ntt-lg", type=int, default=24)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-lg", type=int, default=21, help="cpu_baseline sample size (bounded)")
+    ap.add_argument("--cpu-lg", type=int, default=22, help="cpu_baseline sample size (bounded)")
     ap.add_argument("--cpu-ntt-lg", type=int, default=22)
-    ap.add_argument("--ref-lg", type=int, default=20, help="--impl reference: points per step")
+    ap.add_argument("--ref-lg", type=int, default=22, help="--impl reference: points per step (bounded sample)")
     ap.add_argument("--ref-ntt-lg", type=int, default=22)
     ap.add_argument("--kzg-lg", type=int, default=22)
     ap.add_argument("--g1-ntt-lg", type=int, default=12, help="size of the G1 iFFT (lagrange_basis) timed inside the KZG extra")
     ap.add_argument("--skip-kzg", action="store_true")
     ap.add_argument("--skip-ntt", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-strong", action="store_true")
+    ap.add_argument("--skip-registered", action="store_true")
+    ap.add_argument("--skip-precomputed", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

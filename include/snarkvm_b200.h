@@ -98,9 +98,26 @@ SNARKVM_API int snarkvm_b200_msm_plan(size_t npoints, int* c, int* nwin, uint32_
 SNARKVM_API int snarkvm_b200_msm_device(void* out144, const void* d_points, size_t npoints, const void* d_scalars,
                             size_t stride, void* stream);
 
+/* `count` MSMs over the SAME resident bases in ONE pass (all commitments of a prover round share powers_of_beta_g,
+ * polycommit/sonic_pc/mod.rs:177-257): one digit/sort keyed by (vector, window, bucket), one set of pair levels, one D2H and one
+ * synchronisation.  d_scalars / nscalars: HOST arrays of device pointers / lengths (canonical 32-byte integers);
+ * out144s: count * 144 B of HOST memory.  Vector i uses the first nscalars[i] bases. */
+SNARKVM_API int snarkvm_b200_msm_batch_device(void* out144s, const void* d_points, size_t stride, const void* const* d_scalars,
+                                              const size_t* nscalars, size_t count, void* stream);
+
 /* MSM pieces for multi-GPU sharding: per-window sums as XYZZ points (192 B each) in HBM ... */
 SNARKVM_API int snarkvm_b200_msm_window_sums_device(void* d_window_sums /* nwin * 192 B */, const void* d_points, size_t npoints,
                                         const void* d_scalars, size_t stride, void* stream);
+/* ... under the plan of `plan_npoints` >= npoints: every rank of a sharded MSM passes the size of the LARGEST shard, so all ranks
+ * use the same window size and window count whatever their own shard length (snarkvm_b200_msm_plan(plan_npoints) gives nwin and c);
+ * an empty shard (npoints = 0) contributes infinity sums.  d_flags: device u32 that receives bit 0 = "a scalar has bits 253..255
+ * set" (the sums are then meaningless), or NULL to ignore. */
+SNARKVM_API int snarkvm_b200_msm_window_sums_plan_device(void* d_window_sums, uint32_t* d_flags, size_t plan_npoints, const void* d_points,
+                                                         size_t npoints, const void* d_scalars, size_t stride, void* stream);
+/* ... the same from HOST buffers: uploads the shard (point ranges overlapped with the kernels of the previous range, pageable sources
+ * staged through pinned buffers) and leaves its window sums in HBM without synchronising, so a collective can follow at once. */
+SNARKVM_API int snarkvm_b200_msm_window_sums_host(void* d_window_sums, uint32_t* d_flags, size_t plan_npoints, const void* h_points,
+                                                  size_t npoints, const void* h_scalars, size_t stride, void* stream);
 /* ... summed across ranks after an all-gather: d_out[i] = sum_r d_in[r][i] ... */
 SNARKVM_API int snarkvm_b200_xyzz_sum_ranks_device(void* d_out, const void* d_in, int nranks, int count, void* stream);
 /* ... and folded on the host: out144 = sum_w 2^(c*w) * window_sums[w]  (h_window_sums in HOST memory). */
@@ -128,10 +145,25 @@ SNARKVM_API int snarkvm_b200_kzg_commit_precomputed_device(void* out144, const v
 SNARKVM_API int snarkvm_b200_kzg_commit_hiding_device(void* out144, const void* d_powers, size_t stride, const void* d_coeffs_mont,
                                                       size_t ncoeffs, const void* d_gamma_powers, const void* d_blinding_mont,
                                                       size_t nblinding, void* stream);
-/* `count` commitments against the same resident powers (one prover round, polycommit/sonic_pc/mod.rs:177-257).
+/* `count` commitments against the same resident powers in ONE pass (one prover round, polycommit/sonic_pc/mod.rs:177-257).
  * d_coeffs_mont / ncoeffs: HOST arrays of device pointers / lengths; out144s: count * 144 B of HOST memory. */
 SNARKVM_API int snarkvm_b200_kzg_commit_batch_device(void* out144s, const void* d_powers, size_t stride, const void* const* d_coeffs_mont,
                                                      const size_t* ncoeffs, size_t count, void* stream);
+/* ... with hiding bounds: polynomial i also gets sum_j blinding_i[j] * gamma_powers[j] (nblinding[i] = 0: plain commitment);
+ * the blinding terms ride in the same pass as a second scalar segment of the same sum. */
+SNARKVM_API int snarkvm_b200_kzg_commit_batch_hiding_device(void* out144s, const void* d_powers, size_t stride,
+                                                            const void* const* d_coeffs_mont, const size_t* ncoeffs,
+                                                            const void* d_gamma_powers, const void* const* d_blinding_mont,
+                                                            const size_t* nblinding, size_t count, void* stream);
+/* ... over the precomputed tables of the resident powers (one bucket set per polynomial). */
+SNARKVM_API int snarkvm_b200_kzg_commit_batch_precomputed_device(void* out144s, const void* handle, const void* const* d_coeffs_mont,
+                                                                 const size_t* ncoeffs, size_t count, void* stream);
+
+/* MSM scratch budget of the current device (bytes): the limit concurrent calls share (half the device unless
+ * SNARKVM_B200_SCRATCH_LIMIT_GB is set; callers that do not fit wait instead of failing), what is in flight, and the high-water mark. */
+SNARKVM_API int snarkvm_b200_msm_scratch_stats(size_t* limit_bytes, size_t* in_use_bytes, size_t* peak_bytes);
+/* change the limit at run time (also resets the high-water mark) */
+SNARKVM_API int snarkvm_b200_msm_set_scratch_limit(size_t limit_bytes);
 
 /* FFT over G1 points (EvaluationDomain::{fft,ifft} with T = G1Projective, fft/domain.rs:169-221): 2^lg affine points in, affine
  * points out, natural order.  direction 1 = inverse, which is UniversalParams::lagrange_basis

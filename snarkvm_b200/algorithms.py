@@ -223,10 +223,12 @@ class KZG10:
         return KZG10.commit_lagrange(lagrange_basis_at_beta_g, divisor), None
 
     @staticmethod
-    def batch_commit(powers_of_beta_g, polynomials_mont):
-        """all plain commitments of one round against the same powers (sonic_pc/mod.rs:177-257) → [count, 18] uint64"""
+    def batch_commit(powers_of_beta_g, polynomials_mont, powers_of_beta_times_gamma_g=None, blindings_mont=None):
+        """all commitments of one round against the same powers in ONE device pass (sonic_pc/mod.rs:177-257) → [count, 18] uint64;
+        `blindings_mont[i]` (or None) is polynomial i's blinding polynomial (hiding_bound = Some(_), kzg10/mod.rs:129-150)"""
         from . import device
-        return device.kzg_commit_batch(powers_of_beta_g, list(polynomials_mont))
+        return device.kzg_commit_batch(powers_of_beta_g, list(polynomials_mont), gamma_powers=powers_of_beta_times_gamma_g,
+                                       blindings_mont=None if blindings_mont is None else list(blindings_mont))
 
 
 class UniversalParams:

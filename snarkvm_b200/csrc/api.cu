@@ -4,10 +4,16 @@
 // cudaError_t code; leave outputs untouched on failure so the Rust caller can fall back.
 #include "../../include/snarkvm_b200.h"
 
+#include <atomic>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -48,7 +54,6 @@ int thread_stream(cudaStream_t* out) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     dev &= 63;
-    ensure_pool_configured();
     if (!t_ctx.have[dev]) {
         e = cudaStreamCreateWithFlags(&t_ctx.stream[dev], cudaStreamNonBlocking);
         if (e != cudaSuccess) return (int)e;
@@ -76,18 +81,42 @@ int thread_copy_stream(cudaStream_t* out) {
 // Registered (resident) bases: the SRS powers of a proving key are constant, and the reference re-passes the same
 // host slice on every commitment (kzg10/mod.rs:119,149).  A caller may register that slice once; snarkvm_msm then
 // recognises the pointer and skips the 104 B/point upload.  Opt-in: the caller promises not to mutate the slice.
-struct ResidentBases { void* d_ptr; size_t npoints; size_t stride; int device; void* tables; /* PrecomputedBases* or null */ };
+// Entries are shared_ptr-owned: a call that found an entry keeps it (device copy, tables) alive until it returns, so a
+// concurrent unregister / re-register only drops the map's reference and the memory goes when the last call ends.
+struct PrecomputedBases { uint32_t* table; size_t n; MsmPlan plan; int device; };
+struct ResidentBases {
+    void* d_ptr = nullptr;
+    size_t npoints = 0, stride = 0;
+    int device = 0;
+    std::atomic<PrecomputedBases*> tables{nullptr};
+    uint8_t head[104] = {}, tail[104] = {};       // first and last point of the host slice at registration (stale-address check)
+    ~ResidentBases() {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != device) cudaSetDevice(device);
+        if (d_ptr) cudaFree(d_ptr);
+        if (PrecomputedBases* t = tables.load()) { cudaFree(t->table); delete t; }
+        if (cur != device) cudaSetDevice(cur);
+    }
+};
 std::mutex g_bases_mu;
-std::map<const void*, ResidentBases> g_bases;
+std::map<const void*, std::shared_ptr<ResidentBases>> g_bases;
 
-bool find_resident(const void* host, size_t npoints, size_t stride, ResidentBases* out) {
+std::shared_ptr<ResidentBases> find_resident(const void* host, size_t npoints, size_t stride) {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return false;
-    std::lock_guard<std::mutex> lock(g_bases_mu);
-    auto it = g_bases.find(host);
-    if (it == g_bases.end() || it->second.device != dev || it->second.stride != stride || it->second.npoints < npoints) return false;
-    *out = it->second;
-    return true;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::shared_ptr<ResidentBases> r;
+    {
+        std::lock_guard<std::mutex> lock(g_bases_mu);
+        auto it = g_bases.find(host);
+        if (it == g_bases.end()) return nullptr;
+        r = it->second;
+    }
+    if (r->device != dev || r->stride != stride || r->npoints < npoints) return nullptr;
+    // a freed and re-used host buffer at the same address would silently compute with stale bases: compare the end points
+    if (memcmp(r->head, host, 104) != 0) return nullptr;
+    if (memcmp(r->tail, (const uint8_t*)host + (r->npoints - 1) * stride, 104) != 0) return nullptr;
+    return r;
 }
 
 void write_infinity(void* out144) {
@@ -95,24 +124,193 @@ void write_infinity(void* out144) {
     host::xyzz_to_normalised_projective(inf, (uint64_t*)out144);
 }
 
-int msm_device_impl(void* out144, const void* d_points, size_t npoints, const void* d_scalars, size_t stride,
+// Runs `njobs` sums through ONE msm_core pass and finishes them on the host: one D2H of njobs·sets XYZZ points plus the
+// overflow flag, ONE stream synchronisation, then the Horner fold per job (253 doublings on 64-bit host limbs ≈ 0.1 ms,
+// exactly where the reference's own plugin finishes, snarkvm.cu:290-295).  out144s: njobs × 144 B of HOST memory.
+int msm_jobs_impl(void* out144s, const MsmPlan& plan, const MsmBases* bases, int nbases, const uint32_t* table, size_t table_n,
+                  const MsmSegment* segs, int nsegs, int njobs, cudaStream_t stream) {
+    const size_t sets = table ? 1 : (size_t)plan.nwin;
+    const size_t npts = (size_t)njobs * sets;
+    uint32_t* d_buf = nullptr;
+    cudaError_t e = pool_alloc(&d_buf, npts * 192 + 256, stream);
+    if (e != cudaSuccess) return (int)e;
+    uint32_t* d_flags = d_buf + npts * 48;
+    int rc = (int)cudaMemsetAsync(d_flags, 0, 256, stream);
+    if (rc == 0) rc = msm_core(d_buf, d_flags, plan, bases, nbases, table, table_n, segs, nsegs, njobs, stream);
+    std::vector<host::Xyzz> sums(npts + 2);
+    if (rc == 0) rc = (int)cudaMemcpyAsync(sums.data(), d_buf, npts * 192 + 256, cudaMemcpyDeviceToHost, stream);
+    cudaFreeAsync(d_buf, stream);
+    if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
+    if (rc != 0) return rc;
+    uint32_t flags = 0;
+    memcpy(&flags, sums.data() + npts, 4);
+    if (flags & 1u) return (int)cudaErrorInvalidValue;           // a scalar ≥ 2^253: not a canonical Fr, let the caller fall back
+    auto finish = [&](int j) {
+        host::Xyzz total = table ? sums[(size_t)j] : host::horner_windows(sums.data() + (size_t)j * sets, plan.nwin, plan.c);
+        host::xyzz_to_normalised_projective(total, (uint64_t*)((uint8_t*)out144s + (size_t)j * 144));
+    };
+    if (njobs <= 2) { for (int j = 0; j < njobs; j++) finish(j); }
+    else {
+        const int nt = njobs < 8 ? njobs : 8;
+        std::vector<std::thread> th;
+        std::atomic<int> next{0};
+        for (int t = 0; t < nt; t++) th.emplace_back([&] { for (int j; (j = next.fetch_add(1)) < njobs;) finish(j); });
+        for (auto& t : th) t.join();
+    }
+    return 0;
+}
+
+int msm_device_impl(void* out144, const void* d_points, size_t npoints, const void* d_scalars, size_t stride, int mont,
                     cudaStream_t stream) {
     if (npoints == 0) { write_infinity(out144); return 0; }
     if (stride < 104 || (stride & 7)) return (int)cudaErrorInvalidValue;
-    ensure_pool_configured();
     MsmPlan plan = msm_make_plan(npoints);
-    uint32_t* d_sums = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&d_sums, (size_t)plan.nwin * 192, stream);
-    if (e != cudaSuccess) return (int)e;
-    int rc = msm_window_sums_device(d_sums, plan, d_points, stride, d_scalars, npoints, stream);
-    std::vector<host::Xyzz> sums((size_t)plan.nwin);
-    if (rc == 0) rc = (int)cudaMemcpyAsync(sums.data(), d_sums, (size_t)plan.nwin * 192, cudaMemcpyDeviceToHost, stream);
-    cudaFreeAsync(d_sums, stream);
-    if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
-    if (rc != 0) return rc;
-    host::Xyzz total = host::horner_windows(sums.data(), plan.nwin, plan.c);
-    host::xyzz_to_normalised_projective(total, (uint64_t*)out144);
+    MsmBases b{d_points, stride, npoints};
+    MsmSegment sg{d_scalars, npoints, 0u, 0u, mont};
+    return msm_jobs_impl(out144, plan, &b, 1, nullptr, 0, &sg, 1, 1, stream);
+}
+
+// ----------------------------------------------------------------------------------------
+// Host → device uploads.  A Rust Vec is PAGEABLE memory: cudaMemcpyAsync from it goes through the driver's own
+// staging at a fraction of the link rate and blocks the calling thread.  Pageable sources therefore go through a ring
+// of pinned buffers owned by the calling thread, filled by a small pool of copy threads (several cores are needed to
+// feed PCIe Gen5) and drained by async DMA on the thread's copy stream; pinned sources (cudaHostAlloc / registered)
+// are copied directly.
+// ----------------------------------------------------------------------------------------
+class CopyPool {
+public:
+    static CopyPool& get() { static CopyPool* p = new CopyPool(); return *p; }      // leaked on purpose: threads outlive static destructors
+    // memcpy(dst, src, bytes) split over the pool and the caller; returns when all of it is done
+    void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+        const size_t piece = (size_t)2 << 20;
+        if (bytes <= piece || nthreads_ == 0) { memcpy(dst, src, bytes); return; }
+        Batch batch;
+        batch.dst = (uint8_t*)dst; batch.src = (const uint8_t*)src; batch.bytes = bytes; batch.piece = piece;
+        batch.npieces = (bytes + piece - 1) / piece;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            queue_.push_back(&batch);
+        }
+        cv_.notify_all();
+        work(batch);                                              // the caller copies too
+        std::unique_lock<std::mutex> lock(mu_);
+        for (auto it = queue_.begin(); it != queue_.end(); ++it) if (*it == &batch) { queue_.erase(it); break; }
+        // no worker can pick the batch up any more; wait for the ones inside it
+        done_cv_.wait(lock, [&] { return batch.active == 0; });
+    }
+private:
+    struct Batch {
+        uint8_t* dst; const uint8_t* src; size_t bytes, piece, npieces;
+        std::atomic<size_t> next{0};
+        int active = 0;                                           // workers inside work(); guarded by mu_
+    };
+    CopyPool() {
+        int n = 6;
+        if (const char* e = getenv("SNARKVM_B200_COPY_THREADS")) { int v = atoi(e); if (v >= 0 && v <= 64) n = v; }
+        nthreads_ = n;
+        for (int i = 0; i < n; i++) std::thread([this] { loop(); }).detach();
+    }
+    static void work(Batch& b) {
+        for (;;) {
+            size_t k = b.next.fetch_add(1);
+            if (k >= b.npieces) return;
+            size_t off = k * b.piece, len = b.bytes - off < b.piece ? b.bytes - off : b.piece;
+            memcpy(b.dst + off, b.src + off, len);
+        }
+    }
+    void loop() {
+        std::unique_lock<std::mutex> lock(mu_);
+        for (;;) {
+            cv_.wait(lock, [&] { return !queue_.empty(); });
+            Batch* b = queue_.front();
+            if (b->next.load() >= b->npieces) { queue_.pop_front(); continue; }      // nothing left to claim in it
+            b->active++;
+            lock.unlock();
+            work(*b);
+            lock.lock();
+            if (--b->active == 0) done_cv_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    std::deque<Batch*> queue_;
+    int nthreads_ = 0;
+};
+
+static bool host_is_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+}
+
+// per-thread ring of pinned staging buffers
+struct StageRing {
+    static constexpr int SLOTS = 4;
+    static constexpr size_t SLOT_BYTES = (size_t)32 << 20;
+    void* buf[SLOTS] = {};
+    cudaEvent_t ev[SLOTS] = {};
+    bool used[SLOTS] = {};
+    int next = 0;
+    int init() {
+        if (buf[0]) return 0;
+        for (int i = 0; i < SLOTS; i++) {
+            cudaError_t e = cudaHostAlloc(&buf[i], SLOT_BYTES, cudaHostAllocDefault);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return (int)e;
+        }
+        return 0;
+    }
+};
+thread_local StageRing t_ring;
+
+// dst (device) ← src (host), enqueued on `copy`: direct DMA for pinned sources, staged for pageable ones
+int upload(void* d_dst, const void* h_src, size_t bytes, cudaStream_t copy, bool pinned) {
+    if (bytes == 0) return 0;
+    static const bool no_stage = getenv("SNARKVM_B200_NO_STAGING") != nullptr;
+    if (pinned || no_stage || bytes < ((size_t)1 << 20)) return (int)cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, copy);
+    int rc = t_ring.init();
+    if (rc) return rc;
+    for (size_t off = 0; off < bytes; off += StageRing::SLOT_BYTES) {
+        const size_t len = bytes - off < StageRing::SLOT_BYTES ? bytes - off : StageRing::SLOT_BYTES;
+        const int sl = t_ring.next;
+        t_ring.next = (sl + 1) % StageRing::SLOTS;
+        if (t_ring.used[sl] && (rc = (int)cudaEventSynchronize(t_ring.ev[sl])) != 0) return rc;     // its previous DMA has drained
+        CopyPool::get().parallel_memcpy(t_ring.buf[sl], (const uint8_t*)h_src + off, len);
+        if ((rc = (int)cudaMemcpyAsync((uint8_t*)d_dst + off, t_ring.buf[sl], len, cudaMemcpyHostToDevice, copy)) != 0) return rc;
+        if ((rc = (int)cudaEventRecord(t_ring.ev[sl], copy)) != 0) return rc;
+        t_ring.used[sl] = true;
+    }
     return 0;
+}
+// src (device) → dst (host) after everything already enqueued on `stream`; returns when dst is complete
+int download(void* h_dst, const void* d_src, size_t bytes, cudaStream_t stream, bool pinned) {
+    if (bytes == 0) return (int)cudaStreamSynchronize(stream);
+    static const bool no_stage = getenv("SNARKVM_B200_NO_STAGING") != nullptr;
+    if (pinned || no_stage || bytes < ((size_t)1 << 20)) {
+        int rc = (int)cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, stream);
+        return rc ? rc : (int)cudaStreamSynchronize(stream);
+    }
+    int rc = t_ring.init();
+    if (rc) return rc;
+    for (int i = 0; i < StageRing::SLOTS; i++)                                // uploads of this thread that may still be reading a slot
+        if (t_ring.used[i] && (rc = (int)cudaEventSynchronize(t_ring.ev[i])) != 0) return rc;
+    // DMA slot k+1 while the copy threads unload slot k
+    const size_t nslices = (bytes + StageRing::SLOT_BYTES - 1) / StageRing::SLOT_BYTES;
+    auto slice_len = [&](size_t k) { size_t off = k * StageRing::SLOT_BYTES; return bytes - off < StageRing::SLOT_BYTES ? bytes - off : StageRing::SLOT_BYTES; };
+    for (size_t k = 0; k < nslices && k < 2; k++) {
+        if ((rc = (int)cudaMemcpyAsync(t_ring.buf[k & 1], (const uint8_t*)d_src + k * StageRing::SLOT_BYTES, slice_len(k), cudaMemcpyDeviceToHost, stream)) != 0) return rc;
+        if ((rc = (int)cudaEventRecord(t_ring.ev[k & 1], stream)) != 0) return rc;
+    }
+    for (size_t k = 0; k < nslices; k++) {
+        if ((rc = (int)cudaEventSynchronize(t_ring.ev[k & 1])) != 0) return rc;
+        CopyPool::get().parallel_memcpy((uint8_t*)h_dst + k * StageRing::SLOT_BYTES, t_ring.buf[k & 1], slice_len(k));
+        if (k + 2 < nslices) {
+            if ((rc = (int)cudaMemcpyAsync(t_ring.buf[k & 1], (const uint8_t*)d_src + (k + 2) * StageRing::SLOT_BYTES, slice_len(k + 2), cudaMemcpyDeviceToHost, stream)) != 0) return rc;
+            if ((rc = (int)cudaEventRecord(t_ring.ev[k & 1], stream)) != 0) return rc;
+        }
+    }
+    for (int i = 0; i < StageRing::SLOTS; i++) t_ring.used[i] = false;      // every slot is idle again
+    return (int)cudaStreamSynchronize(stream);
 }
 
 // NN is native (bit reversal fused into the last pass); the other orders add explicit derange passes:
@@ -128,15 +326,14 @@ int ntt_ordered(void* d, uint32_t lg, int order, int dir, int type, void* scratc
 
 int polymul_device_impl(void* d_out, size_t pcount, const void* const* d_polys, const size_t* plens, size_t ecount,
                         const void* const* d_evals, const size_t* elens, uint32_t lg, cudaStream_t stream) {
-    ensure_pool_configured();
     const size_t n = (size_t)1 << lg, bytes = n * 32;
     if (pcount + ecount == 0) return 0;
     for (size_t i = 0; i < pcount; i++) if (plens[i] > n) return (int)cudaErrorInvalidValue;
     for (size_t i = 0; i < ecount; i++) if (elens[i] != n) return (int)cudaErrorInvalidValue;   // polynomial.cuh:95
     void *tmp = nullptr, *scratch = nullptr;
     cudaError_t e;
-    if ((e = cudaMallocAsync(&tmp, bytes, stream)) != cudaSuccess) return (int)e;
-    if ((e = cudaMallocAsync(&scratch, bytes, stream)) != cudaSuccess) { cudaFreeAsync(tmp, stream); return (int)e; }
+    if ((e = pool_alloc(&tmp, bytes, stream)) != cudaSuccess) return (int)e;
+    if ((e = pool_alloc(&scratch, bytes, stream)) != cudaSuccess) { cudaFreeAsync(tmp, stream); return (int)e; }
     int rc = 0;
     bool have = false;
     for (size_t i = 0; i < pcount && rc == 0; i++) {
@@ -175,13 +372,14 @@ snarkvm_error_t snarkvm_ntt(void* inout, uint32_t lg, snarkvm_ntt_order_t order,
     int rc = thread_stream(&stream);
     if (rc) return make_error(rc);
     const size_t bytes = ((size_t)1 << lg) * 32;
+    const bool pinned = host_is_pinned(inout);
     void *d = nullptr, *scratch = nullptr;
-    rc = (int)cudaMallocAsync(&d, bytes, stream);
-    if (rc == 0) rc = (int)cudaMallocAsync(&scratch, bytes, stream);
-    if (rc == 0) rc = (int)cudaMemcpyAsync(d, inout, bytes, cudaMemcpyHostToDevice, stream);
+    rc = (int)pool_alloc(&d, bytes, stream);
+    if (rc == 0) rc = (int)pool_alloc(&scratch, bytes, stream);
+    if (rc == 0) rc = upload(d, inout, bytes, stream, pinned);
     if (rc == 0) rc = ntt_ordered(d, lg, (int)order, (int)dir, (int)type, scratch, stream);
     if (rc == 0) rc = (int)cudaStreamSynchronize(stream);          // only copy back on success (snarkvm.cu:178-183)
-    if (rc == 0) rc = (int)cudaMemcpyAsync(inout, d, bytes, cudaMemcpyDeviceToHost, stream);
+    if (rc == 0) rc = download(inout, d, bytes, stream, pinned);
     if (d) cudaFreeAsync(d, stream);
     if (scratch) cudaFreeAsync(scratch, stream);
     int rs = (int)cudaStreamSynchronize(stream);
@@ -205,21 +403,21 @@ snarkvm_error_t snarkvm_polymul(void* out, size_t pcount, const void* polynomial
     std::vector<void*> dbuf(pcount + ecount, nullptr);
     std::vector<const void*> dp(pcount), de(ecount);
     void* d_out = nullptr;
-    rc = (int)cudaMallocAsync(&d_out, bytes, stream);
+    rc = (int)pool_alloc(&d_out, bytes, stream);
     for (size_t i = 0; i < pcount && rc == 0; i++) {
         size_t b = plens[i] ? plens[i] * 32 : 32;
-        rc = (int)cudaMallocAsync(&dbuf[i], b, stream);
-        if (rc == 0 && plens[i]) rc = (int)cudaMemcpyAsync(dbuf[i], polys[i], plens[i] * 32, cudaMemcpyHostToDevice, stream);
+        rc = (int)pool_alloc(&dbuf[i], b, stream);
+        if (rc == 0 && plens[i]) rc = upload(dbuf[i], polys[i], plens[i] * 32, stream, host_is_pinned(polys[i]));
         dp[i] = dbuf[i];
     }
     for (size_t i = 0; i < ecount && rc == 0; i++) {
-        rc = (int)cudaMallocAsync(&dbuf[pcount + i], bytes, stream);
-        if (rc == 0) rc = (int)cudaMemcpyAsync(dbuf[pcount + i], evals[i], bytes, cudaMemcpyHostToDevice, stream);
+        rc = (int)pool_alloc(&dbuf[pcount + i], bytes, stream);
+        if (rc == 0) rc = upload(dbuf[pcount + i], evals[i], bytes, stream, host_is_pinned(evals[i]));
         de[i] = dbuf[pcount + i];
     }
     if (rc == 0) rc = polymul_device_impl(d_out, pcount, dp.data(), plens, ecount, de.data(), elens, lg, stream);
     if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
-    if (rc == 0) rc = (int)cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, stream);
+    if (rc == 0) rc = download(out, d_out, bytes, stream, host_is_pinned(out));
     for (void* p : dbuf) if (p) cudaFreeAsync(p, stream);
     if (d_out) cudaFreeAsync(d_out, stream);
     int rs = (int)cudaStreamSynchronize(stream);
@@ -267,19 +465,20 @@ snarkvm_error_t snarkvm_msm(void* out, const void* points, size_t npoints, const
     int rc = thread_stream(&stream);
     if (rc) return make_error(rc);
     void *d_points = nullptr, *d_scalars = nullptr;
-    ResidentBases rb;
-    const bool resident = find_resident(points, npoints, ffi_affine_sz, &rb);
+    std::shared_ptr<ResidentBases> rb = find_resident(points, npoints, ffi_affine_sz);     // kept alive until this call returns
+    const bool resident = rb != nullptr;
     std::vector<size_t> bounds{0, npoints};
     if (!resident) bounds = msm_ranges(npoints);
     const int chunks = (int)bounds.size() - 1;
-    if (!resident) rc = (int)cudaMallocAsync(&d_points, npoints * ffi_affine_sz, stream);
-    if (rc == 0) rc = (int)cudaMallocAsync(&d_scalars, npoints * 32, stream);
+    const bool pin_s = host_is_pinned(scalars), pin_p = resident || host_is_pinned(points);
+    if (!resident) rc = (int)pool_alloc(&d_points, npoints * ffi_affine_sz, stream);
+    if (rc == 0) rc = (int)pool_alloc(&d_scalars, npoints * 32, stream);
     uint64_t result[18];
     if (chunks == 1) {
-        if (rc == 0) rc = (int)cudaMemcpyAsync(d_scalars, scalars, npoints * 32, cudaMemcpyHostToDevice, stream);
-        if (rc == 0 && !resident) rc = (int)cudaMemcpyAsync(d_points, points, npoints * ffi_affine_sz, cudaMemcpyHostToDevice, stream);
-        if (rc == 0 && resident && rb.tables) rc = snarkvm_b200_msm_precomputed_device(result, rb.tables, d_scalars, npoints, stream);
-        else if (rc == 0) rc = msm_device_impl(result, resident ? rb.d_ptr : d_points, npoints, d_scalars, ffi_affine_sz, stream);
+        if (rc == 0) rc = upload(d_scalars, scalars, npoints * 32, stream, pin_s);
+        if (rc == 0 && !resident) rc = upload(d_points, points, npoints * ffi_affine_sz, stream, pin_p);
+        if (rc == 0 && resident && rb->tables.load()) rc = snarkvm_b200_msm_precomputed_device(result, rb->tables.load(), d_scalars, npoints, stream);
+        else if (rc == 0) rc = msm_device_impl(result, resident ? rb->d_ptr : d_points, npoints, d_scalars, ffi_affine_sz, 0, stream);
     } else {
         cudaStream_t copy = nullptr;
         if (rc == 0) rc = thread_copy_stream(&copy);
@@ -292,30 +491,36 @@ snarkvm_error_t snarkvm_msm(void* out, const void* points, size_t npoints, const
         std::vector<cudaEvent_t> ev((size_t)chunks + 1, nullptr);
         for (auto& e : ev) if (rc == 0) rc = (int)cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
         uint32_t* d_sums = nullptr;
-        if (rc == 0) rc = (int)cudaMallocAsync((void**)&d_sums, sum_off.back() * 192, stream);
+        const size_t nsums = sum_off.back();
+        if (rc == 0) rc = (int)pool_alloc(&d_sums, nsums * 192 + 256, stream);
+        uint32_t* d_flags = d_sums ? d_sums + nsums * 48 : nullptr;
+        if (rc == 0) rc = (int)cudaMemsetAsync(d_flags, 0, 256, stream);
         // the pool allocations above are ordered on `stream`; the copy stream may touch them only after this point
         if (rc == 0) rc = (int)cudaEventRecord(ev[chunks], stream);
         if (rc == 0) rc = (int)cudaStreamWaitEvent(copy, ev[chunks], 0);
+        // Issue order: upload of range k, then the kernels of range k.  A pageable upload keeps this thread busy (staging)
+        // until its last slice is on its way, so the kernels of range k−1 — already enqueued — run underneath it.
         for (int k = 0; k < chunks && rc == 0; k++) {
             const size_t i0 = bounds[k], cn = bounds[k + 1] - i0;
-            rc = (int)cudaMemcpyAsync((uint8_t*)d_scalars + i0 * 32, (const uint8_t*)scalars + i0 * 32, cn * 32, cudaMemcpyHostToDevice, copy);
-            if (rc == 0) rc = (int)cudaMemcpyAsync((uint8_t*)d_points + i0 * ffi_affine_sz, (const uint8_t*)points + i0 * ffi_affine_sz,
-                                                   cn * ffi_affine_sz, cudaMemcpyHostToDevice, copy);
+            rc = upload((uint8_t*)d_scalars + i0 * 32, (const uint8_t*)scalars + i0 * 32, cn * 32, copy, pin_s);
+            if (rc == 0) rc = upload((uint8_t*)d_points + i0 * ffi_affine_sz, (const uint8_t*)points + i0 * ffi_affine_sz, cn * ffi_affine_sz, copy, pin_p);
             if (rc == 0) rc = (int)cudaEventRecord(ev[k], copy);
-        }
-        for (int k = 0; k < chunks && rc == 0; k++) {
-            const size_t i0 = bounds[k], cn = bounds[k + 1] - i0;
-            rc = (int)cudaStreamWaitEvent(stream, ev[k], 0);
-            if (rc == 0) rc = msm_window_sums_device(d_sums + sum_off[k] * 48, plans[k], (const uint8_t*)d_points + i0 * ffi_affine_sz,
+            if (rc == 0) rc = (int)cudaStreamWaitEvent(stream, ev[k], 0);
+            if (rc == 0) rc = msm_window_sums_device(d_sums + sum_off[k] * 48, d_flags, plans[k], (const uint8_t*)d_points + i0 * ffi_affine_sz,
                                                      ffi_affine_sz, (const uint8_t*)d_scalars + i0 * 32, cn, stream);
         }
-        std::vector<host::Xyzz> sums(sum_off.back());
-        if (rc == 0) rc = (int)cudaMemcpyAsync(sums.data(), d_sums, sums.size() * 192, cudaMemcpyDeviceToHost, stream);
+        std::vector<host::Xyzz> sums(nsums + 2);
+        if (rc == 0) rc = (int)cudaMemcpyAsync(sums.data(), d_sums, nsums * 192 + 256, cudaMemcpyDeviceToHost, stream);
         if (d_sums) cudaFreeAsync(d_sums, stream);
         // on any failure the copy stream may still be writing: drain it before the buffers go back to the pool
         if (copy) { int rs = (int)cudaStreamSynchronize(copy); if (rc == 0) rc = rs; }
         if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (rc == 0) {
+            uint32_t flags = 0;
+            memcpy(&flags, sums.data() + nsums, 4);
+            if (flags & 1u) rc = (int)cudaErrorInvalidValue;
+        }
         if (rc == 0) {
             host::Xyzz total = host::xyzz_inf();
             for (int k = 0; k < chunks; k++) host::xyzz_add(total, host::horner_windows(sums.data() + sum_off[k], plans[k].nwin, plans[k].c));
@@ -354,14 +559,128 @@ int snarkvm_b200_msm_plan(size_t npoints, int* c, int* nwin, uint32_t* cap) {
 int snarkvm_b200_msm_device(void* out144, const void* d_points, size_t npoints, const void* d_scalars, size_t stride,
                             void* stream) {
     if (!out144) return (int)cudaErrorInvalidValue;
-    return msm_device_impl(out144, d_points, npoints, d_scalars, stride, (cudaStream_t)stream);
+    return msm_device_impl(out144, d_points, npoints, d_scalars, stride, 0, (cudaStream_t)stream);
+}
+
+// `count` MSMs over the SAME resident bases in one pass: one digit/sort keyed by (vector, window, bucket), one set of pair
+// levels, count × nwin window sums, one D2H + one synchronisation, Horner per vector on the host.
+static int msm_batch_impl(void* out144s, const void* d_points, size_t stride, const void* const* d_scalars, const size_t* nscalars,
+                          size_t count, int mont, const void* d_points2, const void* const* d_scalars2, const size_t* nscalars2,
+                          cudaStream_t stream) {
+    if (count == 0) return 0;
+    if (!out144s || !d_scalars || !nscalars || stride < 104 || (stride & 7)) return (int)cudaErrorInvalidValue;
+    // empty vectors commit to the identity; the rest become jobs
+    std::vector<MsmSegment> segs;
+    std::vector<size_t> job_of(count, (size_t)-1);
+    size_t max_n = 0, total_n = 0, max_n2 = 0;
+    uint32_t njobs = 0;
+    for (size_t i = 0; i < count; i++) {
+        const size_t n2 = (d_scalars2 && nscalars2) ? nscalars2[i] : 0;
+        if (nscalars[i] == 0 && n2 == 0) { write_infinity((uint8_t*)out144s + i * 144); continue; }
+        job_of[i] = njobs;
+        if (nscalars[i]) segs.push_back(MsmSegment{d_scalars[i], nscalars[i], 0u, njobs, mont});
+        if (nscalars[i] > max_n) max_n = nscalars[i];
+        if (n2 > max_n2) max_n2 = n2;
+        total_n += nscalars[i] + n2;
+        njobs++;
+    }
+    if (njobs == 0) return 0;
+    if (max_n >= (1ull << 31)) return (int)cudaErrorInvalidValue;
+    // second segments (the blinding polynomials against powers_of_beta_times_gamma_g) index the bases after the first array
+    for (size_t i = 0; i < count; i++) {
+        const size_t n2 = (d_scalars2 && nscalars2) ? nscalars2[i] : 0;
+        if (n2) segs.push_back(MsmSegment{d_scalars2[i], n2, (uint32_t)max_n, (uint32_t)job_of[i], mont});
+    }
+    MsmBases bases[2] = {{d_points, stride, max_n}, {d_points2, stride, max_n2}};
+    const int nbases = max_n2 ? 2 : 1;
+    if (max_n2 && !d_points2) return (int)cudaErrorInvalidValue;
+    size_t job_max = max_n + max_n2;
+    MsmPlan plan = msm_make_plan_batch(job_max ? job_max : 1, total_n);
+    std::vector<uint8_t> outs((size_t)njobs * 144);
+    int rc = msm_jobs_impl(outs.data(), plan, bases, nbases, nullptr, 0, segs.data(), (int)segs.size(), (int)njobs, stream);
+    if (rc != 0) return rc;
+    for (size_t i = 0; i < count; i++) if (job_of[i] != (size_t)-1) memcpy((uint8_t*)out144s + i * 144, outs.data() + job_of[i] * 144, 144);
+    return 0;
+}
+
+int snarkvm_b200_msm_batch_device(void* out144s, const void* d_points, size_t stride, const void* const* d_scalars, const size_t* nscalars,
+                                  size_t count, void* stream) {
+    return msm_batch_impl(out144s, d_points, stride, d_scalars, nscalars, count, 0, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int snarkvm_b200_msm_window_sums_device(void* d_window_sums, const void* d_points, size_t npoints, const void* d_scalars,
                                         size_t stride, void* stream) {
-    if (stride < 104 || (stride & 7) || npoints == 0) return (int)cudaErrorInvalidValue;
-    MsmPlan plan = msm_make_plan(npoints);
-    return msm_window_sums_device((uint32_t*)d_window_sums, plan, d_points, stride, d_scalars, npoints, (cudaStream_t)stream);
+    return snarkvm_b200_msm_window_sums_plan_device(d_window_sums, nullptr, npoints, d_points, npoints, d_scalars, stride, stream);
+}
+
+// Window sums under the plan of `plan_npoints` (every rank of a sharded MSM passes the SAME plan_npoints — the largest shard —
+// so all ranks use one window size whatever their own shard length; an empty shard contributes infinity sums).
+// d_flags: device u32 (zeroed here) that gets bit 0 set if a scalar has bits 253..255 set, or NULL.
+int snarkvm_b200_msm_window_sums_plan_device(void* d_window_sums, uint32_t* d_flags, size_t plan_npoints, const void* d_points,
+                                             size_t npoints, const void* d_scalars, size_t stride, void* stream_v) {
+    if (!d_window_sums || stride < 104 || (stride & 7) || plan_npoints == 0 || npoints > plan_npoints) return (int)cudaErrorInvalidValue;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    MsmPlan plan = msm_make_plan(plan_npoints);
+    uint32_t* own_flags = nullptr;
+    int rc = 0;
+    if (!d_flags) { rc = (int)pool_alloc(&own_flags, 256, stream); if (rc) return rc; d_flags = own_flags; }
+    rc = (int)cudaMemsetAsync(d_flags, 0, 4, stream);
+    if (rc == 0 && npoints == 0) rc = (int)cudaMemsetAsync(d_window_sums, 0, (size_t)plan.nwin * 192, stream);     // XYZZ infinity = zeros
+    else if (rc == 0) rc = msm_window_sums_device((uint32_t*)d_window_sums, d_flags, plan, d_points, stride, d_scalars, npoints, stream);
+    if (own_flags) cudaFreeAsync(own_flags, stream);
+    return rc;
+}
+
+// Host-buffer form of the sharded building block: uploads this rank's shard (point ranges overlapped with the kernels of the
+// previous range, pageable sources staged through pinned buffers) and leaves its window sums under the plan of `plan_npoints`
+// in HBM — nothing is synchronised, so the caller can enqueue its collective right behind it.
+int snarkvm_b200_msm_window_sums_host(void* d_window_sums, uint32_t* d_flags, size_t plan_npoints, const void* h_points, size_t npoints,
+                                      const void* h_scalars, size_t stride, void* stream_v) {
+    if (!d_window_sums || stride < 104 || (stride & 7) || plan_npoints == 0 || npoints > plan_npoints) return (int)cudaErrorInvalidValue;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    MsmPlan plan = msm_make_plan(plan_npoints);
+    uint32_t* own_flags = nullptr;
+    int rc = 0;
+    if (!d_flags) { rc = (int)pool_alloc(&own_flags, 256, stream); if (rc) return rc; d_flags = own_flags; }
+    rc = (int)cudaMemsetAsync(d_flags, 0, 4, stream);
+    if (npoints == 0) {
+        if (rc == 0) rc = (int)cudaMemsetAsync(d_window_sums, 0, (size_t)plan.nwin * 192, stream);
+        if (own_flags) cudaFreeAsync(own_flags, stream);
+        return rc;
+    }
+    if (!h_points || !h_scalars) { if (own_flags) cudaFreeAsync(own_flags, stream); return (int)cudaErrorInvalidValue; }
+    std::vector<size_t> bounds = msm_ranges(npoints);
+    const int chunks = (int)bounds.size() - 1;
+    const bool pin_s = host_is_pinned(h_scalars), pin_p = host_is_pinned(h_points);
+    cudaStream_t copy = nullptr;
+    void *d_points = nullptr, *d_scalars = nullptr;
+    uint32_t* d_parts = nullptr;
+    std::vector<cudaEvent_t> ev((size_t)chunks + 1, nullptr);
+    if (rc == 0) rc = thread_copy_stream(&copy);
+    if (rc == 0) rc = (int)pool_alloc(&d_points, npoints * stride, stream);
+    if (rc == 0) rc = (int)pool_alloc(&d_scalars, npoints * 32, stream);
+    if (rc == 0 && chunks > 1) rc = (int)pool_alloc(&d_parts, (size_t)chunks * plan.nwin * 192, stream);
+    for (auto& e : ev) if (rc == 0) rc = (int)cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (rc == 0) rc = (int)cudaEventRecord(ev[chunks], stream);
+    if (rc == 0) rc = (int)cudaStreamWaitEvent(copy, ev[chunks], 0);
+    for (int k = 0; k < chunks && rc == 0; k++) {
+        const size_t i0 = bounds[k], cn = bounds[k + 1] - i0;
+        rc = upload((uint8_t*)d_scalars + i0 * 32, (const uint8_t*)h_scalars + i0 * 32, cn * 32, copy, pin_s);
+        if (rc == 0) rc = upload((uint8_t*)d_points + i0 * stride, (const uint8_t*)h_points + i0 * stride, cn * stride, copy, pin_p);
+        if (rc == 0) rc = (int)cudaEventRecord(ev[k], copy);
+        if (rc == 0) rc = (int)cudaStreamWaitEvent(stream, ev[k], 0);
+        uint32_t* dst = chunks > 1 ? d_parts + (size_t)k * plan.nwin * 48 : (uint32_t*)d_window_sums;
+        if (rc == 0) rc = msm_window_sums_device(dst, d_flags, plan, (const uint8_t*)d_points + i0 * stride, stride,
+                                                 (const uint8_t*)d_scalars + i0 * 32, cn, stream);
+    }
+    if (rc == 0 && chunks > 1) rc = xyzz_sum_ranks_device((uint32_t*)d_window_sums, d_parts, chunks, plan.nwin, stream);
+    if (rc != 0 && copy) cudaStreamSynchronize(copy);              // a failed call must not leave copies writing into freed buffers
+    if (d_parts) cudaFreeAsync(d_parts, stream);
+    if (d_points) cudaFreeAsync(d_points, stream);
+    if (d_scalars) cudaFreeAsync(d_scalars, stream);
+    if (own_flags) cudaFreeAsync(own_flags, stream);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    return rc;
 }
 
 int snarkvm_b200_xyzz_sum_ranks_device(void* d_out, const void* d_in, int nranks, int count, void* stream) {
@@ -378,23 +697,20 @@ int snarkvm_b200_msm_finish(void* out144, const void* h_window_sums, int nwin, i
     return 0;
 }
 
+int snarkvm_b200_msm_scratch_stats(size_t* limit_bytes, size_t* in_use_bytes, size_t* peak_bytes) {
+    return msm_scratch_stats(limit_bytes, in_use_bytes, peak_bytes);
+}
+int snarkvm_b200_msm_set_scratch_limit(size_t limit_bytes) { return msm_set_scratch_limit(limit_bytes); }
+
+// KZG10::commit core: the Montgomery → canonical conversion (to_bigint, kzg10/mod.rs:469-474) happens inside the digit kernel
 int snarkvm_b200_kzg_commit_device(void* out144, const void* d_powers, size_t stride, const void* d_coeffs_mont,
                                    size_t ncoeffs, void* stream_v) {
     if (!out144) return (int)cudaErrorInvalidValue;
-    if (ncoeffs == 0) { write_infinity(out144); return 0; }
-    cudaStream_t stream = (cudaStream_t)stream_v;
-    void* d_plain = nullptr;
-    int rc = (int)cudaMallocAsync(&d_plain, ncoeffs * 32, stream);
-    if (rc == 0) rc = fr_from_mont_device(d_plain, d_coeffs_mont, ncoeffs, stream);
-    if (rc == 0) rc = msm_device_impl(out144, d_powers, ncoeffs, d_plain, stride, stream);
-    if (d_plain) cudaFreeAsync(d_plain, stream);
-    return rc;
+    return msm_device_impl(out144, d_powers, ncoeffs, d_coeffs_mont, stride, 1, (cudaStream_t)stream_v);
 }
 
 // Precomputed tables for a fixed base set (an SRS): handle = {table, n, plan}.  One-time cost: (nwin−1)·c doublings and
 // nwin−1 inversions per point; memory npoints·nwin·128 B.
-struct PrecomputedBases { uint32_t* table; size_t n; MsmPlan plan; int device; };
-
 int snarkvm_b200_msm_precompute_device(void** handle_out, const void* d_points, size_t npoints, size_t stride, void* stream_v) {
     if (!handle_out || !d_points || npoints == 0 || stride < 104 || (stride & 7)) return (int)cudaErrorInvalidValue;
     cudaStream_t stream = (cudaStream_t)stream_v;
@@ -430,66 +746,69 @@ int snarkvm_b200_msm_precomputed_info(const void* handle, size_t* npoints, int* 
     return 0;
 }
 
-int snarkvm_b200_msm_precomputed_device(void* out144, const void* handle, const void* d_scalars, size_t nscalars, void* stream_v) {
+static int msm_precomputed_impl(void* out144, const void* handle, const void* d_scalars, size_t nscalars, int mont, cudaStream_t stream) {
     if (!out144 || !handle) return (int)cudaErrorInvalidValue;
     const PrecomputedBases* h = (const PrecomputedBases*)handle;
     if (nscalars > h->n) return (int)cudaErrorInvalidValue;
     if (nscalars == 0) { write_infinity(out144); return 0; }
     if (!d_scalars) return (int)cudaErrorInvalidValue;
-    cudaStream_t stream = (cudaStream_t)stream_v;
-    uint32_t* d_sum = nullptr;
-    cudaError_t e = cudaMallocAsync(&d_sum, 192, stream);
-    if (e != cudaSuccess) return (int)e;
-    int rc = msm_precomputed_sum_device(d_sum, h->plan, h->table, h->n, d_scalars, nscalars, stream);
-    host::Xyzz sum;
-    if (rc == 0) rc = (int)cudaMemcpyAsync(&sum, d_sum, 192, cudaMemcpyDeviceToHost, stream);
-    cudaFreeAsync(d_sum, stream);
-    if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
-    if (rc != 0) return rc;
-    host::xyzz_to_normalised_projective(sum, (uint64_t*)out144);
-    return 0;
+    MsmSegment sg{d_scalars, nscalars, 0u, 0u, mont};
+    return msm_jobs_impl(out144, h->plan, nullptr, 0, h->table, h->n, &sg, 1, 1, stream);
 }
-
+int snarkvm_b200_msm_precomputed_device(void* out144, const void* handle, const void* d_scalars, size_t nscalars, void* stream_v) {
+    return msm_precomputed_impl(out144, handle, d_scalars, nscalars, 0, (cudaStream_t)stream_v);
+}
 int snarkvm_b200_kzg_commit_precomputed_device(void* out144, const void* handle, const void* d_coeffs_mont, size_t ncoeffs, void* stream_v) {
-    if (!out144 || !handle) return (int)cudaErrorInvalidValue;
-    if (ncoeffs == 0) { write_infinity(out144); return 0; }
-    cudaStream_t stream = (cudaStream_t)stream_v;
-    void* d_plain = nullptr;
-    int rc = (int)cudaMallocAsync(&d_plain, ncoeffs * 32, stream);
-    if (rc == 0) rc = fr_from_mont_device(d_plain, d_coeffs_mont, ncoeffs, stream);
-    if (rc == 0) rc = snarkvm_b200_msm_precomputed_device(out144, handle, d_plain, ncoeffs, stream_v);
-    if (d_plain) cudaFreeAsync(d_plain, stream);
-    return rc;
+    return msm_precomputed_impl(out144, handle, d_coeffs_mont, ncoeffs, 1, (cudaStream_t)stream_v);
+}
+// all commitments of a round over the tables of the resident powers: one pass, one bucket set per polynomial
+int snarkvm_b200_kzg_commit_batch_precomputed_device(void* out144s, const void* handle, const void* const* d_coeffs_mont, const size_t* ncoeffs,
+                                                     size_t count, void* stream_v) {
+    if (count == 0) return 0;
+    if (!out144s || !handle || !d_coeffs_mont || !ncoeffs) return (int)cudaErrorInvalidValue;
+    const PrecomputedBases* h = (const PrecomputedBases*)handle;
+    std::vector<MsmSegment> segs;
+    std::vector<size_t> job_of(count, (size_t)-1);
+    uint32_t njobs = 0;
+    for (size_t i = 0; i < count; i++) {
+        if (ncoeffs[i] > h->n) return (int)cudaErrorInvalidValue;
+        if (ncoeffs[i] == 0) { write_infinity((uint8_t*)out144s + i * 144); continue; }
+        job_of[i] = njobs;
+        segs.push_back(MsmSegment{d_coeffs_mont[i], ncoeffs[i], 0u, njobs++, 1});
+    }
+    if (njobs == 0) return 0;
+    std::vector<uint8_t> outs((size_t)njobs * 144);
+    int rc = msm_jobs_impl(outs.data(), h->plan, nullptr, 0, h->table, h->n, segs.data(), (int)segs.size(), (int)njobs, (cudaStream_t)stream_v);
+    if (rc != 0) return rc;
+    for (size_t i = 0; i < count; i++) if (job_of[i] != (size_t)-1) memcpy((uint8_t*)out144s + i * 144, outs.data() + job_of[i] * 144, 144);
+    return 0;
 }
 
 // KZG10::commit with a hiding bound (polycommit/kzg10/mod.rs:98-156): commitment to the plaintext polynomial against
 // powers_of_beta_g plus the commitment to the blinding polynomial against powers_of_beta_times_gamma_g.  The caller samples the
 // blinding polynomial (KZGRandomness::rand, :129-140) and passes its Montgomery coefficients; nblinding = 0 is the non-hiding
 // commit.  Zero coefficients contribute nothing, so skip_leading_zeros_and_convert_to_bigints (:455-467) needs no special path.
+// Both MSMs run as ONE pass: the blinding terms are a second scalar segment of the same job whose digits point at the gamma
+// powers appended to the dense base array, so they land in the same buckets and the sum comes out of one Horner fold.
 int snarkvm_b200_kzg_commit_hiding_device(void* out144, const void* d_powers, size_t stride, const void* d_coeffs_mont, size_t ncoeffs,
                                           const void* d_gamma_powers, const void* d_blinding_mont, size_t nblinding, void* stream) {
     if (!out144) return (int)cudaErrorInvalidValue;
-    uint64_t a[18], b[18];
-    int rc = snarkvm_b200_kzg_commit_device(a, d_powers, stride, d_coeffs_mont, ncoeffs, stream);
-    if (rc == 0) rc = snarkvm_b200_kzg_commit_device(b, d_gamma_powers, stride, d_blinding_mont, nblinding, stream);
-    if (rc != 0) return rc;
-    host::Xyzz sum = host::xyzz_from_projective(a);
-    host::xyzz_add(sum, host::xyzz_from_projective(b));
-    host::xyzz_to_normalised_projective(sum, (uint64_t*)out144);
-    return 0;
+    const void* c1[1] = {d_coeffs_mont};
+    const void* c2[1] = {d_blinding_mont};
+    return msm_batch_impl(out144, d_powers, stride, c1, &ncoeffs, 1, 1, d_gamma_powers, c2, &nblinding, (cudaStream_t)stream);
 }
 
-// All commitments of one prover round share powers_of_beta_g (sonic_pc/mod.rs:177-257): count polynomials, one call, the
-// bases stay where they are.  out144s: count × 144 B of HOST memory.
+// All commitments of one prover round share powers_of_beta_g (sonic_pc/mod.rs:177-257): count polynomials, ONE pass over the
+// resident bases.  out144s: count × 144 B of HOST memory.
 int snarkvm_b200_kzg_commit_batch_device(void* out144s, const void* d_powers, size_t stride, const void* const* d_coeffs_mont,
                                          const size_t* ncoeffs, size_t count, void* stream) {
-    if (count == 0) return 0;
-    if (!out144s || !d_coeffs_mont || !ncoeffs) return (int)cudaErrorInvalidValue;
-    for (size_t i = 0; i < count; i++) {
-        int rc = snarkvm_b200_kzg_commit_device((uint8_t*)out144s + i * 144, d_powers, stride, d_coeffs_mont[i], ncoeffs[i], stream);
-        if (rc != 0) return rc;
-    }
-    return 0;
+    return msm_batch_impl(out144s, d_powers, stride, d_coeffs_mont, ncoeffs, count, 1, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+// ... with hiding: polynomial i also gets Σ blinding_i[j]·gamma_powers[j] (nblinding[i] may be 0)
+int snarkvm_b200_kzg_commit_batch_hiding_device(void* out144s, const void* d_powers, size_t stride, const void* const* d_coeffs_mont,
+                                                const size_t* ncoeffs, const void* d_gamma_powers, const void* const* d_blinding_mont,
+                                                const size_t* nblinding, size_t count, void* stream) {
+    return msm_batch_impl(out144s, d_powers, stride, d_coeffs_mont, ncoeffs, count, 1, d_gamma_powers, d_blinding_mont, nblinding, (cudaStream_t)stream);
 }
 
 int snarkvm_b200_g1_ntt_device(void* d_out, size_t out_stride, const void* d_in, size_t in_stride, uint32_t lg, int direction, void* stream) {
@@ -535,46 +854,50 @@ int snarkvm_b200_srs_decode_device(void* d_out, size_t stride, const void* d_in9
 
 int snarkvm_b200_register_bases(const void* host_points, size_t npoints, size_t stride) {
     if (!host_points || npoints == 0 || stride < 104 || (stride & 7)) return (int)cudaErrorInvalidValue;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
+    auto rb = std::make_shared<ResidentBases>();
+    cudaError_t e = cudaGetDevice(&rb->device);
     if (e != cudaSuccess) return (int)e;
-    void* d = nullptr;
-    if ((e = cudaMalloc(&d, npoints * stride)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemcpy(d, host_points, npoints * stride, cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d); return (int)e; }
+    if ((e = cudaMalloc(&rb->d_ptr, npoints * stride)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemcpy(rb->d_ptr, host_points, npoints * stride, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+    rb->npoints = npoints; rb->stride = stride;
+    memcpy(rb->head, host_points, 104);
+    memcpy(rb->tail, (const uint8_t*)host_points + (npoints - 1) * stride, 104);
     std::lock_guard<std::mutex> lock(g_bases_mu);
-    auto it = g_bases.find(host_points);
-    if (it != g_bases.end()) { cudaFree(it->second.d_ptr); if (it->second.tables) snarkvm_b200_msm_precomputed_free(it->second.tables); g_bases.erase(it); }
-    g_bases[host_points] = ResidentBases{d, npoints, stride, dev, nullptr};
+    g_bases[host_points] = rb;                                  // a previous registration of this address is released by its last user
     return 0;
 }
 int snarkvm_b200_unregister_bases(const void* host_points) {
-    std::lock_guard<std::mutex> lock(g_bases_mu);
-    auto it = g_bases.find(host_points);
-    if (it == g_bases.end()) return (int)cudaErrorInvalidValue;
-    cudaFree(it->second.d_ptr);
-    if (it->second.tables) snarkvm_b200_msm_precomputed_free(it->second.tables);
-    g_bases.erase(it);
-    return 0;
+    std::shared_ptr<ResidentBases> old;
+    {
+        std::lock_guard<std::mutex> lock(g_bases_mu);
+        auto it = g_bases.find(host_points);
+        if (it == g_bases.end()) return (int)cudaErrorInvalidValue;
+        old = it->second;
+        g_bases.erase(it);
+    }
+    return 0;                                                    // `old` frees the device memory here unless a call still holds it
 }
 // register + build the fixed-base tables (snarkvm_b200_msm_precompute_device) from the uploaded copy: later snarkvm_msm calls
 // on this slice run over the tables (one bucket set, wider windows).  Costs npoints·nwin·128 B of HBM and seconds of set-up.
 int snarkvm_b200_register_bases_precomputed(const void* host_points, size_t npoints, size_t stride) {
     int rc = snarkvm_b200_register_bases(host_points, npoints, stride);
     if (rc != 0) return rc;
-    void* d = nullptr;
+    std::shared_ptr<ResidentBases> rb;
     {
         std::lock_guard<std::mutex> lock(g_bases_mu);
-        d = g_bases[host_points].d_ptr;
+        auto it = g_bases.find(host_points);
+        if (it == g_bases.end()) return (int)cudaErrorInvalidValue;
+        rb = it->second;
     }
     cudaStream_t stream;
     if ((rc = thread_stream(&stream)) != 0) return rc;
     void* tables = nullptr;
-    rc = snarkvm_b200_msm_precompute_device(&tables, d, npoints, stride, stream);
+    rc = snarkvm_b200_msm_precompute_device(&tables, rb->d_ptr, npoints, stride, stream);
     if (rc != 0) { snarkvm_b200_unregister_bases(host_points); return rc; }
-    std::lock_guard<std::mutex> lock(g_bases_mu);
-    auto it = g_bases.find(host_points);
-    if (it == g_bases.end() || it->second.d_ptr != d) { snarkvm_b200_msm_precomputed_free(tables); return (int)cudaErrorInvalidValue; }   // raced with unregister
-    it->second.tables = tables;
+    // the entry a concurrent call may already hold just gains its tables (atomic pointer); both forms stay valid until the
+    // last holder lets go
+    PrecomputedBases* expected = nullptr;
+    if (!rb->tables.compare_exchange_strong(expected, (PrecomputedBases*)tables)) { snarkvm_b200_msm_precomputed_free(tables); }
     return 0;
 }
 

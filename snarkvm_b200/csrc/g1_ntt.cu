@@ -77,13 +77,12 @@ __global__ void __launch_bounds__(32) k_g1_ntt_finish(const uint32_t* __restrict
 int g1_ntt_device(void* d_out, size_t out_stride, const void* d_in, size_t in_stride, uint32_t lg, int direction, cudaStream_t stream) {
     if (!d_out || !d_in || lg > 26 || in_stride < 104 || (in_stride & 7) || out_stride < 104 || (out_stride & 7) || direction < 0 || direction > 1)
         return (int)cudaErrorInvalidValue;
-    ensure_pool_configured();
     const size_t n = (size_t)1 << lg;
     const void* tw = nullptr;
     int lgN = 0, rc = 0;
     if (lg > 0 && (rc = ntt_get_twiddles((int)lg, &tw, &lgN)) != 0) return rc;
     uint32_t* X = nullptr;
-    cudaError_t e = cudaMallocAsync(&X, n * XYZZ_WORDS * 4, stream);
+    cudaError_t e = pool_alloc(&X, n * XYZZ_WORDS * 4, stream);
     if (e != cudaSuccess) return (int)e;
     k_g1_to_xyzz<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>((const uint8_t*)d_in, in_stride, n, X);
     count_launch();

@@ -2,6 +2,7 @@
 #include "msm.cuh"
 
 #include <atomic>
+#include <condition_variable>
 #include <memory>
 #include <mutex>
 #include <utility>
@@ -18,19 +19,6 @@ namespace b200 {
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n); }
-
-void ensure_pool_configured() {
-    static std::once_flag once[64];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return;
-    std::call_once(once[dev & 63], [dev] {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            uint64_t thr = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-    });
-}
 
 static std::atomic<bool> g_prof{false};
 static std::mutex g_prof_mu;
@@ -99,17 +87,40 @@ MsmPlan msm_make_plan(size_t npoints) {
     return p;
 }
 
+// Plan for `njobs` sums sharing one base set in one pass: the window size follows the LARGEST job (bucket load), the
+// number of pair levels follows the TOTAL work (a level is worth it while it fills the machine) as long as the buckets
+// of the largest job still hold a few points after the halvings.
+MsmPlan msm_make_plan_batch(size_t max_n, size_t total_n) {
+    MsmPlan p = msm_make_plan(max_n);
+    if (total_n > max_n) {
+        int lgt = ceil_log2(total_n < 2 ? 2 : total_n);
+        int levels = lgt >= 21 ? 4 : lgt == 20 ? 1 : 0;
+        while (levels > 0 && ((max_n >> (p.c - 1)) >> levels) < 2) levels--;
+        if (const char* e = getenv("SNARKVM_B200_MSM_LEVELS")) { int v = atoi(e); if (v >= 0 && v <= 16) levels = v; }
+        if (levels > p.levels) p.levels = levels;
+        size_t cap = total_n * (size_t)p.nwin / 300000 + 1;
+        if (cap < 16) cap = 16;
+        if (const char* e = getenv("SNARKVM_B200_MSM_CAP")) { long v = atol(e); if (v >= 1) cap = (size_t)v; }
+        p.cap = (uint32_t)cap;
+    }
+    return p;
+}
+
 // ---------------------------------------------------------------------------
 // Signed-digit recoding of a canonical 253-bit scalar (8 little-endian u32 words).
 // digit_w ∈ [-2^(c-1), 2^(c-1)]; returns magnitude and sign for window w given the
 // running carry (sequential over w).
 // ---------------------------------------------------------------------------
 // flat != 0 (precomputed tables 2^{c·w}·P_i): every window feeds the SAME bucket set and the entry names record
-// w·n + i of the table instead of point i.
-template <bool SCATTER>
+// w·flat + i of the table instead of point i.  slot_base: first counter of this job's bucket sets; index_base: position of
+// this scalar vector's first point in the call's dense base array.  MONT: the scalars are Montgomery Fr (polynomial
+// coefficients) and are converted here (to_bigint, kzg10/mod.rs:469-474).  Scalars with bits 253..255 set are outside
+// what nwin windows cover: they raise bit 0 of *flags and the caller returns an error instead of a wrong point.
+template <bool SCATTER, bool MONT>
 __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ scalars, size_t n, int c, int nwin,
                                                 uint32_t nbuckets, uint32_t* __restrict__ counters /* hist or cursors */,
-                                                uint32_t* __restrict__ sorted, size_t flat /* 0, or the table's points per window */) {
+                                                uint32_t* __restrict__ sorted, size_t flat /* 0, or the table's points per window */,
+                                                uint32_t slot_base, uint32_t index_base, uint32_t* __restrict__ flags) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -118,6 +129,15 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
         uint4 a = __ldg(q), b = __ldg(q + 1);
         s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
     }
+    if (MONT) {
+        Fr x;
+#pragma unroll
+        for (int k = 0; k < 8; k++) x.v[k] = s[k];
+        x = x.from_mont();
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = x.v[k];
+    }
+    if (!SCATTER && (s[7] >> 29)) atomicOr(flags, 1u);
     const uint32_t half = 1u << (c - 1);
     uint32_t carry = 0;
     for (int w = 0; w < nwin; w++) {
@@ -132,10 +152,10 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
         uint32_t mag = neg ? (1u << c) - raw : raw;
         carry = neg;
         if (mag != 0u) {
-            uint32_t slot = (flat ? 0u : (uint32_t)w * nbuckets) + (mag - 1u);
+            uint32_t slot = slot_base + (flat ? 0u : (uint32_t)w * nbuckets) + (mag - 1u);
             if (SCATTER) {
                 uint32_t pos = atomicAdd(&counters[slot], 1u);
-                sorted[pos] = (uint32_t)(flat ? (size_t)w * flat + i : i) | (neg << 31);
+                sorted[pos] = (uint32_t)(flat ? (size_t)w * flat + i : (size_t)index_base + i) | (neg << 31);
             } else {
                 atomicAdd(&counters[slot], 1u);
             }
@@ -148,6 +168,15 @@ __global__ void k_items_per_bucket(const uint32_t* __restrict__ hist, uint32_t* 
     if (i < total_buckets) items[i] = (hist[i] + cap - 1u) / cap;
 }
 
+// A dense base record: x, y (Montgomery) in one 128-byte line, infinity encoded as (0, 0) — written by k_densify_bases
+// (per call) or k_precompute_tables (per SRS).
+FF_DEV AffinePoint load_record(const uint32_t* __restrict__ records, uint32_t idx) {
+    const uint32_t* p = records + (size_t)idx * 32;
+    AffinePoint a;
+    a.x = Fq::load_ldg(p); a.y = Fq::load_ldg(p + 12);
+    a.inf = a.x.is_zero() && a.y.is_zero();
+    return a;
+}
 // One thread per work item (a run of ≤ cap sorted entries of one bucket): XYZZ mixed additions
 // of gathered affine bases.  partial[item] receives the item's sum.
 // 128-thread CTAs, 4 per SM (≤ 128 registers/thread, a few hundred bytes of spill): measured on B200 at
@@ -157,7 +186,7 @@ __global__ void k_items_per_bucket(const uint32_t* __restrict__ hist, uint32_t* 
 #define MSM_ACC_THREADS 128
 #define MSM_ACC_MINBLOCKS 4
 #endif
-__global__ void __launch_bounds__(MSM_ACC_THREADS, MSM_ACC_MINBLOCKS) k_bucket_accumulate(const uint8_t* __restrict__ points, size_t stride,
+__global__ void __launch_bounds__(MSM_ACC_THREADS, MSM_ACC_MINBLOCKS) k_bucket_accumulate(const uint32_t* __restrict__ records /* 128-byte dense bases or table */,
                                                             const uint32_t* __restrict__ sorted,
                                                             const uint32_t* __restrict__ bucket_start /* [TB+1] */,
                                                             const uint32_t* __restrict__ item_start /* [TB+1] */,
@@ -180,11 +209,11 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, MSM_ACC_MINBLOCKS) k_bucket_a
     XYZZ acc = XYZZ::infinity();
     // software pipeline: fetch entry k+1 while adding entry k
     uint32_t e = sorted[s0];
-    AffinePoint p = load_affine(points, stride, e & 0x7fffffffu);
+    AffinePoint p = load_record(records, e & 0x7fffffffu);
     for (uint32_t k = s0; k < s1; k++) {
         uint32_t e_cur = e;
         AffinePoint p_cur = p;
-        if (k + 1 < s1) { e = sorted[k + 1]; p = load_affine(points, stride, e & 0x7fffffffu); }
+        if (k + 1 < s1) { e = sorted[k + 1]; p = load_record(records, e & 0x7fffffffu); }
         acc.add_affine(p_cur, (e_cur >> 31) != 0u);
     }
     acc.store(partial + (size_t)t * XYZZ_WORDS);
@@ -398,6 +427,222 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair_level(const uint32_t* 
     }
 }
 
+
+// =================================================================================================
+// Pair level, second design (round 2): warp-interleaved outputs + a shared-memory operand ring.
+//
+// v1 above gives every THREAD a run of T consecutive outputs: the 32 lanes of a load instruction then touch 32
+// different DRAM pages / L1 lines (sorted[], prefix[], the level's dense input), every record is fetched with the
+// multiplier idle behind a 4-deep dependent chain (off_out → off_in → sorted → record), and ncu shows 2.5–4.3
+// long-scoreboard stall cycles per issued instruction at 65–72 % of the multiplier pipe.  Here a WARP owns 32·T
+// consecutive outputs and lane l takes outputs W0 + 32·j + l, j < T — any partition works for Montgomery's trick —
+// so sorted[], prefix[] and the dense inputs/outputs of a step are contiguous across the warp, and the operands of
+// step j+1 are already on their way into shared memory (cp.async / LDGSTS, 16-byte granules into a per-warp
+// [stage][chunk][lane] ring, conflict-free for LDS.128) while step j multiplies: the index chain runs two steps
+// ahead (bucket walk + sorted[] entry), the record copies one step ahead, and the multiplier calls read their
+// operands from shared memory when they need them, so nothing but the running inverse is live across a call.
+// Each record still crosses DRAM once per pass (forward: x only; backward: x and y); prefix products go to HBM
+// coalesced (48 B per output) and come back one step late behind the first multiplication of the step.
+// =================================================================================================
+FF_DEV uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+FF_DEV void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+FF_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+FF_DEV void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+FF_DEV void cp_async_wait_0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+static constexpr int RING_CHUNKS = 12;                       // x1 y1 x2 y2, three 16-byte chunks each
+static constexpr int RING_STAGE_U4 = RING_CHUNKS * 32;       // uint4 per warp per stage (6 KiB)
+static constexpr int PAIR2_SMEM = PAIR_THREADS * 48 + 4 * 2 * RING_STAGE_U4 * 16;   // shared inversion + 4 warps × 2 stages
+
+FF_DEV Fq ring_fq(const uint4* slot) {                       // slot = &ring[(stage·12 + first chunk)·32 + lane]
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { uint4 t = slot[i * 32]; r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w; }
+    return r;
+}
+
+struct PairDesc {            // one lane's output of one step
+    uint32_t idx;            // position of the first input (in `sorted` at level 0, in dense_in above)
+    uint32_t eP, eQ;         // level 0: sorted entries (point index | sign << 31)
+    uint32_t flags;          // bit 0: output exists, bit 1: it has a second input
+};
+
+template <bool GATHER>
+FF_DEV PairDesc pair_make_desc(int64_t j, uint32_t T, uint32_t W0, uint32_t W1, int lane, uint32_t& b,
+                               const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off_in,
+                               const uint32_t* __restrict__ off_out) {
+    PairDesc d; d.idx = 0; d.eP = 0; d.eQ = 0; d.flags = 0;
+    if (j < 0 || j >= (int64_t)T) return d;
+    const uint64_t o64 = (uint64_t)W0 + 32ull * (uint64_t)j + (uint32_t)lane;
+    if (o64 >= W1) return d;
+    const uint32_t o = (uint32_t)o64;
+    while (o >= __ldg(off_out + b + 1)) b++;
+    while (o < __ldg(off_out + b)) b--;
+    const uint32_t i = o - __ldg(off_out + b), base_in = __ldg(off_in + b), cnt = __ldg(off_in + b + 1) - base_in;
+    d.idx = base_in + 2u * i;
+    d.flags = 1u | ((2u * i + 1u < cnt) ? 2u : 0u);
+    if (GATHER) {
+        d.eP = __ldg(sorted + d.idx);
+        if (d.flags & 2u) d.eQ = __ldg(sorted + d.idx + 1);
+    }
+    return d;
+}
+template <bool GATHER>
+FF_DEV const uint32_t* pair_src(const PairDesc& d, int which, const uint32_t* __restrict__ dense_bases, const uint32_t* __restrict__ dense_in) {
+    if (GATHER) return dense_bases + (size_t)((which ? d.eQ : d.eP) & 0x7fffffffu) * BASE_WORDS;
+    return dense_in + (size_t)(d.idx + (uint32_t)which) * DENSE_WORDS;
+}
+// copies of step operands into ring stage `st` (forward: x1, x2; backward: all four coordinates)
+template <bool GATHER, bool FULL>
+FF_DEV void pair_issue(const PairDesc& d, uint4* ring, int st, int lane, const uint32_t* __restrict__ dense_bases,
+                       const uint32_t* __restrict__ dense_in) {
+    if (d.flags & 1u) {
+        const uint32_t dst = smem_addr_u32(ring + (size_t)st * RING_STAGE_U4 + lane);
+        const uint32_t* p = pair_src<GATHER>(d, 0, dense_bases, dense_in);
+#pragma unroll
+        for (int k = 0; k < (FULL ? 6 : 3); k++) cp_async16(dst + (uint32_t)k * 512u, p + 4 * k);
+        if (d.flags & 2u) {
+            const uint32_t* q = pair_src<GATHER>(d, 1, dense_bases, dense_in);
+#pragma unroll
+            for (int k = 0; k < (FULL ? 6 : 3); k++) cp_async16(dst + (uint32_t)(6 + k) * 512u, q + 4 * k);
+        }
+    }
+    cp_async_commit();
+}
+// full classification of one pair from global memory (rare path of the forward pass: equal x, or an x that is 0)
+template <bool GATHER>
+FF_DEV int pair_classify_global(const PairDesc& d, const uint32_t* __restrict__ dense_bases, const uint32_t* __restrict__ dense_in, Fq& den) {
+    DensePoint P = load_dense(pair_src<GATHER>(d, 0, dense_bases, dense_in));
+    DensePoint Q = load_dense(pair_src<GATHER>(d, 1, dense_bases, dense_in));
+    if (GATHER) { if ((d.eP >> 31) && !P.inf) P.y = P.y.neg(); if ((d.eQ >> 31) && !Q.inf) Q.y = Q.y.neg(); }
+    return classify_pair(P, Q, true, den);
+}
+
+template <bool GATHER>
+__global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair_level2(const uint32_t* __restrict__ dense_bases,
+                                                         const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ dense_in,
+                                                         const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out,
+                                                         uint32_t total_buckets, uint32_t T, uint32_t* __restrict__ prefix,
+                                                         uint32_t* __restrict__ dense_out) {
+    extern __shared__ uint4 pair2_smem[];
+    uint32_t* sh_inv = reinterpret_cast<uint32_t*>(pair2_smem);                       // 128 × 48 B
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* ring = pair2_smem + PAIR_THREADS * 3 + (size_t)warp * 2 * RING_STAGE_U4;    // this warp's two stages
+    const uint32_t total = __ldg(off_out + total_buckets);
+    const uint64_t w0_64 = ((uint64_t)blockIdx.x * (PAIR_THREADS / 32) + (uint32_t)warp) * 32ull * T;
+    const uint32_t W0 = w0_64 < total ? (uint32_t)w0_64 : total;
+    const uint32_t W1 = (w0_64 + 32ull * T < total) ? (uint32_t)(w0_64 + 32ull * T) : total;
+    uint32_t b = 0;
+    if ((uint64_t)W0 + (uint32_t)lane < W1) {                                          // bucket of this lane's first output
+        const uint32_t o = W0 + (uint32_t)lane;
+        uint32_t lo = 0, hi = total_buckets;
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (__ldg(off_out + mid) <= o) lo = mid; else hi = mid; }
+        b = lo;
+    }
+
+    // ---------------- forward: running product of the denominators ----------------
+    Fq run = Fq::one();
+    {
+        PairDesc cur = pair_make_desc<GATHER>(0, T, W0, W1, lane, b, sorted, off_in, off_out);
+        pair_issue<GATHER, false>(cur, ring, 0, lane, dense_bases, dense_in);
+        PairDesc nxt = pair_make_desc<GATHER>(1, T, W0, W1, lane, b, sorted, off_in, off_out);
+        for (uint32_t j = 0; j < T; j++) {
+            PairDesc nn = pair_make_desc<GATHER>((int64_t)j + 2, T, W0, W1, lane, b, sorted, off_in, off_out);
+            pair_issue<GATHER, false>(nxt, ring, (int)((j + 1) & 1u), lane, dense_bases, dense_in);
+            cp_async_wait_1();
+            Fq d = Fq::one();
+            if (cur.flags & 2u) {
+                const uint4* slot = ring + (size_t)(j & 1u) * RING_STAGE_U4 + lane;
+                Fq x1 = ring_fq(slot), x2 = ring_fq(slot + 6 * 32);
+                if (x1 == x2 || x1.is_zero() || x2.is_zero()) {
+                    Fq den;
+                    if (pair_classify_global<GATHER>(cur, dense_bases, dense_in, den) >= PAIR_ADD) d = den;
+                } else {
+                    d = x2 - x1;
+                }
+            }
+            run = run * d;
+            if (cur.flags & 1u) run.store(prefix + ((size_t)W0 + 32ull * j + (uint32_t)lane) * 12);
+            cur = nxt; nxt = nn;
+        }
+        cp_async_wait_0();
+    }
+    Fq inv = cta_shared_inverse(run, sh_inv);
+    // ---------------- backward: one inverse per pair, then the affine addition ----------------
+    {
+        PairDesc cur = pair_make_desc<GATHER>((int64_t)T - 1, T, W0, W1, lane, b, sorted, off_in, off_out);
+        pair_issue<GATHER, true>(cur, ring, 0, lane, dense_bases, dense_in);
+        PairDesc nxt = pair_make_desc<GATHER>((int64_t)T - 2, T, W0, W1, lane, b, sorted, off_in, off_out);
+        for (uint32_t k = 0; k < T; k++) {
+            const uint32_t j = T - 1 - k;
+            PairDesc nn = pair_make_desc<GATHER>((int64_t)j - 2, T, W0, W1, lane, b, sorted, off_in, off_out);
+            pair_issue<GATHER, true>(nxt, ring, (int)((k + 1) & 1u), lane, dense_bases, dense_in);
+            const size_t o = (size_t)W0 + 32ull * j + (uint32_t)lane;
+            Fq pf = Fq::one();
+            if ((cur.flags & 1u) && j != 0) pf = Fq::load(prefix + (o - 32) * 12);          // behind the first multiplication
+            cp_async_wait_1();
+            const uint4* slot = ring + (size_t)(k & 1u) * RING_STAGE_U4 + lane;
+            // classify (same decisions as the forward pass)
+            int kind = PAIR_COPY1;
+            Fq d = Fq::one(), num = Fq::zero();
+            const bool negP = GATHER && (cur.eP >> 31), negQ = GATHER && (cur.eQ >> 31);
+            if (cur.flags & 2u) {
+                Fq x1 = ring_fq(slot), x2 = ring_fq(slot + 6 * 32);
+                if (x1 == x2 || x1.is_zero() || x2.is_zero()) {
+                    DensePoint P, Q;
+                    P.x = x1; P.y = ring_fq(slot + 3 * 32); P.inf = P.x.is_zero() && P.y.is_zero();
+                    Q.x = x2; Q.y = ring_fq(slot + 9 * 32); Q.inf = Q.x.is_zero() && Q.y.is_zero();
+                    if (negP && !P.inf) P.y = P.y.neg();
+                    if (negQ && !Q.inf) Q.y = Q.y.neg();
+                    Fq den;
+                    kind = classify_pair(P, Q, true, den);
+                    if (kind >= PAIR_ADD) d = den;
+                    if (kind == PAIR_ADD) num = Q.y - P.y;
+                    else if (kind == PAIR_DBL) { Fq xx = P.x.sqr(); num = xx.dbl() + xx; }
+                } else {
+                    kind = PAIR_ADD;
+                    d = x2 - x1;
+                    Fq y1 = ring_fq(slot + 3 * 32), y2 = ring_fq(slot + 9 * 32);
+                    if (negP) y1 = y1.neg();
+                    if (negQ) y2 = y2.neg();
+                    num = y2 - y1;
+                }
+            }
+            Fq inv_next = inv * d;
+            Fq inv_d = (j != 0) ? inv * pf : inv;
+            inv = inv_next;
+            Fq lambda = num * inv_d;
+            Fq x3 = lambda.sqr();
+            {
+                Fq x1 = ring_fq(slot), x2 = (cur.flags & 2u) ? ring_fq(slot + 6 * 32) : x1;
+                x3 = x3 - x1 - x2;
+                Fq t = x1 - x3;
+                Fq y3 = lambda * t;
+                if (cur.flags & 1u) {
+                    DensePoint R;
+                    if (kind >= PAIR_ADD) {
+                        Fq y1 = ring_fq(slot + 3 * 32);
+                        if (negP) y1 = y1.neg();
+                        R.x = x3; R.y = y3 - y1; R.inf = false;
+                    } else if (kind == PAIR_INF) {
+                        R.inf = true; R.x = Fq::zero(); R.y = Fq::zero();
+                    } else {
+                        const int c0 = (kind == PAIR_COPY2) ? 6 : 0;
+                        R.x = ring_fq(slot + c0 * 32); R.y = ring_fq(slot + (c0 + 3) * 32);
+                        R.inf = R.x.is_zero() && R.y.is_zero();
+                        if (((kind == PAIR_COPY2) ? negQ : negP) && !R.inf) R.y = R.y.neg();
+                    }
+                    store_dense(dense_out + o * DENSE_WORDS, R);
+                }
+            }
+            cur = nxt; nxt = nn;
+        }
+        cp_async_wait_0();
+    }
+}
+
 __global__ void k_halve_counts(const uint32_t* __restrict__ off_in, uint32_t* __restrict__ cnt_out, uint32_t total_buckets) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < total_buckets) cnt_out[i] = (off_in[i + 1] - off_in[i] + 1u) >> 1;
@@ -511,112 +756,304 @@ int xyzz_sum_ranks_device(uint32_t* d_out, const uint32_t* d_in, int nranks, int
     return (int)cudaGetLastError();
 }
 
-// table != nullptr: "flat" mode over precomputed tables (record w·table_n + i = 2^{c·w}·P_i): all windows share one bucket
-// set, so the pipeline sees ONE window of npoints·nwin entries and writes a single sum.
-static int msm_core(uint32_t* d_window_sums, const MsmPlan& plan, const void* d_points, size_t stride, const uint32_t* table,
-                    size_t table_n, const void* d_scalars, size_t npoints, cudaStream_t stream) {
-    int rc = 0;
-    ensure_pool_configured();
-    const bool flat = table != nullptr;
-    const uint32_t nwin_red = flat ? 1u : (uint32_t)plan.nwin;    // bucket sets to reduce
-    const uint32_t TB = nwin_red * plan.nbuckets;                 // total buckets
-    const size_t max_entries = npoints * (size_t)plan.nwin;
-    if (npoints == 0 || npoints >= (1ull << 31) || max_entries >= (1ull << 32)) return (int)cudaErrorInvalidValue;
-    if (flat && (table_n * (size_t)plan.nwin >= (1ull << 31) || plan.levels < 1 || npoints > table_n)) return (int)cudaErrorInvalidValue;
-    const int levels = plan.levels;
-    const size_t bucket_cap = flat ? max_entries : npoints;       // most entries a single bucket can hold
+// ---------------------------------------------------------------------------
+// Scratch: one private stream-ordered pool per device (the default pool is left alone) and a byte budget that
+// bounds how much MSM scratch is in flight per device.  The FFI is entered concurrently from many rayon workers
+// (sonic_pc/mod.rs:186-245): without the gate, a burst of large commitments would each take tens of GB and the
+// losers would fail with cudaErrorMemoryAllocation (⇒ silent CPU fallback on the Rust side); with it they queue.
+// ---------------------------------------------------------------------------
+struct DeviceScratch {
+    std::mutex mu;
+    std::condition_variable cv;
+    cudaMemPool_t pool = nullptr;
+    size_t limit = 0, in_use = 0, peak = 0;
+    bool ready = false;
+};
+static DeviceScratch g_scratch[64];
 
-    // Everything after the bucket sort runs per GROUP of whole windows, so the dense scratch of the pair levels
-    // (96 B per point per window) stays inside a budget: 2^24 points → all 15 windows at once (24 GB),
-    // 2^26 points → 3 groups of 6/6/3 windows.
-    size_t budget = (size_t)40 << 30;
+static int scratch_init(DeviceScratch& ds, int dev) {
+    if (ds.ready) return 0;
+    size_t free_b = 0, total_b = 0;
+    cudaError_t e = cudaMemGetInfo(&free_b, &total_b);
+    if (e != cudaSuccess) return (int)e;
+    size_t limit = total_b / 2;                                       // default: half the device
+    if (const char* v = getenv("SNARKVM_B200_SCRATCH_LIMIT_GB")) { long g = atol(v); if (g >= 1) limit = (size_t)g << 30; }
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    if ((e = cudaMemPoolCreate(&ds.pool, &props)) != cudaSuccess) return (int)e;
+    uint64_t thr = limit;                                             // keep up to `limit` cached between calls, not more
+    cudaMemPoolSetAttribute(ds.pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    ds.limit = limit;
+    ds.ready = true;
+    return 0;
+}
+// small, ungated allocations (window sums, NTT scratch, polynomial temporaries) from the same private pool
+int pool_alloc_raw(void** p, size_t bytes, cudaStream_t stream) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    DeviceScratch& ds = g_scratch[dev & 63];
+    {
+        std::lock_guard<std::mutex> lock(ds.mu);
+        int rc = scratch_init(ds, dev);
+        if (rc) return rc;
+    }
+    return (int)cudaMallocFromPoolAsync(p, bytes ? bytes : 16, ds.pool, stream);
+}
+struct ScratchLease { DeviceScratch* ds; size_t bytes; };
+static void CUDART_CB scratch_release_cb(void* p) {
+    ScratchLease* l = (ScratchLease*)p;
+    { std::lock_guard<std::mutex> lock(l->ds->mu); l->ds->in_use -= l->bytes; }
+    l->ds->cv.notify_all();
+    delete l;
+}
+// blocks until `bytes` fit in the device's budget (a request larger than the whole budget runs alone), then allocates
+static int scratch_acquire(void** out, size_t bytes, cudaStream_t stream, DeviceScratch** ds_out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    DeviceScratch& ds = g_scratch[dev & 63];
+    {
+        std::unique_lock<std::mutex> lock(ds.mu);
+        int rc = scratch_init(ds, dev);
+        if (rc) return rc;
+        ds.cv.wait(lock, [&] { return ds.in_use == 0 || ds.in_use + bytes <= ds.limit; });
+        ds.in_use += bytes;
+        if (ds.in_use > ds.peak) ds.peak = ds.in_use;
+    }
+    e = cudaMallocFromPoolAsync(out, bytes, ds.pool, stream);
+    if (e != cudaSuccess) {
+        { std::lock_guard<std::mutex> lock(ds.mu); ds.in_use -= bytes; }
+        ds.cv.notify_all();
+        return (int)e;
+    }
+    *ds_out = &ds;
+    return 0;
+}
+// frees in stream order and returns the bytes to the budget when the stream gets there
+static void scratch_release(void* p, size_t bytes, cudaStream_t stream, DeviceScratch* ds) {
+    cudaFreeAsync(p, stream);
+    ScratchLease* l = new ScratchLease{ds, bytes};
+    if (cudaLaunchHostFunc(stream, scratch_release_cb, l) != cudaSuccess) scratch_release_cb(l);
+}
+int msm_scratch_stats(size_t* limit, size_t* in_use, size_t* peak) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    DeviceScratch& ds = g_scratch[dev & 63];
+    std::lock_guard<std::mutex> lock(ds.mu);
+    if (limit) *limit = ds.limit;
+    if (in_use) *in_use = ds.in_use;
+    if (peak) *peak = ds.peak;
+    return 0;
+}
+
+int msm_set_scratch_limit(size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (bytes == 0) return (int)cudaErrorInvalidValue;
+    DeviceScratch& ds = g_scratch[dev & 63];
+    {
+        std::lock_guard<std::mutex> lock(ds.mu);
+        int rc = scratch_init(ds, dev);
+        if (rc) return rc;
+        ds.limit = bytes;
+        ds.peak = ds.in_use;
+        uint64_t thr = bytes;
+        cudaMemPoolSetAttribute(ds.pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    ds.cv.notify_all();
+    return 0;
+}
+
+struct Arena {
+    uint8_t* base = nullptr;
+    size_t off = 0;
+    template <class T> T* take(size_t count) {
+        T* p = base ? (T*)(base + off) : nullptr;
+        off += (count * sizeof(T) + 255) & ~(size_t)255;
+        return p;
+    }
+};
+
+// The general form: `njobs` independent sums (one per committed polynomial), each fed by one or more scalar segments,
+// over ONE set of resident bases.  All jobs go through one digit/sort pass keyed by (job, window, bucket), one set of pair
+// levels and one reduction; d_window_sums receives njobs × (flat ? 1 : nwin) XYZZ points, job-major.
+// table != nullptr: "flat" mode over precomputed tables (record w·table_n + i = 2^{c·w}·P_i): all windows of a job share
+// one bucket set, so the pipeline sees ONE set of n·nwin entries per job and writes a single sum per job.
+int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, const MsmBases* bases, int nbases,
+             const uint32_t* table, size_t table_n, const MsmSegment* segs, int nsegs, int njobs, cudaStream_t stream) {
+    int rc = 0;
+    const bool flat = table != nullptr;
+    const uint32_t sets_per_job = flat ? 1u : (uint32_t)plan.nwin;   // bucket sets to reduce per job
+    if (njobs < 1 || nsegs < 1 || (!flat && nbases < 1)) return (int)cudaErrorInvalidValue;
+    const uint64_t nsets64 = (uint64_t)njobs * sets_per_job;
+    const uint64_t TB64 = nsets64 * plan.nbuckets;
+    if (TB64 >= (1ull << 31)) return (int)cudaErrorInvalidValue;
+    const uint32_t nsets = (uint32_t)nsets64, TB = (uint32_t)TB64;
+    size_t total_scalars = 0, total_bases = 0;
+    std::vector<size_t> job_n((size_t)njobs, 0);
+    for (int i = 0; i < nbases; i++) {
+        if (bases[i].stride < 104 || (bases[i].stride & 7)) return (int)cudaErrorInvalidValue;
+        total_bases += bases[i].n;
+    }
+    for (int i = 0; i < nsegs; i++) {
+        if (segs[i].job >= (uint32_t)njobs) return (int)cudaErrorInvalidValue;
+        if (flat ? (segs[i].base0 != 0 || segs[i].n > table_n) : ((size_t)segs[i].base0 + segs[i].n > total_bases)) return (int)cudaErrorInvalidValue;
+        total_scalars += segs[i].n;
+        job_n[segs[i].job] += segs[i].n;
+    }
+    size_t max_job_n = 0;
+    for (size_t v : job_n) if (v > max_job_n) max_job_n = v;
+    const size_t max_entries = total_scalars * (size_t)plan.nwin;
+    if (total_scalars == 0 || total_bases >= (1ull << 31) || max_entries >= (1ull << 32)) return (int)cudaErrorInvalidValue;
+    if (flat && table_n * (size_t)plan.nwin >= (1ull << 31)) return (int)cudaErrorInvalidValue;
+    const int levels = plan.levels;
+    const size_t set_cap = flat ? max_job_n * (size_t)plan.nwin : max_job_n;   // most entries one bucket set (or one bucket) can hold
+
+    // Everything after the bucket sort runs per GROUP of whole bucket sets, so the dense scratch of the pair levels
+    // (≈ 100 B per entry) stays inside a budget: 2^24 points → 15 windows in 3 groups of 5, a 2^26-point shard 1–2 windows at a time.
+    size_t budget = (size_t)12 << 30;
     if (const char* e = getenv("SNARKVM_B200_MSM_SCRATCH_GB")) { long v = atol(e); if (v >= 1) budget = (size_t)v << 30; }
-    uint32_t gw = nwin_red;
-    if (levels > 0 && !flat) {
-        size_t per_window = npoints * (size_t)96 + 1;
-        size_t fit = budget / per_window;
+    uint32_t gw = nsets;
+    if (levels > 0) {
+        size_t per_set = set_cap * (size_t)100 + 1;
+        size_t fit = budget / per_set;
         if (fit < 1) fit = 1;
         if (fit < gw) gw = (uint32_t)fit;
     }
     const uint32_t TBg = gw * plan.nbuckets;                      // buckets of the largest group
-    const size_t entries_g = flat ? max_entries : npoints * (size_t)gw;
+    size_t entries_g = set_cap * (size_t)gw;                      // most entries a group can hold
+    if (entries_g > max_entries) entries_g = max_entries;
     const size_t max_items = (size_t)TBg + entries_g / plan.cap + 1;
-
-    uint32_t *hist = nullptr, *bucket_start = nullptr, *cursors = nullptr, *items = nullptr, *item_start = nullptr;
-    uint32_t *sorted = nullptr, *partial = nullptr, *red_a = nullptr, *red_b = nullptr;
-    uint32_t *off_a = nullptr, *off_b = nullptr, *dense_a = nullptr, *dense_b = nullptr, *prefix = nullptr, *dense_bases = nullptr;
-    uint32_t *partial2 = nullptr, *items2 = nullptr;
     const size_t dense_cap_a = entries_g / 2 + TBg + 1, dense_cap_b = entries_g / 4 + 2 * (size_t)TBg + 1;
-    size_t pair_waves = 0;                       // 0 = fewest whole waves with T ≤ 1024 outputs per thread
+
+    size_t pair_waves = 0;                       // 0 = fewest whole waves with T ≤ 1024 outputs per lane
     if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_WAVES")) { long v = atol(e); if (v >= 1) pair_waves = (size_t)v; }
+    bool pair_v1 = false;                        // A/B switch: the round-1 thread-contiguous pair level
+    if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_V1")) pair_v1 = atoi(e) != 0;
     int sm_count = 148;
-    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
-    void* cub_tmp = nullptr;
-    size_t cub_bytes = 0;
+    {
+        static std::once_flag smem_once[64];
+        int dev = 0; cudaGetDevice(&dev);
+        std::call_once(smem_once[dev & 63], [] {
+            cudaFuncSetAttribute(k_pair_level2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR2_SMEM);
+            cudaFuncSetAttribute(k_pair_level2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR2_SMEM);
+        });
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+    }
     // The reduction tail is a chain of dependent point additions per thread (≈ 16 µs each for a lone warp): short chunks
     // and a narrow (8:1) tree keep that chain short — what matters at 2^16–2^20 points, where the tail is 20–50 % of the call.
     const uint32_t chunk = plan.nbuckets < 16u ? plan.nbuckets : 16u;
     const uint32_t tree = 8;
-    const uint32_t chunks_per_window = plan.nbuckets / chunk;
+    const uint32_t chunks_per_set = plan.nbuckets / chunk;
 
-    CUDA_TRY(cudaMallocAsync(&hist, (size_t)(TB + 1) * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&bucket_start, (size_t)(TB + 1) * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&cursors, (size_t)(TB + 1) * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&items, (size_t)(TBg + 1) * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&item_start, (size_t)(TBg + 1) * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&sorted, max_entries * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&partial, max_items * XYZZ_WORDS * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&partial2, ((size_t)TBg + max_items / 32 + 2) * XYZZ_WORDS * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&items2, (size_t)(TBg + 1) * 4, stream));
-    if (levels > 0) {
-        CUDA_TRY(cudaMallocAsync(&off_a, (size_t)(TBg + 1) * 4, stream));
-        CUDA_TRY(cudaMallocAsync(&off_b, (size_t)(TBg + 1) * 4, stream));
-        CUDA_TRY(cudaMallocAsync(&dense_a, dense_cap_a * DENSE_WORDS * 4, stream));
-        if (levels > 1) CUDA_TRY(cudaMallocAsync(&dense_b, dense_cap_b * DENSE_WORDS * 4, stream));
-        CUDA_TRY(cudaMallocAsync(&prefix, dense_cap_a * 12 * 4, stream));
-        if (!flat) CUDA_TRY(cudaMallocAsync(&dense_bases, npoints * (size_t)BASE_WORDS * 4, stream));
-    }
-    CUDA_TRY(cudaMallocAsync(&red_a, (size_t)gw * chunks_per_window * XYZZ_WORDS * 4, stream));
-    CUDA_TRY(cudaMallocAsync(&red_b, (size_t)gw * (chunks_per_window / tree + 1) * XYZZ_WORDS * 4, stream));
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, hist, bucket_start, (int)(TB + 1), stream));
-    CUDA_TRY(cudaMallocAsync(&cub_tmp, cub_bytes ? cub_bytes : 16, stream));
+    size_t cub_bytes = 0;
+    if (cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)(TB + 1), stream) != cudaSuccess) return (int)cudaErrorUnknown;
+    if (cub_bytes < 16) cub_bytes = 16;
+
+    // ---- one scratch block, carved up ----
+    uint32_t *hist, *bucket_start, *cursors, *items, *item_start, *items2, *sorted, *partial, *partial2, *red_a, *red_b;
+    uint32_t *off_a = nullptr, *off_b = nullptr, *dense_a = nullptr, *dense_b = nullptr, *prefix = nullptr, *dense_bases = nullptr;
+    uint8_t* cub_tmp;
+    Arena ar;
+    auto layout = [&](Arena& a) {
+        hist = a.take<uint32_t>((size_t)TB + 1);
+        bucket_start = a.take<uint32_t>((size_t)TB + 1);
+        cursors = a.take<uint32_t>((size_t)TB + 1);
+        items = a.take<uint32_t>((size_t)TBg + 1);
+        item_start = a.take<uint32_t>((size_t)TBg + 1);
+        items2 = a.take<uint32_t>((size_t)TBg + 1);
+        sorted = a.take<uint32_t>(max_entries);
+        partial = a.take<uint32_t>(max_items * XYZZ_WORDS);
+        partial2 = a.take<uint32_t>(((size_t)TBg + max_items / 32 + 2) * XYZZ_WORDS);
+        red_a = a.take<uint32_t>((size_t)gw * chunks_per_set * XYZZ_WORDS);
+        red_b = a.take<uint32_t>((size_t)gw * (chunks_per_set / tree + 1) * XYZZ_WORDS);
+        cub_tmp = a.take<uint8_t>(cub_bytes);
+        if (!flat) dense_bases = a.take<uint32_t>(total_bases * (size_t)BASE_WORDS);
+        if (levels > 0) {
+            off_a = a.take<uint32_t>((size_t)TBg + 1);
+            off_b = a.take<uint32_t>((size_t)TBg + 1);
+            dense_a = a.take<uint32_t>(dense_cap_a * DENSE_WORDS);
+            if (levels > 1) dense_b = a.take<uint32_t>(dense_cap_b * DENSE_WORDS);
+            prefix = a.take<uint32_t>(dense_cap_a * 12);
+        }
+    };
+    layout(ar);
+    const size_t scratch_bytes = ar.off;
+    void* block = nullptr;
+    DeviceScratch* ds = nullptr;
+    if ((rc = scratch_acquire(&block, scratch_bytes, stream, &ds)) != 0) return rc;
+    ar.base = (uint8_t*)block; ar.off = 0;
+    layout(ar);
 
     CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)(TB + 1) * 4, stream));
     {
-        // ---- bucket sort of all windows: histogram → offsets → scatter ----
-        const unsigned grid = (unsigned)((npoints + 255) / 256);
+        // ---- bucket sort of all jobs and windows: histogram → offsets → scatter ----
         {
             ProfScope sort_scope(PROF_MSM_SORT, stream);
-            k_digits<false><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, hist, nullptr, flat ? table_n : 0);
-            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, hist, bucket_start, (int)(TB + 1), stream));
-            CUDA_TRY(cudaMemcpyAsync(cursors, bucket_start, (size_t)(TB + 1) * 4, cudaMemcpyDeviceToDevice, stream));
-            k_digits<true><<<grid, 256, 0, stream>>>((const uint32_t*)d_scalars, npoints, plan.c, plan.nwin, plan.nbuckets, cursors, sorted, flat ? table_n : 0);
-            count_launch(4);
+            for (int pass = 0; pass < 2; pass++) {
+                for (int i = 0; i < nsegs; i++) {
+                    const MsmSegment& sg = segs[i];
+                    if (sg.n == 0) continue;
+                    const unsigned grid = (unsigned)((sg.n + 255) / 256);
+                    const uint32_t slot_base = sg.job * sets_per_job * plan.nbuckets;
+                    const uint32_t* sc = (const uint32_t*)sg.d_scalars;
+                    const size_t fl = flat ? table_n : 0;
+                    if (pass == 0) {
+                        if (sg.mont) k_digits<false, true><<<grid, 256, 0, stream>>>(sc, sg.n, plan.c, plan.nwin, plan.nbuckets, hist, nullptr, fl, slot_base, sg.base0, d_flags);
+                        else k_digits<false, false><<<grid, 256, 0, stream>>>(sc, sg.n, plan.c, plan.nwin, plan.nbuckets, hist, nullptr, fl, slot_base, sg.base0, d_flags);
+                    } else {
+                        if (sg.mont) k_digits<true, true><<<grid, 256, 0, stream>>>(sc, sg.n, plan.c, plan.nwin, plan.nbuckets, cursors, sorted, fl, slot_base, sg.base0, d_flags);
+                        else k_digits<true, false><<<grid, 256, 0, stream>>>(sc, sg.n, plan.c, plan.nwin, plan.nbuckets, cursors, sorted, fl, slot_base, sg.base0, d_flags);
+                    }
+                    count_launch();
+                }
+                if (pass == 0) {
+                    CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, hist, bucket_start, (int)(TB + 1), stream));
+                    CUDA_TRY(cudaMemcpyAsync(cursors, bucket_start, (size_t)(TB + 1) * 4, cudaMemcpyDeviceToDevice, stream));
+                    count_launch(2);
+                }
+            }
         }
         const uint32_t* gather_src = flat ? table : dense_bases;
-        if (levels > 0 && !flat) {
+        if (!flat) {
             ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
-            k_densify_bases<<<(unsigned)((npoints + 255) / 256), 256, 0, stream>>>((const uint8_t*)d_points, stride, npoints, dense_bases);
-            count_launch();
+            size_t at = 0;
+            for (int i = 0; i < nbases; i++) {
+                if (bases[i].n == 0) continue;
+                k_densify_bases<<<(unsigned)((bases[i].n + 255) / 256), 256, 0, stream>>>((const uint8_t*)bases[i].d_points, bases[i].stride, bases[i].n,
+                                                                                        dense_bases + at * BASE_WORDS);
+                count_launch();
+                at += bases[i].n;
+            }
         }
-        for (uint32_t w0 = 0; w0 < nwin_red; w0 += gw) {
-            const uint32_t wn = nwin_red - w0 < gw ? nwin_red - w0 : gw;                           // windows (bucket sets) in this group
+        for (uint32_t w0 = 0; w0 < nsets; w0 += gw) {
+            const uint32_t wn = nsets - w0 < gw ? nsets - w0 : gw;                                // bucket sets in this group
             const uint32_t tb = wn * plan.nbuckets;
             const uint32_t* bs = bucket_start + (size_t)w0 * plan.nbuckets;                       // tb + 1 absolute offsets into `sorted`
-            const size_t entries = flat ? max_entries : npoints * (size_t)wn;
+            size_t entries = set_cap * (size_t)wn;                                                // bound on the group's entries
+            if (entries > max_entries) entries = max_entries;
             size_t items_bound = 1;                                                                // ≥ item count of any single bucket
+            size_t items_launched = 1;                                                             // ≥ total item count of the group
             const uint32_t* final_partial = nullptr;
             const uint32_t* final_start = nullptr;
             if (levels == 0) {
-                CUDA_TRY(cudaMemsetAsync(items, 0, (size_t)(tb + 1) * 4, stream));
-                k_items_per_bucket<<<(tb + 255) / 256, 256, 0, stream>>>(hist + (size_t)w0 * plan.nbuckets, items, tb, plan.cap);
+                k_items_per_bucket<<<(tb + 256) / 256, 256, 0, stream>>>(hist + (size_t)w0 * plan.nbuckets, items, tb, plan.cap);
                 CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(tb + 1), stream));
-                count_launch(3);
+                count_launch(2);
                 const size_t group_items = (size_t)tb + entries / plan.cap + 1;
-                items_bound = bucket_cap / plan.cap + 1;                // a bucket belongs to one window: ≤ n entries
+                items_bound = set_cap / plan.cap + 1;
+                items_launched = group_items;
                 ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
                 k_bucket_accumulate<<<(unsigned)((group_items + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
-                    (const uint8_t*)d_points, stride, sorted, bs, item_start, tb, plan.cap, partial);
+                    gather_src, sorted, bs, item_start, tb, plan.cap, partial);
+                count_launch();
             } else {
                 ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
                 const uint32_t* off_in = bs;
@@ -630,7 +1067,7 @@ static int msm_core(uint32_t* d_window_sums, const MsmPlan& plan, const void* d_
                     k_halve_counts<<<(tb + 256) / 256, 256, 0, stream>>>(off_in, cursors, tb);
                     CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cursors, off_out, (int)(tb + 1), stream));
                     bound = bound / 2 + tb;                              // Σ ceil(cnt/2) ≤ Σ cnt/2 + #buckets
-                    // Whole waves: 148 SMs × 4 resident CTAs × 128 threads = 75776 threads run at once; give every thread
+                    // Whole waves: 148 SMs × 4 resident CTAs × 128 threads = 75776 lanes run at once; give every lane
                     // the same number T of outputs and launch an integer number of such waves, so no partial last wave
                     // idles most of the machine (a level is one long-running CTA per slot, not many short ones).
                     const size_t wave = (size_t)sm_count * 4 * 128;
@@ -641,34 +1078,47 @@ static int msm_core(uint32_t* d_window_sums, const MsmPlan& plan, const void* d_
                     const unsigned lgrid = (unsigned)((nthreads + 127) / 128);
                     // level 0 reads absolute positions of `sorted` (off_in = bs); its outputs and all later levels are
                     // group-relative (the scans start at 0)
-                    if (l == 0)
-                        k_pair_level<true><<<lgrid, 128, 0, stream>>>(gather_src, sorted, nullptr, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
-                    else
-                        k_pair_level<false><<<lgrid, 128, 0, stream>>>(nullptr, nullptr, dense_in, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
-                    count_launch(4);
+                    if (pair_v1) {
+                        if (l == 0)
+                            k_pair_level<true><<<lgrid, 128, 0, stream>>>(gather_src, sorted, nullptr, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
+                        else
+                            k_pair_level<false><<<lgrid, 128, 0, stream>>>(nullptr, nullptr, dense_in, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
+                    } else {
+                        if (l == 0)
+                            k_pair_level2<true><<<lgrid, 128, PAIR2_SMEM, stream>>>(gather_src, sorted, nullptr, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
+                        else
+                            k_pair_level2<false><<<lgrid, 128, PAIR2_SMEM, stream>>>(nullptr, nullptr, dense_in, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
+                    }
+                    count_launch(3);
                     off_in = off_out;
                     dense_in = dense_out;
                 }
                 k_items_from_offsets<<<(tb + 256) / 256, 256, 0, stream>>>(off_in, items, tb, plan.cap);
                 CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(tb + 1), stream));
                 const size_t group_items = (size_t)tb + bound / plan.cap + 1;
-                items_bound = ((bucket_cap >> levels) + 1) / plan.cap + 1;
+                items_bound = ((set_cap >> levels) + 1) / plan.cap + 1;
+                items_launched = group_items;
                 k_bucket_accumulate_dense<<<(unsigned)((group_items + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
                     dense_in, off_in, item_start, tb, plan.cap, partial);
-                count_launch(4);
+                count_launch(3);
             }
             ProfScope red_scope(PROF_MSM_REDUCE, stream);
             {
-                // fold item partials 32:1 until no bucket can hold more than one (worst case: all entries in one bucket)
+                // fold item partials 32:1 until no bucket can hold more than one (worst case: all entries in one bucket).
+                // `worst` (≥ the item count of any single bucket) only decides when to stop; the launch covers
+                // Σ_b ceil(items_b / 32) ≤ #buckets + total/32 outputs, where `total_bound` bounds the items of ALL buckets
+                // (a few hot buckets over a full background need far more outputs than tb + worst/32).
                 size_t worst = items_bound;
+                size_t total_bound = items_launched;
                 uint32_t* p_in = partial; uint32_t* p_out = partial2;
                 uint32_t* st_in = item_start; uint32_t* st_out = items2;
                 while (worst > 1) {
                     k_group_counts<<<(tb + 256) / 256, 256, 0, stream>>>(st_in, cursors, tb);
                     CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cursors, st_out, (int)(tb + 1), stream));
-                    const size_t out_bound = (size_t)tb + (worst + 31) / 32;
+                    const size_t out_bound = (size_t)tb + total_bound / 32 + 1;
+                    total_bound = out_bound;
                     k_partial_group_sum<<<(unsigned)((out_bound + 127) / 128), 128, 0, stream>>>(p_in, st_in, st_out, tb, p_out);
-                    count_launch(4);
+                    count_launch(3);
                     worst = (worst + 31) / 32;
                     uint32_t* t1 = p_in; p_in = p_out; p_out = t1;
                     uint32_t* t2 = st_in; st_in = st_out; st_out = t2;
@@ -676,11 +1126,11 @@ static int msm_core(uint32_t* d_window_sums, const MsmPlan& plan, const void* d_
                 final_partial = p_in; final_start = st_in;
             }
             uint32_t* group_sums = d_window_sums + (size_t)w0 * XYZZ_WORDS;
-            const uint32_t nthreads = chunks_per_window * wn;
-            k_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, stream>>>(final_partial, final_start, plan.nbuckets, chunk, chunks_per_window, wn, red_a);
+            const uint32_t nthreads = chunks_per_set * wn;
+            k_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, stream>>>(final_partial, final_start, plan.nbuckets, chunk, chunks_per_set, wn, red_a);
             count_launch(1);
-            // tree over the per-chunk sums: groups of `tree` until one point per window remains
-            uint32_t per_row = chunks_per_window;
+            // tree over the per-chunk sums: groups of `tree` until one point per bucket set remains
+            uint32_t per_row = chunks_per_set;
             const uint32_t* src = red_a;
             uint32_t* bufs[2] = {red_b, red_a};
             int which = 0;
@@ -692,24 +1142,21 @@ static int msm_core(uint32_t* d_window_sums, const MsmPlan& plan, const void* d_
                 count_launch();
                 src = target; which ^= 1; per_row = out_per_row;
             }
-            if (chunks_per_window == 1)
+            if (chunks_per_set == 1)
                 CUDA_TRY(cudaMemcpyAsync(group_sums, red_a, (size_t)wn * XYZZ_WORDS * 4, cudaMemcpyDeviceToDevice, stream));
         }
         CUDA_TRY(cudaGetLastError());
     }
 done:
-    cudaFreeAsync(hist, stream); cudaFreeAsync(bucket_start, stream); cudaFreeAsync(cursors, stream);
-    cudaFreeAsync(items, stream); cudaFreeAsync(item_start, stream); cudaFreeAsync(sorted, stream);
-    cudaFreeAsync(off_a, stream); cudaFreeAsync(off_b, stream); cudaFreeAsync(dense_a, stream); cudaFreeAsync(dense_b, stream);
-    cudaFreeAsync(prefix, stream); if (dense_bases) cudaFreeAsync(dense_bases, stream);
-    cudaFreeAsync(partial2, stream); cudaFreeAsync(items2, stream);
-    cudaFreeAsync(partial, stream); cudaFreeAsync(red_a, stream); cudaFreeAsync(red_b, stream); cudaFreeAsync(cub_tmp, stream);
+    scratch_release(block, scratch_bytes, stream, ds);
     return rc;
 }
 
-int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const void* d_points, size_t stride,
+int msm_window_sums_device(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, const void* d_points, size_t stride,
                            const void* d_scalars, size_t npoints, cudaStream_t stream) {
-    return msm_core(d_window_sums, plan, d_points, stride, nullptr, 0, d_scalars, npoints, stream);
+    MsmBases b{d_points, stride, npoints};
+    MsmSegment sg{d_scalars, npoints, 0u, 0u, 0};
+    return msm_core(d_window_sums, d_flags, plan, &b, 1, nullptr, 0, &sg, 1, 1, stream);
 }
 
 MsmPlan msm_make_plan_precomputed(size_t npoints) {
@@ -740,9 +1187,10 @@ int msm_precompute_tables_device(uint32_t* d_table, const MsmPlan& plan, const v
     return (int)cudaGetLastError();
 }
 
-int msm_precomputed_sum_device(uint32_t* d_sum, const MsmPlan& plan, const uint32_t* d_table, size_t table_n, const void* d_scalars,
-                               size_t nscalars, cudaStream_t stream) {
-    return msm_core(d_sum, plan, nullptr, 0, d_table, table_n, d_scalars, nscalars, stream);
+int msm_precomputed_sum_device(uint32_t* d_sum, uint32_t* d_flags, const MsmPlan& plan, const uint32_t* d_table, size_t table_n, const void* d_scalars,
+                               size_t nscalars, int mont, cudaStream_t stream) {
+    MsmSegment sg{d_scalars, nscalars, 0u, 0u, mont};
+    return msm_core(d_sum, d_flags, plan, nullptr, 0, d_table, table_n, &sg, 1, 1, stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -33,11 +33,28 @@ struct MsmPlan {
 };
 
 MsmPlan msm_make_plan(size_t npoints);
+MsmPlan msm_make_plan_batch(size_t max_n, size_t total_n);
 
-// Computes the per-window sums Σ_b b·S_{w,b} as XYZZ points (48 words each) into
-// d_window_sums[plan.nwin][48].  All pointers are device pointers.  Scratch is taken
-// from the stream-ordered pool of the current device.  Returns cudaError_t as int.
-int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const void* d_points, size_t stride,
+// One MSM call = `njobs` independent sums over one resident base set.
+struct MsmBases {            // base arrays, densified back to back into 128-byte records (their indices follow each other)
+    const void* d_points;
+    size_t stride, n;
+};
+struct MsmSegment {          // one scalar vector; segment i of job j adds Σ_k scalars[k]·base[base0 + k] into job j's sum
+    const void* d_scalars;   // n × 32 B in HBM
+    size_t n;
+    uint32_t base0;          // index of its first point in the concatenated base array (0 in table mode)
+    uint32_t job;
+    int mont;                // 1: Montgomery Fr (polynomial coefficients), converted to canonical integers in the digit kernel
+};
+// d_window_sums[njobs][flat ? 1 : plan.nwin] XYZZ points (48 words each); *d_flags (device u32, zeroed by the caller) gets bit 0
+// set when a scalar has bits 253..255 set.  All pointers are device pointers; scratch comes from the library's private
+// stream-ordered pool under the per-device byte budget.  Returns cudaError_t as int.
+int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, const MsmBases* bases, int nbases,
+             const uint32_t* table, size_t table_n, const MsmSegment* segs, int nsegs, int njobs, cudaStream_t stream);
+
+// single sum, canonical scalars: per-window sums Σ_b b·S_{w,b} into d_window_sums[plan.nwin][48]
+int msm_window_sums_device(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, const void* d_points, size_t stride,
                            const void* d_scalars, size_t npoints, cudaStream_t stream);
 
 // Resident bases with precomputed tables 2^{c·w}·P_i (w < nwin; 128 B per record): all windows then share ONE bucket set, so
@@ -45,7 +62,8 @@ int msm_window_sums_device(uint32_t* d_window_sums, const MsmPlan& plan, const v
 MsmPlan msm_make_plan_precomputed(size_t npoints);
 int msm_precompute_tables_device(uint32_t* d_table, const MsmPlan& plan, const void* d_points, size_t stride, size_t npoints, cudaStream_t stream);
 // d_sum: ONE XYZZ point (192 B) = Σ scalars[i]·P_i over the first nscalars (≤ table_n) points
-int msm_precomputed_sum_device(uint32_t* d_sum, const MsmPlan& plan, const uint32_t* d_table, size_t table_n, const void* d_scalars, size_t nscalars, cudaStream_t stream);
+int msm_precomputed_sum_device(uint32_t* d_sum, uint32_t* d_flags, const MsmPlan& plan, const uint32_t* d_table, size_t table_n, const void* d_scalars,
+                               size_t nscalars, int mont, cudaStream_t stream);
 
 // Deterministic test/bench input: P_i = h(seed, i)·G with a 64-bit multiplier h
 // (every point is in the prime-order subgroup because G is).  Writes the reference
@@ -59,9 +77,13 @@ int srs_decode_device(void* d_out, size_t stride, const void* d_in, size_t npoin
 // out[i] = Σ_r in[r][i]  over `nranks` arrays of `count` XYZZ points (multi-GPU combine).
 int xyzz_sum_ranks_device(uint32_t* d_out, const uint32_t* d_in, int nranks, int count, cudaStream_t stream);
 
-// Once per device: keep freed scratch inside the stream-ordered pool (release threshold = max) so that
-// steady-state calls never go back to the driver for their ~GB of workspace.
-void ensure_pool_configured();
+// Allocation from the library's private stream-ordered pool of the current device (release threshold = the scratch budget:
+// half the device unless SNARKVM_B200_SCRATCH_LIMIT_GB says otherwise); free with cudaFreeAsync.  The default pool is untouched.
+int pool_alloc_raw(void** p, size_t bytes, cudaStream_t stream);
+template <class T> inline cudaError_t pool_alloc(T** p, size_t bytes, cudaStream_t stream) { return (cudaError_t)pool_alloc_raw((void**)p, bytes, stream); }
+// MSM scratch budget of the current device: bytes allowed in flight, in flight now, and the high-water mark
+int msm_scratch_stats(size_t* limit, size_t* in_use, size_t* peak);
+int msm_set_scratch_limit(size_t bytes);      // also resets the high-water mark
 
 uint64_t launch_count();
 void count_launch(int n = 1);

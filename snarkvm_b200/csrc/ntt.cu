@@ -315,7 +315,6 @@ int ntt_device(void* d_inout, uint32_t lg, int direction, int type, void* d_scra
     if (direction != NTT_FORWARD && direction != NTT_INVERSE) return (int)cudaErrorInvalidValue;
     if (type != NTT_STANDARD && type != NTT_COSET) return (int)cudaErrorInvalidValue;
     int rc = 0;
-    ensure_pool_configured();
     Fr* A = (Fr*)d_inout;
     Fr* B = (Fr*)d_scratch;
     bool own_scratch = false;
@@ -337,7 +336,7 @@ int ntt_device(void* d_inout, uint32_t lg, int direction, int type, void* d_scra
         // split lg into P passes of near-equal stage counts
         int P = lg <= (uint32_t)TILE_LG ? 1 : (int)((lg + MAX_STAGES - 1) / MAX_STAGES);
         if (P > 1 && !B) {
-            CUDA_TRY(cudaMallocAsync((void**)&B, ((size_t)1 << lg) * sizeof(Fr), stream));
+            CUDA_TRY(pool_alloc((void**)&B, ((size_t)1 << lg) * sizeof(Fr), stream));
             own_scratch = true;
         }
         int t0 = 0;

@@ -127,12 +127,11 @@ int poly_evaluate_device(void* out_mont_host, const void* d_coeffs, size_t m, co
     if (!out_mont_host || !point_mont_host) return (int)cudaErrorInvalidValue;
     if (m == 0) { memset(out_mont_host, 0, 32); return 0; }
     if (!d_coeffs) return (int)cudaErrorInvalidValue;
-    ensure_pool_configured();
     FrArg z;
     memcpy(z.v, point_mont_host, 32);
     const size_t threads = (m + EVAL_K - 1) / EVAL_K, blocks = (threads + EVAL_THREADS - 1) / EVAL_THREADS;
     uint32_t* scratch = nullptr;
-    cudaError_t e = cudaMallocAsync(&scratch, (blocks + 1) * 32, stream);
+    cudaError_t e = pool_alloc(&scratch, (blocks + 1) * 32, stream);
     if (e != cudaSuccess) return (int)e;
     k_poly_eval_partial<<<(unsigned)blocks, EVAL_THREADS, 0, stream>>>((const uint32_t*)d_coeffs, m, z, scratch);
     k_fr_sum<<<1, EVAL_THREADS, 0, stream>>>(scratch, blocks, scratch + blocks * 8);
@@ -209,12 +208,11 @@ __global__ void k_lin_final(const uint32_t* __restrict__ p, size_t L, FrArg z_ar
 int poly_divide_by_linear_device(void* d_q, const void* d_p, size_t m, const void* point_mont_host, cudaStream_t stream) {
     if (m <= 1) return 0;
     if (!d_q || !d_p || !point_mont_host) return (int)cudaErrorInvalidValue;
-    ensure_pool_configured();
     FrArg z;
     memcpy(z.v, point_mont_host, 32);
     const size_t L = m - 1, nchunks = (L + LIN_K - 1) / LIN_K;
     uint32_t* scratch = nullptr;                             // A[nchunks] then cin[nchunks]
-    cudaError_t e = cudaMallocAsync(&scratch, nchunks * 64, stream);
+    cudaError_t e = pool_alloc(&scratch, nchunks * 64, stream);
     if (e != cudaSuccess) return (int)e;
     const unsigned grid = (unsigned)((nchunks + 127) / 128);
     k_lin_local<<<grid, 128, 0, stream>>>((const uint32_t*)d_p, L, z, scratch);
@@ -247,9 +245,8 @@ int sparse_matvec_device(void* d_out, const void* d_row_ptr, const void* d_cols,
                          size_t nvars, cudaStream_t stream) {
     if (nrows == 0) return 0;
     if (!d_out || !d_row_ptr || !d_x) return (int)cudaErrorInvalidValue;
-    ensure_pool_configured();
     int* bad = nullptr;
-    cudaError_t e = cudaMallocAsync(&bad, sizeof(int), stream);
+    cudaError_t e = pool_alloc(&bad, sizeof(int), stream);
     if (e != cudaSuccess) return (int)e;
     int rc = (int)cudaMemsetAsync(bad, 0, sizeof(int), stream);
     k_sparse_matvec<<<(unsigned)((nrows + 127) / 128), 128, 0, stream>>>((const uint32_t*)d_row_ptr, (const uint32_t*)d_cols, (const uint32_t*)d_vals,

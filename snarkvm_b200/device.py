@@ -92,15 +92,64 @@ def msm(bases: torch.Tensor, scalars: torch.Tensor, stride: int = AFFINE_STRIDE)
     return out
 
 
-def msm_window_sums(bases: torch.Tensor, scalars: torch.Tensor, stride: int = AFFINE_STRIDE) -> torch.Tensor:
-    """Per-window XYZZ sums [nwin, 24] (int64 view of 192-byte points), left in HBM."""
+def msm_window_sums(bases: torch.Tensor, scalars: torch.Tensor, stride: int = AFFINE_STRIDE, plan_npoints: int | None = None,
+                    flags: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Per-window XYZZ sums [nwin, 24] (int64 view of 192-byte points), left in HBM.  `plan_npoints` (≥ the number of
+    scalars) fixes the window plan — all ranks of a sharded MSM pass the largest shard size; an empty shard gives infinity
+    sums.  `flags`: optional int32 CUDA tensor [1] that receives bit 0 = "a scalar ≥ 2^253 was seen"."""
     npoints = _msm_args(bases, scalars, stride)
-    plan = msm_plan(npoints)
-    sums = torch.empty((plan["nwin"], XYZZ_BYTES // 8), dtype=torch.int64, device=bases.device)
-    with torch.cuda.device(bases.device):
-        _lib.check(_lib.lib().snarkvm_b200_msm_window_sums_device(sums.data_ptr(), _check(bases, "bases"), npoints,
-                                                                   _check(scalars, "scalars"), stride, _stream()))
+    pn = npoints if plan_npoints is None else int(plan_npoints)
+    if pn < max(npoints, 1):
+        raise ValueError("plan_npoints must be at least the shard size and positive")
+    plan = msm_plan(pn)
+    dev = bases.device if bases.is_cuda else scalars.device
+    sums = torch.empty((plan["nwin"], XYZZ_BYTES // 8), dtype=torch.int64, device=dev) if out is None else out
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().snarkvm_b200_msm_window_sums_plan_device(
+            _check(sums, "out"), flags.data_ptr() if flags is not None else None, pn, _check(bases, "bases") if npoints else None, npoints,
+            _check(scalars, "scalars") if npoints else None, stride, _stream()))
     return sums
+
+
+def msm_window_sums_host(out: torch.Tensor, flags: torch.Tensor | None, plan_npoints: int, points: np.ndarray, scalars: np.ndarray,
+                         stride: int = AFFINE_STRIDE) -> torch.Tensor:
+    """msm_window_sums from HOST buffers (numpy uint8 [n, stride] points, uint64 [n, 4] canonical scalars): the library uploads
+    them (ranges overlapped with the kernels, pageable memory staged through pinned buffers) and leaves the sums in `out`
+    (CUDA, [nwin, 24] int64) without synchronising."""
+    npoints = scalars.shape[0]
+    if npoints > points.shape[0]:
+        raise ValueError(f"length mismatch {points.shape[0]} points < {npoints} scalars")
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().snarkvm_b200_msm_window_sums_host(
+            _check(out, "out"), flags.data_ptr() if flags is not None else None, int(plan_npoints), points.ctypes.data if npoints else None,
+            npoints, scalars.ctypes.data if npoints else None, stride, _stream()))
+    return out
+
+
+def msm_batch(bases: torch.Tensor, scalar_vectors: list, stride: int = AFFINE_STRIDE) -> np.ndarray:
+    """`len(scalar_vectors)` MSMs over the same resident bases in ONE pass → [count, 18] u64 (normalised projective each)."""
+    count = len(scalar_vectors)
+    out = np.zeros((count, 18), dtype=np.uint64)
+    if count == 0:
+        return out
+    lens = [_msm_args(bases, v, stride) for v in scalar_vectors]
+    ptrs = (ctypes.c_void_p * count)(*[(_check(v, "scalars") if n else None) for v, n in zip(scalar_vectors, lens)])
+    szs = (ctypes.c_size_t * count)(*lens)
+    with torch.cuda.device(bases.device):
+        _lib.check(_lib.lib().snarkvm_b200_msm_batch_device(out.ctypes.data, _check(bases, "bases"), stride, ptrs, szs, count, _stream()))
+    return out
+
+
+def msm_set_scratch_limit(nbytes: int) -> None:
+    """bytes of MSM scratch concurrent calls on the current device may hold together (callers beyond it wait)"""
+    _lib.check(_lib.lib().snarkvm_b200_msm_set_scratch_limit(int(nbytes)))
+
+
+def msm_scratch_stats() -> dict:
+    """MSM scratch budget of the current device: {'limit', 'in_use', 'peak'} in bytes."""
+    a, b, c = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+    _lib.check(_lib.lib().snarkvm_b200_msm_scratch_stats(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+    return {"limit": a.value, "in_use": b.value, "peak": c.value}
 
 
 def xyzz_sum_ranks(gathered: torch.Tensor, nranks: int, count: int) -> torch.Tensor:
@@ -145,8 +194,11 @@ def kzg_commit_hiding(powers: torch.Tensor, coeffs_mont: torch.Tensor, gamma_pow
     return out
 
 
-def kzg_commit_batch(powers: torch.Tensor, polys_mont: list, stride: int = AFFINE_STRIDE) -> np.ndarray:
-    """One call for all commitments of a round against the same resident powers (sonic_pc/mod.rs:177-257) → [count, 18] u64."""
+def kzg_commit_batch(powers: torch.Tensor, polys_mont: list, stride: int = AFFINE_STRIDE, gamma_powers: torch.Tensor | None = None,
+                     blindings_mont: list | None = None) -> np.ndarray:
+    """All commitments of a round against the same resident powers in ONE pass (sonic_pc/mod.rs:177-257) → [count, 18] u64.
+    With `gamma_powers` and `blindings_mont` (one Montgomery coefficient tensor or None per polynomial) the hiding terms
+    Σ_j blinding_i[j]·gamma_powers[j] (kzg10/mod.rs:129-150) ride in the same pass."""
     count = len(polys_mont)
     out = np.zeros((count, 18), dtype=np.uint64)
     if count == 0:
@@ -155,10 +207,21 @@ def kzg_commit_batch(powers: torch.Tensor, polys_mont: list, stride: int = AFFIN
     lens = [_nbytes(p) // 32 for p in polys_mont]
     if max(lens) > nb:
         raise ValueError("polynomial degree exceeds the number of powers")         # check_degree_is_too_large, mod.rs:105
-    ptrs = (ctypes.c_void_p * count)(*[_check(p, "poly") for p in polys_mont])
+    ptrs = (ctypes.c_void_p * count)(*[(_check(p, "poly") if n else None) for p, n in zip(polys_mont, lens)])
     szs = (ctypes.c_size_t * count)(*lens)
     with torch.cuda.device(powers.device):
-        _lib.check(_lib.lib().snarkvm_b200_kzg_commit_batch_device(out.ctypes.data, _check(powers, "powers"), stride, ptrs, szs, count, _stream()))
+        if blindings_mont is None:
+            _lib.check(_lib.lib().snarkvm_b200_kzg_commit_batch_device(out.ctypes.data, _check(powers, "powers"), stride, ptrs, szs, count, _stream()))
+        else:
+            if len(blindings_mont) != count:
+                raise ValueError("one blinding polynomial (or None) per polynomial")
+            blens = [0 if b is None else _nbytes(b) // 32 for b in blindings_mont]
+            if max(blens) > _nbytes(gamma_powers) // stride:
+                raise ValueError("hiding bound exceeds powers_of_beta_times_gamma_g")          # check_hiding_bound, mod.rs:134-137
+            bptrs = (ctypes.c_void_p * count)(*[(_check(b, "blinding") if n else None) for b, n in zip(blindings_mont, blens)])
+            bszs = (ctypes.c_size_t * count)(*blens)
+            _lib.check(_lib.lib().snarkvm_b200_kzg_commit_batch_hiding_device(
+                out.ctypes.data, _check(powers, "powers"), stride, ptrs, szs, _check(gamma_powers, "gamma_powers"), bptrs, bszs, count, _stream()))
     return out
 
 
@@ -300,6 +363,23 @@ class PrecomputedBases:
 
     def kzg_commit(self, coeffs_mont: torch.Tensor) -> np.ndarray:
         return self._run(_lib.lib().snarkvm_b200_kzg_commit_precomputed_device, coeffs_mont)
+
+    def kzg_commit_batch(self, polys_mont: list) -> np.ndarray:
+        """all commitments of a round over the tables, one pass → [count, 18] u64"""
+        if self._h is None:
+            raise ValueError("PrecomputedBases was freed")
+        count = len(polys_mont)
+        out = np.zeros((count, 18), dtype=np.uint64)
+        if count == 0:
+            return out
+        lens = [_nbytes(p) // 32 for p in polys_mont]
+        if max(lens) > self.npoints:
+            raise ValueError("more coefficients than bases")
+        ptrs = (ctypes.c_void_p * count)(*[(_check(p, "poly") if n else None) for p, n in zip(polys_mont, lens)])
+        szs = (ctypes.c_size_t * count)(*lens)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().snarkvm_b200_kzg_commit_batch_precomputed_device(out.ctypes.data, self._h, ptrs, szs, count, _stream()))
+        return out
 
     def free(self) -> None:
         if self._h is not None:

@@ -418,3 +418,160 @@ def test_registered_bases_precomputed(oracle_cpu, bases64k):
     finally:
         cuda.unregister_bases(bases)
     assert (cuda.msm(bases, scal) == oracle_cpu.msm(bases, scal, 0)).all()      # plain path again after unregistering
+
+
+@pytest.mark.parametrize("lg,levels", [(16, None), (16, 2), (17, 1), (18, None), (18, 3)])
+def test_msm_half_repeated_scalars(oracle_cpu, monkeypatch, lg, levels):
+    """Half of the scalars equal to ONE random value over a uniform background (e.g. commit_lagrange of an evaluation
+    vector with a dominant value): every window then has one hot bucket on top of ~all other buckets being non-empty,
+    which needs more fold outputs than #buckets + hot/32 (round-1 ADVICE: the fold launch was sized from the hottest
+    bucket only and left partials unwritten).  With and without pair levels."""
+    from snarkvm_b200 import device
+    if levels is not None:
+        monkeypatch.setenv("SNARKVM_B200_MSM_LEVELS", str(levels))
+    n = 1 << lg
+    bases = device.generate_bases(n, seed=500 + lg)
+    scal = random_canonical_fr(n, seed=700 + lg)
+    rng = np.random.default_rng(lg)
+    hot = rng.permutation(n)[: n // 2]
+    scal[hot] = scal[0]
+    got = device.msm(bases, _dev(scal))
+    assert (got == oracle_cpu.msm(bases.cpu().numpy(), scal, 0)).all()
+    # a few dozen hot values instead of one
+    scal2 = random_canonical_fr(n, seed=800 + lg)
+    scal2[hot] = scal2[rng.integers(0, 48, size=hot.size)]
+    assert (device.msm(bases, _dev(scal2)) == oracle_cpu.msm(bases.cpu().numpy(), scal2, 0)).all()
+
+
+def test_msm_rejects_scalars_above_253_bits(oracle_cpu, bases64k):
+    """Scalars are canonical integers < r < 2^253 (to_bigint output).  A BigInteger256 with bits 253..255 set is outside what the
+    signed-digit windows cover: the call must return an error (the Rust caller then falls back to its CPU path,
+    variable_base/mod.rs:39-43) instead of a silently wrong point."""
+    from snarkvm_b200 import CudaError, cuda
+    n = 2000
+    scal = random_canonical_fr(n, seed=5)
+    assert (cuda.msm(bases64k[:n], scal) == oracle_cpu.msm(bases64k[:n], scal, 0)).all()
+    bad = scal.copy()
+    bad[777, 3] |= np.uint64(1 << 63)
+    with pytest.raises(CudaError):
+        cuda.msm(bases64k[:n], bad)
+    bad = scal.copy()
+    bad[3, 3] |= np.uint64(1 << 61)
+    with pytest.raises(CudaError):
+        cuda.msm(bases64k[:n], bad)
+
+
+def test_kzg_commit_hiding_full_size(oracle_cpu):
+    """BASELINE config 4: KZG10::commit of a 2^22-coefficient polynomial with hiding_bound = Some(1)
+    (kzg10/mod.rs:98-156: commitment + MSM(powers_of_beta_times_gamma_g, blinding polynomial of degree hiding_bound + 1))."""
+    from snarkvm_b200 import device
+    from snarkvm_b200.algorithms import KZG10
+    n = 1 << 22
+    powers = device.generate_bases(n, seed=4100)
+    gamma = device.generate_bases(8, seed=4101)
+    coeffs = random_canonical_fr(n, seed=4102)                 # Montgomery images
+    blind = random_canonical_fr(3, seed=4103)                  # hiding_bound + 2 coefficients (degree hiding_bound + 1)
+    got = KZG10.commit(powers, _dev(coeffs), gamma, _dev(blind))
+    a = oracle_cpu.msm(powers.cpu().numpy(), oracle_cpu.fr_from_mont(coeffs), 0)
+    b = oracle_cpu.msm(gamma.cpu().numpy()[:3], oracle_cpu.fr_from_mont(blind), 0)
+    assert (got == oracle_cpu.g1_add(a, b)).all()
+
+
+def test_msm_batch_one_pass(oracle_cpu, bases64k, monkeypatch):
+    """snarkvm_b200_msm_batch_device / kzg_commit_batch: many scalar vectors over the same resident bases in ONE pass
+    (sonic_pc/mod.rs:177-257) — different lengths, an empty vector, a length-1 vector, equal vectors; every sum must equal the
+    oracle's MSM of that vector alone."""
+    from snarkvm_b200 import device
+    from snarkvm_b200.algorithms import KZG10
+    dbases = _dev(bases64k)
+    lens = [5000, 0, 1, 65536, 12345, 5000, 777, 40000]
+    vecs = [random_canonical_fr(n, seed=900 + i) for i, n in enumerate(lens)]
+    vecs[5] = vecs[0].copy()
+    got = device.msm_batch(dbases, [_dev(v) for v in vecs])
+    for i, v in enumerate(vecs):
+        assert (got[i] == oracle_cpu.msm(bases64k[:len(v)], v, 0)).all(), i
+    # Montgomery coefficients (KZG commit) + pair levels forced on
+    monkeypatch.setenv("SNARKVM_B200_MSM_LEVELS", "3")
+    got = KZG10.batch_commit(dbases, [_dev(v) for v in vecs])
+    for i, v in enumerate(vecs):
+        assert (got[i] == oracle_cpu.msm(bases64k[:len(v)], oracle_cpu.fr_from_mont(v), 0)).all(), i
+
+
+def test_kzg_commit_batch_hiding_one_pass(oracle_cpu, bases64k):
+    """A round of hiding commitments in one pass: polynomial i gets Σ_j blinding_i[j]·gamma_powers[j] through a second scalar
+    segment of the same sum; some polynomials are not hiding (None), one is empty but hiding."""
+    from snarkvm_b200 import device
+    from snarkvm_b200.algorithms import KZG10
+    dbases = _dev(bases64k)
+    gamma = device.generate_bases(16, seed=31337)
+    gamma_h = gamma.cpu().numpy()
+    lens = [3000, 20000, 0, 65536, 9]
+    blens = [3, 0, 2, 4, 16]
+    polys = [random_canonical_fr(n, seed=50 + i) for i, n in enumerate(lens)]
+    blinds = [random_canonical_fr(n, seed=70 + i) if n else None for i, n in enumerate(blens)]
+    got = KZG10.batch_commit(dbases, [_dev(p) for p in polys], gamma, [None if b is None else _dev(b) for b in blinds])
+    for i, (p, b) in enumerate(zip(polys, blinds)):
+        want = oracle_cpu.msm(bases64k[:len(p)], oracle_cpu.fr_from_mont(p), 0)
+        if b is not None:
+            want = oracle_cpu.g1_add(want, oracle_cpu.msm(gamma_h[:len(b)], oracle_cpu.fr_from_mont(b), 0))
+        assert (got[i] == want).all(), i
+    # the single-commitment entry point takes the same route
+    one = KZG10.commit(dbases, _dev(polys[0]), gamma, _dev(blinds[0]))
+    assert (one == got[0]).all()
+
+
+def test_msm_batch_large_round(oracle_cpu):
+    """8 × 2^17-coefficient polynomials in one pass (a Varuna-sized round): the batch plan turns pair levels on although each
+    polynomial alone would run without them."""
+    from snarkvm_b200 import device
+    n = 1 << 17
+    bases = device.generate_bases(n, seed=4242)
+    bh = bases.cpu().numpy()
+    vecs = [random_canonical_fr(n - 1000 * i, seed=600 + i) for i in range(8)]
+    got = device.msm_batch(bases, [_dev(v) for v in vecs])
+    for i, v in enumerate(vecs):
+        assert (got[i] == oracle_cpu.msm(bh[:len(v)], v, 0)).all(), i
+    pre = device.PrecomputedBases(bases)
+    got = pre.kzg_commit_batch([_dev(v) for v in vecs[:4]])
+    for i, v in enumerate(vecs[:4]):
+        assert (got[i] == oracle_cpu.msm(bh[:len(v)], oracle_cpu.fr_from_mont(v), 0)).all(), i
+    pre.free()
+
+
+def test_msm_concurrent_large_calls_share_scratch_budget(oracle_cpu):
+    """Eight host threads call snarkvm_msm with 2^20 points each while the scratch budget only fits about two calls: the others
+    must WAIT for their turn (no cudaErrorMemoryAllocation ⇒ silent CPU fallback on the Rust side), all results must be right, and
+    the high-water mark must respect the budget."""
+    import threading
+    from snarkvm_b200 import cuda, device
+    n = 1 << 20
+    seed = 999
+    bases = device.generate_bases(n, seed).cpu().numpy()
+    ks = np.zeros((n, 4), dtype=np.uint64)
+    ks[:, 0] = generated_base_multipliers(seed, n)
+    g = affine_array([py.G1_GENERATOR])[0]
+    scal = [random_canonical_fr(n, seed=10 + k) for k in range(8)]
+    cuda.msm(bases, scal[0])                                    # warm up: pool + one call's scratch
+    one_call = device.msm_scratch_stats()["peak"]
+    old_limit = device.msm_scratch_stats()["limit"]
+    device.msm_set_scratch_limit(int(one_call * 2.5))
+    results, errors = {}, []
+
+    def work(k):
+        try:
+            results[k] = cuda.msm(bases, scal[k])
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+
+    try:
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        st = device.msm_scratch_stats()
+    finally:
+        device.msm_set_scratch_limit(old_limit)
+    assert not errors, errors
+    assert st["peak"] <= int(one_call * 2.5) and st["in_use"] == 0
+    for k in range(8):
+        want = oracle_cpu.g1_mul(g, oracle_cpu.fr_dot_canonical(scal[k], ks))
+        assert (results[k] == want).all(), k

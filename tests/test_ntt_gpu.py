@@ -91,8 +91,7 @@ def test_ntt_full_size_properties(oracle_cpu, lg):
     cy = device.ntt_(dx.clone(), NTTDirection.Forward, NTTType.Coset)
     assert not torch.equal(cy, y)
     assert torch.equal(device.ntt_(cy, NTTDirection.Inverse, NTTType.Coset), dx)
-    if lg <= 20:
-        assert (_host(y) == oracle_cpu.ntt(x, 0, 0)).all()
+    assert (_host(y) == oracle_cpu.ntt(x, 0, 0)).all()
     # y_0 = Σ x_j and y_{n/2} = Σ (−1)^j x_j, summed with Python integers on the canonical values
     vals = oracle_cpu.fr_from_mont(x)
     def to_int(rows):
@@ -159,3 +158,20 @@ def test_ntt_input_output_orders(oracle_cpu, lg):
         assert (got == want).all()
         got = np.ascontiguousarray(x[perm]); cuda.NTT(n, got, cuda.NTTInputOutputOrder.RR, cuda.NTTDirection(d), cuda.NTTType(t))
         assert (got == want[perm]).all()
+
+
+@pytest.mark.parametrize("lg", [22, 23, 24])
+def test_ntt_large_sizes_vs_oracle(oracle_cpu, lg):
+    """BASELINE config 3 (and the sizes between, whose pass splits differ: 8+7+7, 8+8+7, 8+8+8): all four
+    (direction, type) modes against the oracle's fft_in_place, element by element."""
+    import torch
+    from snarkvm_b200 import device
+    from snarkvm_b200.cuda import NTTDirection, NTTType
+    n = 1 << lg
+    x = random_fr_mont(n, seed=2200 + lg)
+    dx = _dev(x)
+    scratch = torch.empty_like(dx)
+    for d, t in MODES:
+        y = device.ntt_(dx.clone(), NTTDirection(d), NTTType(t), scratch)
+        assert (_host(y) == oracle_cpu.ntt(x, d, t)).all(), (lg, d, t)
+        del y

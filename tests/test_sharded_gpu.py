@@ -32,12 +32,13 @@ def _worker(rank, world, port, n, tmpdir):
     dist.destroy_process_group()
 
 
-def test_sharded_msm_two_gpus(tmp_path, oracle_cpu):
+@pytest.mark.parametrize("n", [1 << 16, (1 << 16) + 1, 3])
+def test_sharded_msm_two_gpus(tmp_path, oracle_cpu, n):
+    """equal shards; ⌈n/2⌉ shards of different lengths whose own plans would differ (2^15 + 1 vs 2^15 points); and a 2 + 1 split"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    n = 1 << 16
     mp.spawn(_worker, args=(2, 29600 + os.getpid() % 1000, n, str(tmp_path)), nprocs=2, join=True)
     want = oracle_cpu.msm(np.load(tmp_path / "bases.npy"), np.load(tmp_path / "scal.npy"), 0)
     for r in range(2):

@@ -1,0 +1,46 @@
+"""A/B of the pair-level kernels (round-1 thread-contiguous v1 vs warp-interleaved smem-ring v2) with the per-phase split,
+plus the scratch-group budget and the small sizes: python tools/ab_v2.py   (run on the GPU box)"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import numpy as np, torch
+from snarkvm_b200 import _lib, device
+
+def run(fn, reps):
+    fn(); torch.cuda.synchronize()
+    _lib.profile_enable(True)
+    for k in range(4): _lib.profile_collect(k)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    ph = [_lib.profile_collect(k)[0] / reps for k in range(3)]
+    _lib.profile_enable(False)
+    return e0.elapsed_time(e1) / reps, ph
+
+rng = np.random.default_rng(0)
+sizes = [int(a) for a in sys.argv[1:]] or [24, 22, 20]
+for lg in sizes:
+    n = 1 << lg
+    bases = device.generate_bases(n, 7)
+    s = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64); s[:, 3] &= np.uint64((1 << 60) - 1)
+    scal = torch.from_numpy(s.view(np.int64)).cuda()
+    ref = None
+    for tag, env in (("v1", {"SNARKVM_B200_MSM_PAIR_V1": "1"}), ("v2", {}), ("v2 40GB groups", {"SNARKVM_B200_MSM_SCRATCH_GB": "40"}),
+                     ("v2 L5", {"SNARKVM_B200_MSM_LEVELS": "5"}), ("v2 L6", {"SNARKVM_B200_MSM_LEVELS": "6"}), ("v2 c+1", {"SNARKVM_B200_MSM_C": str(device.msm_plan(n)["c"] + 1)})):
+        for k in ("SNARKVM_B200_MSM_PAIR_V1", "SNARKVM_B200_MSM_SCRATCH_GB", "SNARKVM_B200_MSM_LEVELS", "SNARKVM_B200_MSM_C"): os.environ.pop(k, None)
+        os.environ.update(env)
+        got = device.msm(bases, scal)
+        if ref is None: ref = got
+        ms, ph = run(lambda: device.msm(bases, scal), 3 if lg >= 24 else 8)
+        print(f"lg={lg} {tag:16s} {ms:8.2f} ms  sort {ph[0]:6.2f}  accumulate {ph[1]:7.2f}  reduce {ph[2]:6.2f}  {'ok' if (got == ref).all() else 'MISMATCH'}", flush=True)
+    for k in ("SNARKVM_B200_MSM_PAIR_V1", "SNARKVM_B200_MSM_SCRATCH_GB", "SNARKVM_B200_MSM_LEVELS", "SNARKVM_B200_MSM_C"): os.environ.pop(k, None)
+    del bases, scal
+    torch.cuda.empty_cache()
+for lg in (12, 14, 16, 18):
+    n = 1 << lg
+    bases = device.generate_bases(n, 7)
+    s = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64); s[:, 3] &= np.uint64((1 << 60) - 1)
+    scal = torch.from_numpy(s.view(np.int64)).cuda()
+    ms, ph = run(lambda: device.msm(bases, scal), 20)
+    print(f"lg={lg} default          {ms:8.3f} ms  sort {ph[0]:6.3f}  accumulate {ph[1]:7.3f}  reduce {ph[2]:6.3f}", flush=True)
+print("scratch:", device.msm_scratch_stats())
