@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
 __global__ void k_items_per_bucket(const uint32_t* __restrict__ hist, uint32_t* __restrict__ items, uint32_t total_buckets, uint32_t cap) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < total_buckets) items[i] = (hist[i] + cap - 1u) / cap;
+    else if (i == total_buckets) items[i] = 0;
 }
 
 // A dense base record: x, y (Montgomery) in one 128-byte line, infinity encoded as (0, 0) — written by k_densify_bases
