@@ -77,6 +77,27 @@ golden["varuna_circuit_0_domain"] = {
               "algorithms/src/snark/varuna/tests.rs:533-809): elements ω^i of the size-8/4/… domains, decimal",
     **dom,
 }
+# Varuna prover known-answer vectors (the only reference-held vectors that pin iFFT / FFT / polymul / division OUTPUTS)
+base = "algorithms/src/snark/varuna/resources/circuit_0"
+kat = {"source": base + "/{polynomials/*.txt, *.input} — test_varuna_with_prover_test_vectors (algorithms/src/snark/varuna/tests.rs:623-803): "
+                 "7×7 TestCircuit (mul_depth 3), VarunaNonHidingMode, fixed challenges; polynomial coefficients in decimal, low degree first"}
+for name in ("w_lde", "z_lde", "h_0", "g_1", "h_1", "g_a", "g_b", "g_c", "h_2"):
+    txt = read(f"{base}/polynomials/{name}.txt")
+    kat[name] = [s.strip() for s in txt.strip().strip("[]").split(",")]
+kat["challenges"] = read(f"{base}/challenges.input").split()
+wit = read(f"{base}/witness.input").strip().splitlines()
+kat["witness_a_b"] = json.loads(wit[0])
+kat["full_assignment"] = json.loads(wit[1])
+inst = read(f"{base}/instance.input").split("\n")
+mats, cur = {}, None
+for line in inst:
+    line = line.strip()
+    if line in ("A", "B", "C"):
+        cur = line; mats[cur] = []
+    elif line:
+        mats[cur].append([int(t) for t in line.rstrip(",").split(",")])
+kat["instance"] = mats
+golden["varuna_circuit_0_prover"] = kat
 with open(os.path.join(OUT, "reference_constants.json"), "w") as f:
     json.dump(golden, f, indent=1)
 

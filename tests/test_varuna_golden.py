@@ -1,0 +1,82 @@
+"""The Varuna prover oracle (oracle/varuna.py) against the reference's OWN golden vectors:
+resources/circuit_0/polynomials/{w_lde,z_lde,h_0,g_1,h_1,g_a,g_b,g_c,h_2}.txt, produced and checked by the reference's
+test_varuna_with_prover_test_vectors (algorithms/src/snark/varuna/tests.rs:623-803) for the 7×7 TestCircuit with witness
+(a, b) = (2, 4), VarunaNonHidingMode and the fixed challenges of challenges.input.  These are the only reference-held vectors that
+pin iFFT / FFT / PolyMultiplier / divide_by_vanishing_poly / batch_inversion_and_mul / Lagrange-coefficient OUTPUTS, so they pin
+every next-row oracle the f1–f3 parity tests rely on."""
+import numpy as np
+import pytest
+
+from oracle import bls12_377 as py
+from oracle import varuna as ov
+
+
+@pytest.fixture(scope="module")
+def kat(golden):
+    return golden["varuna_circuit_0_prover"]
+
+
+@pytest.fixture(scope="module")
+def proved(kat):
+    a, b = kat["witness_a_b"]
+    cs = ov.test_circuit(a, b, mul_depth=3, num_constraints=7, num_variables=7)
+    circuit = ov.Circuit(ov.test_circuit(a, b, 3, 7, 7))
+    prover = ov.Prover(circuit, [cs])
+    ch = [int(x) for x in kat["challenges"]]
+    alpha, _eta_a, eta_b, eta_c, beta, delta_a, delta_b, delta_c, _gamma = ch
+    prover.first_round()
+    prover.assignments()
+    prover.second_round()
+    prover.third_round(alpha, eta_b, eta_c)
+    prover.fourth_round(alpha, beta)
+    prover.fifth_round([delta_a, delta_b, delta_c])
+    return circuit, prover
+
+
+def ints(v):
+    return [int(x) for x in v]
+
+
+def test_instance_matrices_and_assignment(kat, proved):
+    circuit, prover = proved
+    for name, m in zip("ABC", (circuit.a, circuit.b, circuit.c)):
+        dense = [[0] * 7 for _ in range(7)]
+        for i, row in enumerate(m):
+            for val, col in row:
+                dense[i][col] = val
+        assert dense == kat["instance"][name], name
+    assert prover.public[0] + prover.private[0] == kat["full_assignment"]
+    assert (circuit.constraint_domain.size, circuit.variable_domain.size, circuit.input_domain.size) == (8, 8, 4)
+    assert [d.size for d in circuit.non_zero_domains] == [8, 8, 8]
+
+
+def test_domain_elements(golden, proved):
+    circuit, _ = proved
+    dom = golden["varuna_circuit_0_domain"]
+    assert circuit.constraint_domain.elements() == ints(dom["R"])
+    assert circuit.variable_domain.elements() == ints(dom["C"])
+    assert circuit.max_non_zero_domain.elements() == ints(dom["K"])
+
+
+def test_round_polynomials_match_reference_vectors(kat, proved):
+    _, p = proved
+    assert p.w_polys[0] == ints(kat["w_lde"])
+    assert p.z_polys[0] == ints(kat["z_lde"])
+    assert p.h_0 == ints(kat["h_0"])
+    assert p.g_1 == ints(kat["g_1"])
+    assert p.h_1 == ints(kat["h_1"])
+    assert p.gs[0] == ints(kat["g_a"])
+    assert p.gs[1] == ints(kat["g_b"])
+    # the reference test writes g_b into g_c.txt (tests.rs:736: `g_c = format!(…gm_polys.g_b…)`), so that file pins g_b again
+    assert p.gs[1] == ints(kat["g_c"])
+    assert p.h_2 == ints(kat["h_2"])
+
+
+def test_matrix_sumcheck_identities(kat, proved):
+    """what the verifier checks for round 4: with f = sum + X·g, a − b·f is divisible by v_K and the quotient is lhs"""
+    circuit, p = proved
+    for g, lhs_k, sm, a_poly, b_poly, arith in zip(p.gs, p.lhs, p.fourth_sums, p.a_polys, p.b_polys, circuit.ariths):
+        f = [sm] + g
+        h = ov.poly_sub(a_poly, ov.poly_mul(b_poly, f))
+        q, r = ov.divide_by_vanishing_poly(h, arith.domain)
+        assert r == [] and q == lhs_k
