@@ -464,48 +464,57 @@ FF_DEV Fq ring_fq(const uint4* slot) {                       // slot = &ring[(st
     return r;
 }
 
+// Output descriptors, written once per level by k_pair_desc (one thread per output, warp-coherent binary search for the
+// bucket) so that the pair kernel never chases off_out → off_in → sorted in its instruction stream: it reads 8 bytes per
+// output, coalesced, two steps ahead.
+//   level 0:  p, q = the two sorted entries (point index | sign << 31); q = NONE when the output has a single input
+//   above:    p = index of the first input in dense_in; q = NONE / anything else
+static constexpr uint32_t PAIR_NONE = 0xffffffffu;
+template <bool GATHER>
+__global__ void __launch_bounds__(256) k_pair_desc(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off_in,
+                                                   const uint32_t* __restrict__ off_out, uint32_t total_buckets, uint2* __restrict__ desc) {
+    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= __ldg(off_out + total_buckets)) return;
+    uint32_t lo = 0, hi = total_buckets;                  // off_out[lo] <= o < off_out[hi]
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (__ldg(off_out + mid) <= o) lo = mid; else hi = mid; }
+    const uint32_t i = o - __ldg(off_out + lo), base_in = __ldg(off_in + lo), cnt = __ldg(off_in + lo + 1) - base_in;
+    const uint32_t idx = base_in + 2u * i;
+    const bool has2 = 2u * i + 1u < cnt;
+    uint2 d;
+    if (GATHER) { d.x = __ldg(sorted + idx); d.y = has2 ? __ldg(sorted + idx + 1) : PAIR_NONE; }
+    else { d.x = idx; d.y = has2 ? 0u : PAIR_NONE; }
+    desc[o] = d;
+}
+
 struct PairDesc {            // one lane's output of one step
-    uint32_t idx;            // position of the first input (in `sorted` at level 0, in dense_in above)
-    uint32_t eP, eQ;         // level 0: sorted entries (point index | sign << 31)
+    uint32_t p, q;           // as written by k_pair_desc
     uint32_t flags;          // bit 0: output exists, bit 1: it has a second input
 };
-
-template <bool GATHER>
-FF_DEV PairDesc pair_make_desc(int64_t j, uint32_t T, uint32_t W0, uint32_t W1, int lane, uint32_t& b,
-                               const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off_in,
-                               const uint32_t* __restrict__ off_out) {
-    PairDesc d; d.idx = 0; d.eP = 0; d.eQ = 0; d.flags = 0;
-    if (j < 0 || j >= (int64_t)T) return d;
+FF_DEV PairDesc pair_load_desc(int64_t j, uint32_t j0, uint32_t j1, uint32_t W0, uint32_t W1, int lane, const uint2* __restrict__ desc) {
+    PairDesc d; d.p = 0; d.q = 0; d.flags = 0;
+    if (j < (int64_t)j0 || j >= (int64_t)j1) return d;
     const uint64_t o64 = (uint64_t)W0 + 32ull * (uint64_t)j + (uint32_t)lane;
     if (o64 >= W1) return d;
-    const uint32_t o = (uint32_t)o64;
-    while (o >= __ldg(off_out + b + 1)) b++;
-    while (o < __ldg(off_out + b)) b--;
-    const uint32_t i = o - __ldg(off_out + b), base_in = __ldg(off_in + b), cnt = __ldg(off_in + b + 1) - base_in;
-    d.idx = base_in + 2u * i;
-    d.flags = 1u | ((2u * i + 1u < cnt) ? 2u : 0u);
-    if (GATHER) {
-        d.eP = __ldg(sorted + d.idx);
-        if (d.flags & 2u) d.eQ = __ldg(sorted + d.idx + 1);
-    }
+    const uint2 v = __ldg(desc + o64);
+    d.p = v.x; d.q = v.y;
+    d.flags = 1u | (v.y != PAIR_NONE ? 2u : 0u);
     return d;
 }
 template <bool GATHER>
-FF_DEV const uint32_t* pair_src(const PairDesc& d, int which, const uint32_t* __restrict__ dense_bases, const uint32_t* __restrict__ dense_in) {
-    if (GATHER) return dense_bases + (size_t)((which ? d.eQ : d.eP) & 0x7fffffffu) * BASE_WORDS;
-    return dense_in + (size_t)(d.idx + (uint32_t)which) * DENSE_WORDS;
+FF_DEV const uint32_t* pair_src(const PairDesc& d, int which, const uint32_t* __restrict__ records) {
+    if (GATHER) return records + (size_t)((which ? d.q : d.p) & 0x7fffffffu) * BASE_WORDS;
+    return records + (size_t)(d.p + (uint32_t)which) * DENSE_WORDS;
 }
 // copies of step operands into ring stage `st` (forward: x1, x2; backward: all four coordinates)
 template <bool GATHER, bool FULL>
-FF_DEV void pair_issue(const PairDesc& d, uint4* ring, int st, int lane, const uint32_t* __restrict__ dense_bases,
-                       const uint32_t* __restrict__ dense_in) {
+FF_DEV void pair_issue(const PairDesc& d, uint4* ring, int st, int lane, const uint32_t* __restrict__ records) {
     if (d.flags & 1u) {
         const uint32_t dst = smem_addr_u32(ring + (size_t)st * RING_STAGE_U4 + lane);
-        const uint32_t* p = pair_src<GATHER>(d, 0, dense_bases, dense_in);
+        const uint32_t* p = pair_src<GATHER>(d, 0, records);
 #pragma unroll
         for (int k = 0; k < (FULL ? 6 : 3); k++) cp_async16(dst + (uint32_t)k * 512u, p + 4 * k);
         if (d.flags & 2u) {
-            const uint32_t* q = pair_src<GATHER>(d, 1, dense_bases, dense_in);
+            const uint32_t* q = pair_src<GATHER>(d, 1, records);
 #pragma unroll
             for (int k = 0; k < (FULL ? 6 : 3); k++) cp_async16(dst + (uint32_t)(6 + k) * 512u, q + 4 * k);
         }
@@ -514,133 +523,177 @@ FF_DEV void pair_issue(const PairDesc& d, uint4* ring, int st, int lane, const u
 }
 // full classification of one pair from global memory (rare path of the forward pass: equal x, or an x that is 0)
 template <bool GATHER>
-FF_DEV int pair_classify_global(const PairDesc& d, const uint32_t* __restrict__ dense_bases, const uint32_t* __restrict__ dense_in, Fq& den) {
-    DensePoint P = load_dense(pair_src<GATHER>(d, 0, dense_bases, dense_in));
-    DensePoint Q = load_dense(pair_src<GATHER>(d, 1, dense_bases, dense_in));
-    if (GATHER) { if ((d.eP >> 31) && !P.inf) P.y = P.y.neg(); if ((d.eQ >> 31) && !Q.inf) Q.y = Q.y.neg(); }
+FF_DEV int pair_classify_global(const PairDesc& d, const uint32_t* __restrict__ records, Fq& den) {
+    DensePoint P = load_dense(pair_src<GATHER>(d, 0, records));
+    DensePoint Q = load_dense(pair_src<GATHER>(d, 1, records));
+    if (GATHER) { if ((d.p >> 31) && !P.inf) P.y = P.y.neg(); if ((d.q >> 31) && !Q.inf) Q.y = Q.y.neg(); }
     return classify_pair(P, Q, true, den);
 }
 
+// One Fermat inversion per CTA (see cta_shared_inverse above), here with the inverting warp chosen by the caller.
+__device__ __noinline__ Fq cta_shared_inverse_by(const Fq& run, uint32_t* sh, int inv_warp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    run.store(sh + tid * 12);
+    __syncthreads();
+    if (warp == inv_warp) {
+        uint32_t* mine = sh + lane * 48;
+        Fq a0 = Fq::load(mine), a1 = Fq::load(mine + 12), a2 = Fq::load(mine + 24), a3 = Fq::load(mine + 36);
+        Fq p1 = a0 * a1, p2 = p1 * a2, p3 = p2 * a3;
+        Fq incl = p3, suff = p3;                           // inclusive prefix / suffix products over lanes
+#pragma unroll 1
+        for (int d = 1; d < 32; d <<= 1) {
+            Fq up = shfl_up_fq(incl, d), dn = shfl_down_fq(suff, d);
+            if (lane >= d) incl = incl * up;
+            if (lane + d < 32) suff = suff * dn;
+        }
+        Fq tinv = shfl_idx_fq(incl, 31).inverse();
+        Fq before = shfl_up_fq(incl, 1), after = shfl_down_fq(suff, 1);
+        Fq ip3 = tinv;                                     // 1 / p3 of this lane = tinv · Π(other lanes)
+        if (lane > 0) ip3 = ip3 * before;
+        if (lane < 31) ip3 = ip3 * after;
+        Fq ip2 = ip3 * a3, ip1 = ip2 * a2;
+        (ip3 * p2).store(mine + 36);                       // 1/a3
+        (ip2 * p1).store(mine + 24);                       // 1/a2
+        (ip1 * a0).store(mine + 12);                       // 1/a1
+        (ip1 * a1).store(mine);                            // 1/a0
+    }
+    __syncthreads();
+    return Fq::load(sh + tid * 12);
+}
+
+// The shared inversion is a bubble: one warp runs ≈ 570 dependent multiplications while the CTA's other warps wait at the
+// barrier, and CTAs that start together reach it together (ncu, round 2: 16 % of every warp's cycles at that barrier, with
+// the four inverting warps of an SM all on the same sub-partition).  Two measures:
+//   * every CTA takes a slot number from a per-SM counter: slot & 3 names the inverting warp, so the (up to) four CTAs
+//     resident on an SM invert on four different sub-partitions whatever the block → SM mapping is;
+//   * every CTA runs its T steps as TWO parts split at (2·slot + 1)/8 of the range, so co-resident CTAs reach their
+//     inversions at different times and the other three keep the multiplier busy meanwhile.
 template <bool GATHER>
-__global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair_level2(const uint32_t* __restrict__ dense_bases,
-                                                         const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ dense_in,
-                                                         const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out,
-                                                         uint32_t total_buckets, uint32_t T, uint32_t* __restrict__ prefix,
-                                                         uint32_t* __restrict__ dense_out) {
+__global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair_level2(const uint32_t* __restrict__ records /* level 0: dense bases / table; above: dense_in */,
+                                                         const uint2* __restrict__ desc, const uint32_t* __restrict__ total_ptr,
+                                                         uint32_t T, uint32_t* __restrict__ prefix, uint32_t* __restrict__ dense_out,
+                                                         uint32_t* __restrict__ sm_slots) {
     extern __shared__ uint4 pair2_smem[];
+    __shared__ uint32_t sh_slot;
     uint32_t* sh_inv = reinterpret_cast<uint32_t*>(pair2_smem);                       // 128 × 48 B
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4* ring = pair2_smem + PAIR_THREADS * 3 + (size_t)warp * 2 * RING_STAGE_U4;    // this warp's two stages
-    const uint32_t total = __ldg(off_out + total_buckets);
+    if (threadIdx.x == 0) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        sh_slot = atomicAdd(sm_slots + (smid & 255u), 1u);
+    }
+    __syncthreads();
+    const uint32_t slot = sh_slot & 3u;
+    const uint32_t total = __ldg(total_ptr);
     const uint64_t w0_64 = ((uint64_t)blockIdx.x * (PAIR_THREADS / 32) + (uint32_t)warp) * 32ull * T;
     const uint32_t W0 = w0_64 < total ? (uint32_t)w0_64 : total;
     const uint32_t W1 = (w0_64 + 32ull * T < total) ? (uint32_t)(w0_64 + 32ull * T) : total;
-    uint32_t b = 0;
-    if ((uint64_t)W0 + (uint32_t)lane < W1) {                                          // bucket of this lane's first output
-        const uint32_t o = W0 + (uint32_t)lane;
-        uint32_t lo = 0, hi = total_buckets;
-        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (__ldg(off_out + mid) <= o) lo = mid; else hi = mid; }
-        b = lo;
-    }
+    const uint32_t Ta = (uint32_t)(((uint64_t)T * (2u * slot + 1u)) >> 3);
 
-    // ---------------- forward: running product of the denominators ----------------
-    Fq run = Fq::one();
-    {
-        PairDesc cur = pair_make_desc<GATHER>(0, T, W0, W1, lane, b, sorted, off_in, off_out);
-        pair_issue<GATHER, false>(cur, ring, 0, lane, dense_bases, dense_in);
-        PairDesc nxt = pair_make_desc<GATHER>(1, T, W0, W1, lane, b, sorted, off_in, off_out);
-        for (uint32_t j = 0; j < T; j++) {
-            PairDesc nn = pair_make_desc<GATHER>((int64_t)j + 2, T, W0, W1, lane, b, sorted, off_in, off_out);
-            pair_issue<GATHER, false>(nxt, ring, (int)((j + 1) & 1u), lane, dense_bases, dense_in);
-            cp_async_wait_1();
-            Fq d = Fq::one();
-            if (cur.flags & 2u) {
-                const uint4* slot = ring + (size_t)(j & 1u) * RING_STAGE_U4 + lane;
-                Fq x1 = ring_fq(slot), x2 = ring_fq(slot + 6 * 32);
-                if (x1 == x2 || x1.is_zero() || x2.is_zero()) {
-                    Fq den;
-                    if (pair_classify_global<GATHER>(cur, dense_bases, dense_in, den) >= PAIR_ADD) d = den;
-                } else {
-                    d = x2 - x1;
-                }
-            }
-            run = run * d;
-            if (cur.flags & 1u) run.store(prefix + ((size_t)W0 + 32ull * j + (uint32_t)lane) * 12);
-            cur = nxt; nxt = nn;
-        }
-        cp_async_wait_0();
-    }
-    Fq inv = cta_shared_inverse(run, sh_inv);
-    // ---------------- backward: one inverse per pair, then the affine addition ----------------
-    {
-        PairDesc cur = pair_make_desc<GATHER>((int64_t)T - 1, T, W0, W1, lane, b, sorted, off_in, off_out);
-        pair_issue<GATHER, true>(cur, ring, 0, lane, dense_bases, dense_in);
-        PairDesc nxt = pair_make_desc<GATHER>((int64_t)T - 2, T, W0, W1, lane, b, sorted, off_in, off_out);
-        for (uint32_t k = 0; k < T; k++) {
-            const uint32_t j = T - 1 - k;
-            PairDesc nn = pair_make_desc<GATHER>((int64_t)j - 2, T, W0, W1, lane, b, sorted, off_in, off_out);
-            pair_issue<GATHER, true>(nxt, ring, (int)((k + 1) & 1u), lane, dense_bases, dense_in);
-            const size_t o = (size_t)W0 + 32ull * j + (uint32_t)lane;
-            Fq pf = Fq::one();
-            if ((cur.flags & 1u) && j != 0) pf = Fq::load(prefix + (o - 32) * 12);          // behind the first multiplication
-            cp_async_wait_1();
-            const uint4* slot = ring + (size_t)(k & 1u) * RING_STAGE_U4 + lane;
-            // classify (same decisions as the forward pass)
-            int kind = PAIR_COPY1;
-            Fq d = Fq::one(), num = Fq::zero();
-            const bool negP = GATHER && (cur.eP >> 31), negQ = GATHER && (cur.eQ >> 31);
-            if (cur.flags & 2u) {
-                Fq x1 = ring_fq(slot), x2 = ring_fq(slot + 6 * 32);
-                if (x1 == x2 || x1.is_zero() || x2.is_zero()) {
-                    DensePoint P, Q;
-                    P.x = x1; P.y = ring_fq(slot + 3 * 32); P.inf = P.x.is_zero() && P.y.is_zero();
-                    Q.x = x2; Q.y = ring_fq(slot + 9 * 32); Q.inf = Q.x.is_zero() && Q.y.is_zero();
-                    if (negP && !P.inf) P.y = P.y.neg();
-                    if (negQ && !Q.inf) Q.y = Q.y.neg();
-                    Fq den;
-                    kind = classify_pair(P, Q, true, den);
-                    if (kind >= PAIR_ADD) d = den;
-                    if (kind == PAIR_ADD) num = Q.y - P.y;
-                    else if (kind == PAIR_DBL) { Fq xx = P.x.sqr(); num = xx.dbl() + xx; }
-                } else {
-                    kind = PAIR_ADD;
-                    d = x2 - x1;
-                    Fq y1 = ring_fq(slot + 3 * 32), y2 = ring_fq(slot + 9 * 32);
-                    if (negP) y1 = y1.neg();
-                    if (negQ) y2 = y2.neg();
-                    num = y2 - y1;
-                }
-            }
-            Fq inv_next = inv * d;
-            Fq inv_d = (j != 0) ? inv * pf : inv;
-            inv = inv_next;
-            Fq lambda = num * inv_d;
-            Fq x3 = lambda.sqr();
-            {
-                Fq x1 = ring_fq(slot), x2 = (cur.flags & 2u) ? ring_fq(slot + 6 * 32) : x1;
-                x3 = x3 - x1 - x2;
-                Fq t = x1 - x3;
-                Fq y3 = lambda * t;
-                if (cur.flags & 1u) {
-                    DensePoint R;
-                    if (kind >= PAIR_ADD) {
-                        Fq y1 = ring_fq(slot + 3 * 32);
-                        if (negP) y1 = y1.neg();
-                        R.x = x3; R.y = y3 - y1; R.inf = false;
-                    } else if (kind == PAIR_INF) {
-                        R.inf = true; R.x = Fq::zero(); R.y = Fq::zero();
+    for (int part = 0; part < 2; part++) {
+        const uint32_t j0 = part ? Ta : 0u, j1 = part ? T : Ta;       // steps of this part (uniform over the CTA)
+        if (j0 == j1) continue;
+        // ---------------- forward: running product of the denominators ----------------
+        Fq run = Fq::one();
+        {
+            PairDesc cur = pair_load_desc(j0, j0, j1, W0, W1, lane, desc);
+            pair_issue<GATHER, false>(cur, ring, 0, lane, records);
+            PairDesc nxt = pair_load_desc((int64_t)j0 + 1, j0, j1, W0, W1, lane, desc);
+            for (uint32_t j = j0; j < j1; j++) {
+                const uint32_t k = j - j0;
+                PairDesc nn = pair_load_desc((int64_t)j + 2, j0, j1, W0, W1, lane, desc);
+                pair_issue<GATHER, false>(nxt, ring, (int)((k + 1) & 1u), lane, records);
+                cp_async_wait_1();
+                Fq d = Fq::one();
+                if (cur.flags & 2u) {
+                    const uint4* slot_p = ring + (size_t)(k & 1u) * RING_STAGE_U4 + lane;
+                    Fq x1 = ring_fq(slot_p), x2 = ring_fq(slot_p + 6 * 32);
+                    if (x1 == x2 || x1.is_zero() || x2.is_zero()) {
+                        Fq den;
+                        if (pair_classify_global<GATHER>(cur, records, den) >= PAIR_ADD) d = den;
                     } else {
-                        const int c0 = (kind == PAIR_COPY2) ? 6 : 0;
-                        R.x = ring_fq(slot + c0 * 32); R.y = ring_fq(slot + (c0 + 3) * 32);
-                        R.inf = R.x.is_zero() && R.y.is_zero();
-                        if (((kind == PAIR_COPY2) ? negQ : negP) && !R.inf) R.y = R.y.neg();
+                        d = x2 - x1;
                     }
-                    store_dense(dense_out + o * DENSE_WORDS, R);
                 }
+                run = run * d;
+                if (cur.flags & 1u) run.store(prefix + ((size_t)W0 + 32ull * j + (uint32_t)lane) * 12);
+                cur = nxt; nxt = nn;
             }
-            cur = nxt; nxt = nn;
+            cp_async_wait_0();
         }
-        cp_async_wait_0();
+        Fq inv = cta_shared_inverse_by(run, sh_inv, (int)slot);
+        // ---------------- backward: one inverse per pair, then the affine addition ----------------
+        {
+            PairDesc cur = pair_load_desc((int64_t)j1 - 1, j0, j1, W0, W1, lane, desc);
+            pair_issue<GATHER, true>(cur, ring, 0, lane, records);
+            PairDesc nxt = pair_load_desc((int64_t)j1 - 2, j0, j1, W0, W1, lane, desc);
+            for (uint32_t k = 0; k < j1 - j0; k++) {
+                const uint32_t j = j1 - 1 - k;
+                PairDesc nn = pair_load_desc((int64_t)j - 2, j0, j1, W0, W1, lane, desc);
+                pair_issue<GATHER, true>(nxt, ring, (int)((k + 1) & 1u), lane, records);
+                const size_t o = (size_t)W0 + 32ull * j + (uint32_t)lane;
+                Fq pf = Fq::one();
+                if ((cur.flags & 1u) && j != j0) pf = Fq::load(prefix + (o - 32) * 12);         // behind the first multiplication
+                cp_async_wait_1();
+                const uint4* slot_p = ring + (size_t)(k & 1u) * RING_STAGE_U4 + lane;
+                // classify (same decisions as the forward pass)
+                int kind = PAIR_COPY1;
+                Fq d = Fq::one(), num = Fq::zero();
+                const bool negP = GATHER && (cur.p >> 31), negQ = GATHER && (cur.q >> 31);
+                if (cur.flags & 2u) {
+                    Fq x1 = ring_fq(slot_p), x2 = ring_fq(slot_p + 6 * 32);
+                    if (x1 == x2 || x1.is_zero() || x2.is_zero()) {
+                        DensePoint P, Q;
+                        P.x = x1; P.y = ring_fq(slot_p + 3 * 32); P.inf = P.x.is_zero() && P.y.is_zero();
+                        Q.x = x2; Q.y = ring_fq(slot_p + 9 * 32); Q.inf = Q.x.is_zero() && Q.y.is_zero();
+                        if (negP && !P.inf) P.y = P.y.neg();
+                        if (negQ && !Q.inf) Q.y = Q.y.neg();
+                        Fq den;
+                        kind = classify_pair(P, Q, true, den);
+                        if (kind >= PAIR_ADD) d = den;
+                        if (kind == PAIR_ADD) num = Q.y - P.y;
+                        else if (kind == PAIR_DBL) { Fq xx = P.x.sqr(); num = xx.dbl() + xx; }
+                    } else {
+                        kind = PAIR_ADD;
+                        d = x2 - x1;
+                        Fq y1 = ring_fq(slot_p + 3 * 32), y2 = ring_fq(slot_p + 9 * 32);
+                        // (±y2) − (±y1) without negating first: one subtraction or one addition, then at most one negation
+                        if (negP == negQ) { num = y2 - y1; if (negP) num = num.neg(); }
+                        else { num = y2 + y1; if (negQ) num = num.neg(); }
+                    }
+                }
+                Fq inv_next = inv * d;
+                Fq inv_d = (j != j0) ? inv * pf : inv;
+                inv = inv_next;
+                Fq lambda = num * inv_d;
+                Fq x3 = lambda.sqr();
+                {
+                    Fq x1 = ring_fq(slot_p), x2 = (cur.flags & 2u) ? ring_fq(slot_p + 6 * 32) : x1;
+                    x3 = x3 - x1 - x2;
+                    Fq t = x1 - x3;
+                    Fq y3 = lambda * t;
+                    if (cur.flags & 1u) {
+                        DensePoint R;
+                        if (kind >= PAIR_ADD) {
+                            Fq y1 = ring_fq(slot_p + 3 * 32);
+                            R.x = x3; R.y = negP ? y3 + y1 : y3 - y1; R.inf = false;           // y3 − (±y1)
+                        } else if (kind == PAIR_INF) {
+                            R.inf = true; R.x = Fq::zero(); R.y = Fq::zero();
+                        } else {
+                            const int c0 = (kind == PAIR_COPY2) ? 6 : 0;
+                            R.x = ring_fq(slot_p + c0 * 32); R.y = ring_fq(slot_p + (c0 + 3) * 32);
+                            R.inf = R.x.is_zero() && R.y.is_zero();
+                            if (((kind == PAIR_COPY2) ? negQ : negP) && !R.inf) R.y = R.y.neg();
+                        }
+                        store_dense(dense_out + o * DENSE_WORDS, R);
+                    }
+                }
+                cur = nxt; nxt = nn;
+            }
+            cp_async_wait_0();
+        }
+        __syncthreads();        // the shared-inversion words and the ring are reused by the next part
     }
 }
 
@@ -922,10 +975,13 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
     if (const char* e = getenv("SNARKVM_B200_MSM_SCRATCH_GB")) { long v = atol(e); if (v >= 1) budget = (size_t)v << 30; }
     uint32_t gw = nsets;
     if (levels > 0) {
-        size_t per_set = set_cap * (size_t)100 + 1;
+        size_t per_set = set_cap * (size_t)104 + 1;          // dense_a 48 + dense_b 24 + prefix 24 + descriptors 4, +4 sorted
         size_t fit = budget / per_set;
         if (fit < 1) fit = 1;
-        if (fit < gw) gw = (uint32_t)fit;
+        if (fit < gw) {
+            const uint32_t ngroups = (uint32_t)((nsets + fit - 1) / fit);          // equal groups (15 sets in 3 groups: 5 + 5 + 5, not 7 + 7 + 1)
+            gw = (nsets + ngroups - 1) / ngroups;
+        }
     }
     const uint32_t TBg = gw * plan.nbuckets;                      // buckets of the largest group
     size_t entries_g = set_cap * (size_t)gw;                      // most entries a group can hold
@@ -960,7 +1016,8 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
 
     // ---- one scratch block, carved up ----
     uint32_t *hist, *bucket_start, *cursors, *items, *item_start, *items2, *sorted, *partial, *partial2, *red_a, *red_b;
-    uint32_t *off_a = nullptr, *off_b = nullptr, *dense_a = nullptr, *dense_b = nullptr, *prefix = nullptr, *dense_bases = nullptr;
+    uint32_t *off_a = nullptr, *off_b = nullptr, *dense_a = nullptr, *dense_b = nullptr, *prefix = nullptr, *dense_bases = nullptr, *sm_slots = nullptr;
+    uint2* desc = nullptr;
     uint8_t* cub_tmp;
     Arena ar;
     auto layout = [&](Arena& a) {
@@ -983,6 +1040,8 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
             dense_a = a.take<uint32_t>(dense_cap_a * DENSE_WORDS);
             if (levels > 1) dense_b = a.take<uint32_t>(dense_cap_b * DENSE_WORDS);
             prefix = a.take<uint32_t>(dense_cap_a * 12);
+            desc = a.take<uint2>(dense_cap_a);
+            sm_slots = a.take<uint32_t>(256);
         }
     };
     layout(ar);
@@ -994,6 +1053,7 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
     layout(ar);
 
     CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)(TB + 1) * 4, stream));
+    if (sm_slots) CUDA_TRY(cudaMemsetAsync(sm_slots, 0, 256 * 4, stream));
     {
         // ---- bucket sort of all jobs and windows: histogram → offsets → scatter ----
         {
@@ -1085,10 +1145,15 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
                         else
                             k_pair_level<false><<<lgrid, 128, 0, stream>>>(nullptr, nullptr, dense_in, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
                     } else {
-                        if (l == 0)
-                            k_pair_level2<true><<<lgrid, 128, PAIR2_SMEM, stream>>>(gather_src, sorted, nullptr, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
-                        else
-                            k_pair_level2<false><<<lgrid, 128, PAIR2_SMEM, stream>>>(nullptr, nullptr, dense_in, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
+                        const unsigned dgrid = (unsigned)((bound + 255) / 256);
+                        if (l == 0) {
+                            k_pair_desc<true><<<dgrid, 256, 0, stream>>>(sorted, off_in, off_out, tb, desc);
+                            k_pair_level2<true><<<lgrid, 128, PAIR2_SMEM, stream>>>(gather_src, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots);
+                        } else {
+                            k_pair_desc<false><<<dgrid, 256, 0, stream>>>(nullptr, off_in, off_out, tb, desc);
+                            k_pair_level2<false><<<lgrid, 128, PAIR2_SMEM, stream>>>(dense_in, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots);
+                        }
+                        count_launch(1);
                     }
                     count_launch(3);
                     off_in = off_out;
