@@ -572,7 +572,7 @@ template <bool GATHER>
 __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair_level2(const uint32_t* __restrict__ records /* level 0: dense bases / table; above: dense_in */,
                                                          const uint2* __restrict__ desc, const uint32_t* __restrict__ total_ptr,
                                                          uint32_t T, uint32_t* __restrict__ prefix, uint32_t* __restrict__ dense_out,
-                                                         uint32_t* __restrict__ sm_slots) {
+                                                         uint32_t* __restrict__ sm_slots, int parts) {
     extern __shared__ uint4 pair2_smem[];
     __shared__ uint32_t sh_slot;
     uint32_t* sh_inv = reinterpret_cast<uint32_t*>(pair2_smem);                       // 128 × 48 B
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair_level2(const uint32_t*
     const uint64_t w0_64 = ((uint64_t)blockIdx.x * (PAIR_THREADS / 32) + (uint32_t)warp) * 32ull * T;
     const uint32_t W0 = w0_64 < total ? (uint32_t)w0_64 : total;
     const uint32_t W1 = (w0_64 + 32ull * T < total) ? (uint32_t)(w0_64 + 32ull * T) : total;
-    const uint32_t Ta = (uint32_t)(((uint64_t)T * (2u * slot + 1u)) >> 3);
+    const uint32_t Ta = parts > 1 ? (uint32_t)(((uint64_t)T * (2u * slot + 1u)) >> 3) : T;
 
     for (int part = 0; part < 2; part++) {
         const uint32_t j0 = part ? Ta : 0u, j1 = part ? T : Ta;       // steps of this part (uniform over the CTA)
@@ -993,6 +993,8 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
     if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_WAVES")) { long v = atol(e); if (v >= 1) pair_waves = (size_t)v; }
     bool pair_v1 = false;                        // A/B switch: the round-1 thread-contiguous pair level
     if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_V1")) pair_v1 = atoi(e) != 0;
+    int pair_parts = 2;                          // 2: staggered two-part CTAs (see k_pair_level2); 1: one inversion per CTA
+    if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_PARTS")) { int v = atoi(e); if (v == 1 || v == 2) pair_parts = v; }
     int sm_count = 148;
     {
         static std::once_flag smem_once[64];
@@ -1148,10 +1150,10 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
                         const unsigned dgrid = (unsigned)((bound + 255) / 256);
                         if (l == 0) {
                             k_pair_desc<true><<<dgrid, 256, 0, stream>>>(sorted, off_in, off_out, tb, desc);
-                            k_pair_level2<true><<<lgrid, 128, PAIR2_SMEM, stream>>>(gather_src, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots);
+                            k_pair_level2<true><<<lgrid, 128, PAIR2_SMEM, stream>>>(gather_src, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots, pair_parts);
                         } else {
                             k_pair_desc<false><<<dgrid, 256, 0, stream>>>(nullptr, off_in, off_out, tb, desc);
-                            k_pair_level2<false><<<lgrid, 128, PAIR2_SMEM, stream>>>(dense_in, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots);
+                            k_pair_level2<false><<<lgrid, 128, PAIR2_SMEM, stream>>>(dense_in, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots, pair_parts);
                         }
                         count_launch(1);
                     }

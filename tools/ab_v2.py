@@ -25,15 +25,18 @@ for lg in sizes:
     s = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64); s[:, 3] &= np.uint64((1 << 60) - 1)
     scal = torch.from_numpy(s.view(np.int64)).cuda()
     ref = None
-    for tag, env in (("v1", {"SNARKVM_B200_MSM_PAIR_V1": "1"}), ("v2", {}), ("v2 40GB groups", {"SNARKVM_B200_MSM_SCRATCH_GB": "40"}),
-                     ("v2 L5", {"SNARKVM_B200_MSM_LEVELS": "5"}), ("v2 L6", {"SNARKVM_B200_MSM_LEVELS": "6"}), ("v2 c+1", {"SNARKVM_B200_MSM_C": str(device.msm_plan(n)["c"] + 1)})):
-        for k in ("SNARKVM_B200_MSM_PAIR_V1", "SNARKVM_B200_MSM_SCRATCH_GB", "SNARKVM_B200_MSM_LEVELS", "SNARKVM_B200_MSM_C"): os.environ.pop(k, None)
+    KEYS = ("SNARKVM_B200_MSM_PAIR_V1", "SNARKVM_B200_MSM_SCRATCH_GB", "SNARKVM_B200_MSM_LEVELS", "SNARKVM_B200_MSM_C", "SNARKVM_B200_MSM_PAIR_PARTS")
+    for tag, env in (("v1", {"SNARKVM_B200_MSM_PAIR_V1": "1"}), ("v1 40GB", {"SNARKVM_B200_MSM_PAIR_V1": "1", "SNARKVM_B200_MSM_SCRATCH_GB": "40"}),
+                     ("v3", {}), ("v3 1part", {"SNARKVM_B200_MSM_PAIR_PARTS": "1"}), ("v3 40GB", {"SNARKVM_B200_MSM_SCRATCH_GB": "40"}),
+                     ("v3 40GB 1part", {"SNARKVM_B200_MSM_SCRATCH_GB": "40", "SNARKVM_B200_MSM_PAIR_PARTS": "1"}),
+                     ("v3 L5", {"SNARKVM_B200_MSM_LEVELS": "5"})):
+        for k in KEYS: os.environ.pop(k, None)
         os.environ.update(env)
         got = device.msm(bases, scal)
         if ref is None: ref = got
         ms, ph = run(lambda: device.msm(bases, scal), 3 if lg >= 24 else 8)
         print(f"lg={lg} {tag:16s} {ms:8.2f} ms  sort {ph[0]:6.2f}  accumulate {ph[1]:7.2f}  reduce {ph[2]:6.2f}  {'ok' if (got == ref).all() else 'MISMATCH'}", flush=True)
-    for k in ("SNARKVM_B200_MSM_PAIR_V1", "SNARKVM_B200_MSM_SCRATCH_GB", "SNARKVM_B200_MSM_LEVELS", "SNARKVM_B200_MSM_C"): os.environ.pop(k, None)
+    for k in KEYS: os.environ.pop(k, None)
     del bases, scal
     torch.cuda.empty_cache()
 for lg in (12, 14, 16, 18):
