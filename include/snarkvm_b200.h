@@ -221,6 +221,10 @@ SNARKVM_API int snarkvm_b200_register_bases_precomputed(const void* host_points,
 SNARKVM_API int snarkvm_b200_profile_enable(int on);
 SNARKVM_API int snarkvm_b200_profile_collect(int kind, double* total_ms, uint64_t* count);
 
+/* Device self-test of the warp-cooperative Fq multiplication / inversion used by the CTA-shared inversions: nwarps pseudo-random cases
+ * (plus 0, 1, q - 1 and a long-carry value) checked against the per-thread multiplier; *mismatches (HOST) = failing cases. */
+SNARKVM_API int snarkvm_b200_selftest_coop(uint32_t nwarps, uint64_t seed, uint32_t* mismatches, void* stream);
+
 /* Deterministic synthetic bases P_i = h(seed, i) * G written in the reference affine layout. */
 SNARKVM_API int snarkvm_b200_generate_bases_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, void* stream);
 

@@ -29,7 +29,7 @@ SYMBOLS = (
     "snarkvm_b200_fr_vec_op_device", "snarkvm_b200_fr_vec_scalar_op_device", "snarkvm_b200_domain_elements_device",
     "snarkvm_b200_register_bases_precomputed",
     "snarkvm_b200_msm_batch_device", "snarkvm_b200_msm_window_sums_plan_device", "snarkvm_b200_kzg_commit_batch_hiding_device",
-    "snarkvm_b200_kzg_commit_batch_precomputed_device", "snarkvm_b200_msm_scratch_stats", "snarkvm_b200_msm_set_scratch_limit", "snarkvm_b200_msm_window_sums_host",
+    "snarkvm_b200_kzg_commit_batch_precomputed_device", "snarkvm_b200_msm_scratch_stats", "snarkvm_b200_msm_set_scratch_limit", "snarkvm_b200_msm_window_sums_host", "snarkvm_b200_selftest_coop",
 )
 
 
@@ -110,6 +110,7 @@ def lib():
     L.snarkvm_b200_kzg_commit_batch_precomputed_device.argtypes = [vp, vp, vp, vp, sz, vp]
     L.snarkvm_b200_msm_scratch_stats.argtypes = [ctypes.POINTER(sz), ctypes.POINTER(sz), ctypes.POINTER(sz)]
     L.snarkvm_b200_msm_set_scratch_limit.argtypes = [sz]
+    L.snarkvm_b200_selftest_coop.argtypes = [u32, u64, ctypes.POINTER(u32), vp]
     L.snarkvm_b200_msm_window_sums_host.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp]
     for s in SYMBOLS[5:]:
         getattr(L, s).restype = i32

@@ -901,6 +901,19 @@ int snarkvm_b200_register_bases_precomputed(const void* host_points, size_t npoi
     return 0;
 }
 
+// device self-test of the warp-cooperative field arithmetic: returns 0 and *mismatches = number of failing warps
+int snarkvm_b200_selftest_coop(uint32_t nwarps, uint64_t seed, uint32_t* mismatches, void* stream_v) {
+    if (!mismatches || nwarps == 0) return (int)cudaErrorInvalidValue;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    uint32_t* d = nullptr;
+    int rc = (int)pool_alloc(&d, 256, stream);
+    if (rc == 0) rc = selftest_coop_device(nwarps, seed, d, stream);
+    if (rc == 0) rc = (int)cudaMemcpyAsync(mismatches, d, 4, cudaMemcpyDeviceToHost, stream);
+    if (d) cudaFreeAsync(d, stream);
+    if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
+    return rc;
+}
+
 int snarkvm_b200_profile_enable(int on) { prof_enable(on != 0); return 0; }
 int snarkvm_b200_profile_collect(int kind, double* total_ms, uint64_t* count) { return prof_collect(kind, total_ms, count); }
 

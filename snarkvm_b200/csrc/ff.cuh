@@ -365,6 +365,92 @@ struct Fp {
 };
 
 // ---------------------------------------------------------------------------
+// Warp-cooperative Montgomery arithmetic: ONE field element spread over a warp, limb j in lane j (lanes ≥ N hold 0).
+// A lone warp running the word-serial multiplier above is latency-bound (≈ 700 dependent instructions per product);
+// here a product is N iterations of { a·b_i, m·p, shift one limb down } on a carry-save value (lo, hi, ex per lane), with
+// three shuffles per iteration, then one ballot-based carry resolution and one ballot-based conditional subtraction:
+// ≈ 170 instructions per product for the whole warp.  Used for the single Fermat inversion a CTA shares (msm.cu), where
+// 31 lanes would otherwise compute the same 570 products redundantly.  tests/manual/coop_mul_model.py is a statement-by-
+// statement model of this code checked against big integers.
+// ---------------------------------------------------------------------------
+FF_DEV uint32_t coop_carries_in(uint32_t gen, uint32_t prop) {
+    // bit j = carry (borrow) into lane j, given the lanes that generate one and the lanes that pass one on
+    const uint32_t a = gen | prop;
+    return (a + gen) ^ a ^ gen;
+}
+template <class P>
+FF_DEV uint32_t coop_mod_limb(int lane) {
+    uint32_t p = 0u;
+#pragma unroll
+    for (int k = 0; k < P::N; k++) if (lane == k) p = P::mod(k);
+    return p;
+}
+// limbs of a·b·R^{-1} mod p, fully reduced; a, b, p = this lane's limbs; all 32 lanes must call it
+template <class P>
+FF_DEV uint32_t coop_mul(uint32_t a, uint32_t b, uint32_t p, int lane) {
+    constexpr int N = P::N;
+    uint32_t lo = 0u, hi = 0u, ex = 0u;
+    uint32_t bi = __shfl_sync(0xffffffffu, b, 0);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const uint32_t bnext = __shfl_sync(0xffffffffu, b, (i + 1) % N);      // off the critical path
+        asm("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;" : "+r"(lo), "+r"(hi), "+r"(ex) : "r"(a), "r"(bi));
+        const uint32_t m = __shfl_sync(0xffffffffu, lo * P::INV32, 0);       // lane 0 decides the reduction multiple
+        asm("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;" : "+r"(lo), "+r"(hi), "+r"(ex) : "r"(m), "r"(p));
+        // lane 0's lo is now 0: divide by 2^32 — V'_j = (V_j >> 32) + lo_{j+1}  (lane 31's own lo is always 0)
+        const uint32_t t = __shfl_down_sync(0xffffffffu, lo, 1);
+        asm("add.cc.u32 %0, %1, %3; addc.u32 %1, %2, 0;" : "=r"(lo), "+r"(hi), "+r"(ex) : "r"(t));
+        ex = 0u;
+        bi = bnext;
+    }
+    // carry-save → canonical limbs: s_j = lo_j + hi_{j-1}, then carries resolved across lanes in one step
+    uint32_t up = __shfl_up_sync(0xffffffffu, hi, 1);
+    if (lane == 0) up = 0u;
+    uint32_t s = lo + up;
+    const uint32_t cin = coop_carries_in(__ballot_sync(0xffffffffu, s < up), __ballot_sync(0xffffffffu, s == 0xffffffffu));
+    s += (cin >> lane) & 1u;
+    // r = s ≥ p ? s − p : s  — the most significant differing limb decides
+    const uint32_t gt = __ballot_sync(0xffffffffu, s > p), lt = __ballot_sync(0xffffffffu, s < p);
+    if (gt >= lt) {
+        const uint32_t bin = coop_carries_in(lt, __ballot_sync(0xffffffffu, s == p));
+        s = s - p - ((bin >> lane) & 1u);
+    }
+    return s;
+}
+// a^{p-2} for an element every lane of the warp holds (e.g. after a broadcast); every lane returns the inverse.  0 ↦ 0.
+template <class P>
+FF_DEV Fp<P> coop_inverse(const Fp<P>& v) {
+    constexpr int N = P::N;
+    const int lane = threadIdx.x & 31;
+    const uint32_t p = coop_mod_limb<P>(lane);
+    uint32_t x = 0u;
+#pragma unroll
+    for (int k = 0; k < N; k++) if (lane == k) x = v.v[k];
+    uint32_t acc = x;
+    bool started = false;
+#pragma unroll 1
+    for (int i = N - 1; i >= 0; i--) {
+        uint32_t e = 0u, borrow_in = 0u;                 // limb i of p − 2 (p ≡ 1 mod 2^32 would borrow; handled generally)
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            const uint32_t mk = P::mod(k), sub = (k == 0 ? 2u : 0u) + borrow_in;
+            const uint32_t ek = mk - sub;
+            borrow_in = (mk < sub) ? 1u : 0u;
+            if (k == i) e = ek;
+        }
+#pragma unroll 1
+        for (int b = 31; b >= 0; b--) {
+            if (started) acc = coop_mul<P>(acc, acc, p, lane);
+            if ((e >> b) & 1u) { acc = started ? coop_mul<P>(acc, x, p, lane) : x; started = true; }
+        }
+    }
+    Fp<P> r;
+#pragma unroll
+    for (int k = 0; k < N; k++) r.v[k] = __shfl_sync(0xffffffffu, acc, k);
+    return r;
+}
+
+// ---------------------------------------------------------------------------
 // BLS12-377 parameters (numbers from curves/src/bls12_377/fr.rs:109-192, fq.rs:85-176,
 // re-expressed as 32-bit limbs; cross-checked in tests against oracle/bls12_377.py).
 // ---------------------------------------------------------------------------

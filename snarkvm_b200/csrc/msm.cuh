@@ -74,6 +74,9 @@ int msm_generate_bases_device(void* d_points, size_t npoints, size_t stride, uin
 // off the curve, out of range or badly flagged.
 int srs_decode_device(void* d_out, size_t stride, const void* d_in, size_t npoints, uint32_t* d_invalid, cudaStream_t stream);
 
+// device self-test of ff.cuh's warp-cooperative multiplication / inversion; *d_mismatches (device u32) counts failing warps
+int selftest_coop_device(uint32_t nwarps, uint64_t seed, uint32_t* d_mismatches, cudaStream_t stream);
+
 // out[i] = Σ_r in[r][i]  over `nranks` arrays of `count` XYZZ points (multi-GPU combine).
 int xyzz_sum_ranks_device(uint32_t* d_out, const uint32_t* d_in, int nranks, int count, cudaStream_t stream);
 

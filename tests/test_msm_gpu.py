@@ -575,3 +575,15 @@ def test_msm_concurrent_large_calls_share_scratch_budget(oracle_cpu):
     for k in range(8):
         want = oracle_cpu.g1_mul(g, oracle_cpu.fr_dot_canonical(scal[k], ks))
         assert (results[k] == want).all(), k
+
+
+def test_warp_cooperative_field_arithmetic_selftest():
+    """ff.cuh coop_mul / coop_inverse (one Fq element spread over a warp, used for the CTA-shared inversions of the pair levels)
+    against the per-thread multiplier, on the device: 0, 1, q − 1, a long-carry value and 20000 pseudo-random elements."""
+    import ctypes
+    import torch
+    from snarkvm_b200 import _lib
+    bad = ctypes.c_uint32(123)
+    with torch.cuda.device(0):
+        _lib.check(_lib.lib().snarkvm_b200_selftest_coop(20000, 0xC0FFEE, ctypes.byref(bad), torch.cuda.current_stream().cuda_stream))
+    assert bad.value == 0

@@ -26,10 +26,10 @@ for lg in sizes:
     scal = torch.from_numpy(s.view(np.int64)).cuda()
     ref = None
     KEYS = ("SNARKVM_B200_MSM_PAIR_V1", "SNARKVM_B200_MSM_SCRATCH_GB", "SNARKVM_B200_MSM_LEVELS", "SNARKVM_B200_MSM_C", "SNARKVM_B200_MSM_PAIR_PARTS")
-    for tag, env in (("v1", {"SNARKVM_B200_MSM_PAIR_V1": "1"}), ("v1 40GB", {"SNARKVM_B200_MSM_PAIR_V1": "1", "SNARKVM_B200_MSM_SCRATCH_GB": "40"}),
-                     ("v3", {}), ("v3 1part", {"SNARKVM_B200_MSM_PAIR_PARTS": "1"}), ("v3 40GB", {"SNARKVM_B200_MSM_SCRATCH_GB": "40"}),
-                     ("v3 40GB 1part", {"SNARKVM_B200_MSM_SCRATCH_GB": "40", "SNARKVM_B200_MSM_PAIR_PARTS": "1"}),
-                     ("v3 L5", {"SNARKVM_B200_MSM_LEVELS": "5"})):
+    for tag, env in (("v1 40GB", {"SNARKVM_B200_MSM_PAIR_V1": "1", "SNARKVM_B200_MSM_SCRATCH_GB": "40"}),
+                     ("v3", {}), ("v3 2part", {"SNARKVM_B200_MSM_PAIR_PARTS": "2"}), ("v3 40GB", {"SNARKVM_B200_MSM_SCRATCH_GB": "40"}),
+                     ("v3 40GB 2part", {"SNARKVM_B200_MSM_SCRATCH_GB": "40", "SNARKVM_B200_MSM_PAIR_PARTS": "2"}),
+                     ("v3 40GB L5", {"SNARKVM_B200_MSM_SCRATCH_GB": "40", "SNARKVM_B200_MSM_LEVELS": "5"})):
         for k in KEYS: os.environ.pop(k, None)
         os.environ.update(env)
         got = device.msm(bases, scal)
