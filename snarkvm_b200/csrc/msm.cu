@@ -491,12 +491,11 @@ struct PairDesc {            // one lane's output of one step
     bool valid;              // the output exists (known from the indices alone, never from loaded data)
     FF_DEV bool has2() const { return valid && q != PAIR_NONE; }
 };
-FF_DEV PairDesc pair_load_desc(int64_t j, uint32_t j0, uint32_t j1, uint32_t W0, uint32_t W1, int lane, const uint2* __restrict__ desc) {
+// descriptor of step j for this lane (dlane = desc + W0 + lane); steps outside [0, nv) do not exist
+FF_DEV PairDesc pair_load_desc(int64_t j, uint32_t nv, const uint2* __restrict__ dlane) {
     PairDesc d; d.p = 0; d.q = PAIR_NONE; d.valid = false;
-    if (j < (int64_t)j0 || j >= (int64_t)j1) return d;
-    const uint64_t o64 = (uint64_t)W0 + 32ull * (uint64_t)j + (uint32_t)lane;
-    if (o64 >= W1) return d;
-    const uint2 v = __ldg(desc + o64);
+    if (j < 0 || j >= (int64_t)nv) return d;
+    const uint2 v = __ldg(dlane + 32 * j);
     d.p = v.x; d.q = v.y; d.valid = true;
     return d;
 }
@@ -561,18 +560,16 @@ __device__ __noinline__ Fq cta_shared_inverse_by(const Fq& run, uint32_t* sh, in
     return Fq::load(sh + tid * 12);
 }
 
-// The shared inversion is a bubble: one warp runs ≈ 570 dependent multiplications while the CTA's other warps wait at the
-// barrier, and CTAs that start together reach it together (ncu, round 2: 16 % of every warp's cycles at that barrier, with
-// the four inverting warps of an SM all on the same sub-partition).  Two measures:
-//   * every CTA takes a slot number from a per-SM counter: slot & 3 names the inverting warp, so the (up to) four CTAs
-//     resident on an SM invert on four different sub-partitions whatever the block → SM mapping is;
-//   * every CTA runs its T steps as TWO parts split at (2·slot + 1)/8 of the range, so co-resident CTAs reach their
-//     inversions at different times and the other three keep the multiplier busy meanwhile.
-template <bool GATHER>
-__global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair_level2(const uint32_t* __restrict__ records /* level 0: dense bases / table; above: dense_in */,
+// The shared inversion is a bubble — one warp works while the CTA's other warps wait at the barrier, and CTAs that start
+// together reach it together — so (i) the inverting warp computes ONE inverse limb-per-lane (coop_inverse, ff.cuh) instead
+// of 32 redundant copies, and (ii) every CTA takes a slot number from a per-SM counter: slot & 3 names the inverting warp, so
+// the CTAs resident on an SM invert on different sub-partitions whatever the block → SM mapping is.
+// MINB = resident CTAs per SM the kernel is compiled for: 4 (128 registers) or 3 (168 registers, no spills).
+template <bool GATHER, int MINB>
+__global__ void __launch_bounds__(PAIR_THREADS, MINB) k_pair_level2(const uint32_t* __restrict__ records /* level 0: dense bases / table; above: dense_in */,
                                                          const uint2* __restrict__ desc, const uint32_t* __restrict__ total_ptr,
                                                          uint32_t T, uint32_t* __restrict__ prefix, uint32_t* __restrict__ dense_out,
-                                                         uint32_t* __restrict__ sm_slots, int parts) {
+                                                         uint32_t* __restrict__ sm_slots) {
     extern __shared__ uint4 pair2_smem[];
     __shared__ uint32_t sh_slot;
     uint32_t* sh_inv = reinterpret_cast<uint32_t*>(pair2_smem);                       // 128 × 48 B
@@ -584,117 +581,112 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pair_level2(const uint32_t*
         sh_slot = atomicAdd(sm_slots + (smid & 255u), 1u);
     }
     __syncthreads();
-    const uint32_t slot = sh_slot & 3u;
+    const int inv_warp = (int)(sh_slot & 3u);
     const uint32_t total = __ldg(total_ptr);
-    const uint64_t w0_64 = ((uint64_t)blockIdx.x * (PAIR_THREADS / 32) + (uint32_t)warp) * 32ull * T;
-    const uint32_t W0 = w0_64 < total ? (uint32_t)w0_64 : total;
-    const uint32_t W1 = (w0_64 + 32ull * T < total) ? (uint32_t)(w0_64 + 32ull * T) : total;
-    const uint32_t Ta = parts > 1 ? (uint32_t)(((uint64_t)T * (2u * slot + 1u)) >> 3) : T;
+    const uint64_t w0_64 = ((uint64_t)blockIdx.x * (PAIR_THREADS / 32) + (uint32_t)warp) * 32ull * T + (uint32_t)lane;   // this lane's first output
+    uint32_t nv = 0;                                                                   // steps that exist for this lane
+    if (w0_64 < total) { const uint64_t left = (total - w0_64 + 31) / 32; nv = left < T ? (uint32_t)left : T; }
+    const uint2* dlane = desc + w0_64;
+    uint32_t* plane = prefix + w0_64 * 12;                                             // prefix of step j at plane + j·32·12
+    uint32_t* olane = dense_out + w0_64 * DENSE_WORDS;
 
-    for (int part = 0; part < 2; part++) {
-        const uint32_t j0 = part ? Ta : 0u, j1 = part ? T : Ta;       // steps of this part (uniform over the CTA)
-        if (j0 == j1) continue;
-        // ---------------- forward: running product of the denominators ----------------
-        Fq run = Fq::one();
-        {
-            PairDesc cur = pair_load_desc(j0, j0, j1, W0, W1, lane, desc);
-            pair_issue<GATHER, false>(cur, ring, 0, lane, records);
-            PairDesc nxt = pair_load_desc((int64_t)j0 + 1, j0, j1, W0, W1, lane, desc);
-            for (uint32_t j = j0; j < j1; j++) {
-                const uint32_t k = j - j0;
-                PairDesc nn = pair_load_desc((int64_t)j + 2, j0, j1, W0, W1, lane, desc);
-                pair_issue<GATHER, false>(nxt, ring, (int)((k + 1) & 1u), lane, records);
-                cp_async_wait_1();
-                Fq d = Fq::one();
-                if (cur.has2()) {
-                    const uint4* slot_p = ring + (size_t)(k & 1u) * RING_STAGE_U4 + lane;
-                    Fq x1 = ring_fq(slot_p), x2 = ring_fq(slot_p + 6 * 32);
-                    if (x1 == x2 || x1.is_zero() || x2.is_zero()) {
-                        Fq den;
-                        if (pair_classify_global<GATHER>(cur, records, den) >= PAIR_ADD) d = den;
-                    } else {
-                        d = x2 - x1;
-                    }
+    // ---------------- forward: running product of the denominators ----------------
+    Fq run = Fq::one();
+    {
+        PairDesc cur = pair_load_desc(0, nv, dlane);
+        pair_issue<GATHER, false>(cur, ring, 0, lane, records);
+        PairDesc nxt = pair_load_desc(1, nv, dlane);
+        for (uint32_t j = 0; j < T; j++) {
+            pair_issue<GATHER, false>(nxt, ring, (int)((j + 1) & 1u), lane, records);      // step j+1's operands (descriptor loaded a step ago)
+            PairDesc nn = pair_load_desc((int64_t)j + 2, nv, dlane);                         // consumed a whole step from now
+            cp_async_wait_1();
+            Fq d = Fq::one();
+            if (cur.has2()) {
+                const uint4* slot_p = ring + (size_t)(j & 1u) * RING_STAGE_U4 + lane;
+                Fq x1 = ring_fq(slot_p), x2 = ring_fq(slot_p + 6 * 32);
+                if (x1 == x2 || x1.is_zero() || x2.is_zero()) {
+                    Fq den;
+                    if (pair_classify_global<GATHER>(cur, records, den) >= PAIR_ADD) d = den;
+                } else {
+                    d = x2 - x1;
                 }
-                run = run * d;
-                if (cur.valid) run.store(prefix + ((size_t)W0 + 32ull * j + (uint32_t)lane) * 12);
-                cur = nxt; nxt = nn;
             }
-            cp_async_wait_0();
+            run = run * d;
+            if (cur.valid) run.store(plane + (size_t)j * (32 * 12));
+            cur = nxt; nxt = nn;
         }
-        Fq inv = cta_shared_inverse_by(run, sh_inv, (int)slot);
-        // ---------------- backward: one inverse per pair, then the affine addition ----------------
-        {
-            PairDesc cur = pair_load_desc((int64_t)j1 - 1, j0, j1, W0, W1, lane, desc);
-            pair_issue<GATHER, true>(cur, ring, 0, lane, records);
-            PairDesc nxt = pair_load_desc((int64_t)j1 - 2, j0, j1, W0, W1, lane, desc);
-            for (uint32_t k = 0; k < j1 - j0; k++) {
-                const uint32_t j = j1 - 1 - k;
-                PairDesc nn = pair_load_desc((int64_t)j - 2, j0, j1, W0, W1, lane, desc);
-                pair_issue<GATHER, true>(nxt, ring, (int)((k + 1) & 1u), lane, records);
-                const size_t o = (size_t)W0 + 32ull * j + (uint32_t)lane;
-                Fq pf = Fq::one();
-                if (cur.valid && j != j0) pf = Fq::load(prefix + (o - 32) * 12);         // behind the first multiplication
-                cp_async_wait_1();
-                const uint4* slot_p = ring + (size_t)(k & 1u) * RING_STAGE_U4 + lane;
-                // classify (same decisions as the forward pass)
-                int kind = PAIR_COPY1;
-                Fq d = Fq::one(), num = Fq::zero();
-                const bool has2 = cur.has2();
-                const bool negP = GATHER && (cur.p >> 31), negQ = GATHER && has2 && (cur.q >> 31);
-                if (has2) {
-                    Fq x1 = ring_fq(slot_p), x2 = ring_fq(slot_p + 6 * 32);
-                    if (x1 == x2 || x1.is_zero() || x2.is_zero()) {
-                        DensePoint P, Q;
-                        P.x = x1; P.y = ring_fq(slot_p + 3 * 32); P.inf = P.x.is_zero() && P.y.is_zero();
-                        Q.x = x2; Q.y = ring_fq(slot_p + 9 * 32); Q.inf = Q.x.is_zero() && Q.y.is_zero();
-                        if (negP && !P.inf) P.y = P.y.neg();
-                        if (negQ && !Q.inf) Q.y = Q.y.neg();
-                        Fq den;
-                        kind = classify_pair(P, Q, true, den);
-                        if (kind >= PAIR_ADD) d = den;
-                        if (kind == PAIR_ADD) num = Q.y - P.y;
-                        else if (kind == PAIR_DBL) { Fq xx = P.x.sqr(); num = xx.dbl() + xx; }
-                    } else {
-                        kind = PAIR_ADD;
-                        d = x2 - x1;
-                        Fq y1 = ring_fq(slot_p + 3 * 32), y2 = ring_fq(slot_p + 9 * 32);
-                        // (±y2) − (±y1) without negating first: one subtraction or one addition, then at most one negation
-                        if (negP == negQ) { num = y2 - y1; if (negP) num = num.neg(); }
-                        else { num = y2 + y1; if (negQ) num = num.neg(); }
-                    }
+        cp_async_wait_0();
+    }
+    Fq inv = cta_shared_inverse_by(run, sh_inv, inv_warp);
+    // ---------------- backward: one inverse per pair, then the affine addition ----------------
+    {
+        PairDesc cur = pair_load_desc((int64_t)T - 1, nv, dlane);
+        pair_issue<GATHER, true>(cur, ring, 0, lane, records);
+        PairDesc nxt = pair_load_desc((int64_t)T - 2, nv, dlane);
+        for (uint32_t k = 0; k < T; k++) {
+            const uint32_t j = T - 1 - k;
+            pair_issue<GATHER, true>(nxt, ring, (int)((k + 1) & 1u), lane, records);
+            PairDesc nn = pair_load_desc((int64_t)j - 2, nv, dlane);
+            Fq pf = Fq::one();
+            if (cur.valid && j != 0) pf = Fq::load(plane + (size_t)(j - 1) * (32 * 12));     // behind the first multiplication
+            cp_async_wait_1();
+            const uint4* slot_p = ring + (size_t)(k & 1u) * RING_STAGE_U4 + lane;
+            // classify (same decisions as the forward pass)
+            int kind = PAIR_COPY1;
+            Fq d = Fq::one(), num = Fq::zero();
+            const bool has2 = cur.has2();
+            const bool negP = GATHER && (cur.p >> 31), negQ = GATHER && has2 && (cur.q >> 31);
+            if (has2) {
+                Fq x1 = ring_fq(slot_p), x2 = ring_fq(slot_p + 6 * 32);
+                if (x1 == x2 || x1.is_zero() || x2.is_zero()) {
+                    DensePoint P, Q;
+                    P.x = x1; P.y = ring_fq(slot_p + 3 * 32); P.inf = P.x.is_zero() && P.y.is_zero();
+                    Q.x = x2; Q.y = ring_fq(slot_p + 9 * 32); Q.inf = Q.x.is_zero() && Q.y.is_zero();
+                    if (negP && !P.inf) P.y = P.y.neg();
+                    if (negQ && !Q.inf) Q.y = Q.y.neg();
+                    Fq den;
+                    kind = classify_pair(P, Q, true, den);
+                    if (kind >= PAIR_ADD) d = den;
+                    if (kind == PAIR_ADD) num = Q.y - P.y;
+                    else if (kind == PAIR_DBL) { Fq xx = P.x.sqr(); num = xx.dbl() + xx; }
+                } else {
+                    kind = PAIR_ADD;
+                    d = x2 - x1;
+                    Fq y1 = ring_fq(slot_p + 3 * 32), y2 = ring_fq(slot_p + 9 * 32);
+                    // (±y2) − (±y1) without negating first: one subtraction or one addition, then at most one negation
+                    if (negP == negQ) { num = y2 - y1; if (negP) num = num.neg(); }
+                    else { num = y2 + y1; if (negQ) num = num.neg(); }
                 }
-                Fq inv_next = inv * d;
-                Fq inv_d = (j != j0) ? inv * pf : inv;
-                inv = inv_next;
-                Fq lambda = num * inv_d;
-                Fq x3 = lambda.sqr();
-                {
-                    Fq x1 = ring_fq(slot_p), x2 = has2 ? ring_fq(slot_p + 6 * 32) : x1;
-                    x3 = x3 - x1 - x2;
-                    Fq t = x1 - x3;
-                    Fq y3 = lambda * t;
-                    if (cur.valid) {
-                        DensePoint R;
-                        if (kind >= PAIR_ADD) {
-                            Fq y1 = ring_fq(slot_p + 3 * 32);
-                            R.x = x3; R.y = negP ? y3 + y1 : y3 - y1; R.inf = false;           // y3 − (±y1)
-                        } else if (kind == PAIR_INF) {
-                            R.inf = true; R.x = Fq::zero(); R.y = Fq::zero();
-                        } else {
-                            const int c0 = (kind == PAIR_COPY2) ? 6 : 0;
-                            R.x = ring_fq(slot_p + c0 * 32); R.y = ring_fq(slot_p + (c0 + 3) * 32);
-                            R.inf = R.x.is_zero() && R.y.is_zero();
-                            if (((kind == PAIR_COPY2) ? negQ : negP) && !R.inf) R.y = R.y.neg();
-                        }
-                        store_dense(dense_out + o * DENSE_WORDS, R);
-                    }
-                }
-                cur = nxt; nxt = nn;
             }
-            cp_async_wait_0();
+            Fq inv_next = inv * d;
+            Fq inv_d = (j != 0) ? inv * pf : inv;
+            inv = inv_next;
+            Fq lambda = num * inv_d;
+            Fq x3 = lambda.sqr();
+            {
+                Fq x1 = ring_fq(slot_p), x2 = has2 ? ring_fq(slot_p + 6 * 32) : x1;
+                x3 = x3 - x1 - x2;
+                Fq t = x1 - x3;
+                Fq y3 = lambda * t;
+                if (cur.valid) {
+                    DensePoint R;
+                    if (kind >= PAIR_ADD) {
+                        Fq y1 = ring_fq(slot_p + 3 * 32);
+                        R.x = x3; R.y = negP ? y3 + y1 : y3 - y1; R.inf = false;           // y3 − (±y1)
+                    } else if (kind == PAIR_INF) {
+                        R.inf = true; R.x = Fq::zero(); R.y = Fq::zero();
+                    } else {
+                        const int c0 = (kind == PAIR_COPY2) ? 6 : 0;
+                        R.x = ring_fq(slot_p + c0 * 32); R.y = ring_fq(slot_p + (c0 + 3) * 32);
+                        R.inf = R.x.is_zero() && R.y.is_zero();
+                        if (((kind == PAIR_COPY2) ? negQ : negP) && !R.inf) R.y = R.y.neg();
+                    }
+                    store_dense(olane + (size_t)j * (32 * DENSE_WORDS), R);
+                }
+            }
+            cur = nxt; nxt = nn;
         }
-        __syncthreads();        // the shared-inversion words and the ring are reused by the next part
+        cp_async_wait_0();
     }
 }
 
@@ -994,15 +986,17 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
     if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_WAVES")) { long v = atol(e); if (v >= 1) pair_waves = (size_t)v; }
     bool pair_v1 = false;                        // A/B switch: the round-1 thread-contiguous pair level
     if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_V1")) pair_v1 = atoi(e) != 0;
-    int pair_parts = 1;                          // 1: one inversion per CTA; 2: staggered two-part CTAs (see k_pair_level2)
-    if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_PARTS")) { int v = atoi(e); if (v == 1 || v == 2) pair_parts = v; }
+    int pair_minb = 4;                           // resident CTAs per SM the pair kernel is built for (4 × 128 regs or 3 × 168 regs)
+    if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_MINB")) { int v = atoi(e); if (v == 3 || v == 4) pair_minb = v; }
     int sm_count = 148;
     {
         static std::once_flag smem_once[64];
         int dev = 0; cudaGetDevice(&dev);
         std::call_once(smem_once[dev & 63], [] {
-            cudaFuncSetAttribute(k_pair_level2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR2_SMEM);
-            cudaFuncSetAttribute(k_pair_level2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR2_SMEM);
+            cudaFuncSetAttribute(k_pair_level2<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR2_SMEM);
+            cudaFuncSetAttribute(k_pair_level2<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR2_SMEM);
+            cudaFuncSetAttribute(k_pair_level2<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR2_SMEM);
+            cudaFuncSetAttribute(k_pair_level2<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR2_SMEM);
         });
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
         if (sm_count <= 0) sm_count = 148;
@@ -1134,7 +1128,7 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
                     // Whole waves: 148 SMs × 4 resident CTAs × 128 threads = 75776 lanes run at once; give every lane
                     // the same number T of outputs and launch an integer number of such waves, so no partial last wave
                     // idles most of the machine (a level is one long-running CTA per slot, not many short ones).
-                    const size_t wave = (size_t)sm_count * 4 * 128;
+                    const size_t wave = (size_t)sm_count * (pair_v1 ? 4 : pair_minb) * 128;
                     size_t waves = (bound + 1024 * wave - 1) / (1024 * wave);
                     if (pair_waves) waves = pair_waves;
                     size_t T = (bound + waves * wave - 1) / (waves * wave);
@@ -1151,10 +1145,12 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
                         const unsigned dgrid = (unsigned)((bound + 255) / 256);
                         if (l == 0) {
                             k_pair_desc<true><<<dgrid, 256, 0, stream>>>(sorted, off_in, off_out, tb, desc);
-                            k_pair_level2<true><<<lgrid, 128, PAIR2_SMEM, stream>>>(gather_src, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots, pair_parts);
+                            if (pair_minb == 3) k_pair_level2<true, 3><<<lgrid, 128, PAIR2_SMEM, stream>>>(gather_src, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots);
+                            else k_pair_level2<true, 4><<<lgrid, 128, PAIR2_SMEM, stream>>>(gather_src, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots);
                         } else {
                             k_pair_desc<false><<<dgrid, 256, 0, stream>>>(nullptr, off_in, off_out, tb, desc);
-                            k_pair_level2<false><<<lgrid, 128, PAIR2_SMEM, stream>>>(dense_in, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots, pair_parts);
+                            if (pair_minb == 3) k_pair_level2<false, 3><<<lgrid, 128, PAIR2_SMEM, stream>>>(dense_in, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots);
+                            else k_pair_level2<false, 4><<<lgrid, 128, PAIR2_SMEM, stream>>>(dense_in, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots);
                         }
                         count_launch(1);
                     }

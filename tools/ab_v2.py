@@ -25,11 +25,12 @@ for lg in sizes:
     s = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64); s[:, 3] &= np.uint64((1 << 60) - 1)
     scal = torch.from_numpy(s.view(np.int64)).cuda()
     ref = None
-    KEYS = ("SNARKVM_B200_MSM_PAIR_V1", "SNARKVM_B200_MSM_SCRATCH_GB", "SNARKVM_B200_MSM_LEVELS", "SNARKVM_B200_MSM_C", "SNARKVM_B200_MSM_PAIR_PARTS")
+    KEYS = ("SNARKVM_B200_MSM_PAIR_V1", "SNARKVM_B200_MSM_SCRATCH_GB", "SNARKVM_B200_MSM_LEVELS", "SNARKVM_B200_MSM_C", "SNARKVM_B200_MSM_PAIR_PARTS", "SNARKVM_B200_MSM_PAIR_MINB")
     for tag, env in (("v1 40GB", {"SNARKVM_B200_MSM_PAIR_V1": "1", "SNARKVM_B200_MSM_SCRATCH_GB": "40"}),
-                     ("v3", {}), ("v3 2part", {"SNARKVM_B200_MSM_PAIR_PARTS": "2"}), ("v3 40GB", {"SNARKVM_B200_MSM_SCRATCH_GB": "40"}),
-                     ("v3 40GB 2part", {"SNARKVM_B200_MSM_SCRATCH_GB": "40", "SNARKVM_B200_MSM_PAIR_PARTS": "2"}),
-                     ("v3 40GB L5", {"SNARKVM_B200_MSM_SCRATCH_GB": "40", "SNARKVM_B200_MSM_LEVELS": "5"})):
+                     ("v4 minb4", {}), ("v4 minb3", {"SNARKVM_B200_MSM_PAIR_MINB": "3"}),
+                     ("v4 minb4 40GB", {"SNARKVM_B200_MSM_SCRATCH_GB": "40"}),
+                     ("v4 minb3 40GB", {"SNARKVM_B200_MSM_SCRATCH_GB": "40", "SNARKVM_B200_MSM_PAIR_MINB": "3"}),
+                     ("v4 minb3 40GB L5", {"SNARKVM_B200_MSM_SCRATCH_GB": "40", "SNARKVM_B200_MSM_PAIR_MINB": "3", "SNARKVM_B200_MSM_LEVELS": "5"})):
         for k in KEYS: os.environ.pop(k, None)
         os.environ.update(env)
         got = device.msm(bases, scal)
