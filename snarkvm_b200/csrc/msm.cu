@@ -452,6 +452,7 @@ FF_DEV void cp_async16(uint32_t dst, const void* src) {
 FF_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 FF_DEV void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 FF_DEV void cp_async_wait_0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+FF_DEV void cp_async_wait_3() { asm volatile("cp.async.wait_group 3;" ::: "memory"); }
 
 static constexpr int RING_CHUNKS = 12;                       // x1 y1 x2 y2, three 16-byte chunks each
 static constexpr int RING_STAGE_U4 = RING_CHUNKS * 32;       // uint4 per warp per stage (6 KiB)
@@ -504,18 +505,19 @@ FF_DEV const uint32_t* pair_src(const PairDesc& d, int which, const uint32_t* __
     if (GATHER) return records + (size_t)((which ? d.q : d.p) & 0x7fffffffu) * BASE_WORDS;
     return records + (size_t)(d.p + (uint32_t)which) * DENSE_WORDS;
 }
-// copies of step operands into ring stage `st` (forward: x1, x2; backward: all four coordinates)
+// copies of step operands into ring stage `st` of `chunks` 16-byte chunks per lane: backward (FULL) x1 y1 x2 y2 in 12 chunks,
+// forward x1 x2 in 6 chunks
 template <bool GATHER, bool FULL>
-FF_DEV void pair_issue(const PairDesc& d, uint4* ring, int st, int lane, const uint32_t* __restrict__ records) {
+FF_DEV void pair_issue(const PairDesc& d, uint4* ring, int st, int lane, const uint32_t* __restrict__ records, int chunks) {
     if (d.valid) {
-        const uint32_t dst = smem_addr_u32(ring + (size_t)st * RING_STAGE_U4 + lane);
+        const uint32_t dst = smem_addr_u32(ring + (size_t)st * (size_t)(chunks * 32) + lane);
         const uint32_t* p = pair_src<GATHER>(d, 0, records);
 #pragma unroll
         for (int k = 0; k < (FULL ? 6 : 3); k++) cp_async16(dst + (uint32_t)k * 512u, p + 4 * k);
         if (d.q != PAIR_NONE) {
             const uint32_t* q = pair_src<GATHER>(d, 1, records);
 #pragma unroll
-            for (int k = 0; k < (FULL ? 6 : 3); k++) cp_async16(dst + (uint32_t)(6 + k) * 512u, q + 4 * k);
+            for (int k = 0; k < (FULL ? 6 : 3); k++) cp_async16(dst + (uint32_t)((FULL ? 6 : 3) + k) * 512u, q + 4 * k);
         }
     }
     cp_async_commit();
@@ -591,19 +593,27 @@ __global__ void __launch_bounds__(PAIR_THREADS, MINB) k_pair_level2(const uint32
     uint32_t* olane = dense_out + w0_64 * DENSE_WORDS;
 
     // ---------------- forward: running product of the denominators ----------------
+    // A forward step is ONE multiplication, far shorter than a gathered DRAM access: the x-only operands (96 B per lane) fit
+    // FOUR ring stages where the backward pass has two, so the copies run three steps ahead of the multiplier
+    // (ncu, round 2: with one step of lead the forward loop held 21 % of the kernel's stall samples for 4 % of its instructions).
     Fq run = Fq::one();
     {
-        PairDesc cur = pair_load_desc(0, nv, dlane);
-        pair_issue<GATHER, false>(cur, ring, 0, lane, records);
-        PairDesc nxt = pair_load_desc(1, nv, dlane);
+        constexpr int PF = 3;                                                   // steps of lead; PF + 1 stages of 6 chunks
+        PairDesc q0 = pair_load_desc(0, nv, dlane), q1 = pair_load_desc(1, nv, dlane), q2 = pair_load_desc(2, nv, dlane);
+        pair_issue<GATHER, false>(q0, ring, 0, lane, records, 6);
+        pair_issue<GATHER, false>(q1, ring, 1, lane, records, 6);
+        pair_issue<GATHER, false>(q2, ring, 2, lane, records, 6);
+        PairDesc ahead = pair_load_desc(PF, nv, dlane);
         for (uint32_t j = 0; j < T; j++) {
-            pair_issue<GATHER, false>(nxt, ring, (int)((j + 1) & 1u), lane, records);      // step j+1's operands (descriptor loaded a step ago)
-            PairDesc nn = pair_load_desc((int64_t)j + 2, nv, dlane);                         // consumed a whole step from now
-            cp_async_wait_1();
+            pair_issue<GATHER, false>(ahead, ring, (int)((j + PF) & 3u), lane, records, 6);       // step j+3 (descriptor loaded a step ago)
+            const PairDesc cur = q0;
+            q0 = q1; q1 = q2; q2 = ahead;
+            ahead = pair_load_desc((int64_t)j + PF + 1, nv, dlane);                              // not touched until the next iteration
+            cp_async_wait_3();
             Fq d = Fq::one();
             if (cur.has2()) {
-                const uint4* slot_p = ring + (size_t)(j & 1u) * RING_STAGE_U4 + lane;
-                Fq x1 = ring_fq(slot_p), x2 = ring_fq(slot_p + 6 * 32);
+                const uint4* slot_p = ring + (size_t)(j & 3u) * (6 * 32) + lane;
+                Fq x1 = ring_fq(slot_p), x2 = ring_fq(slot_p + 3 * 32);
                 if (x1 == x2 || x1.is_zero() || x2.is_zero()) {
                     Fq den;
                     if (pair_classify_global<GATHER>(cur, records, den) >= PAIR_ADD) d = den;
@@ -613,7 +623,6 @@ __global__ void __launch_bounds__(PAIR_THREADS, MINB) k_pair_level2(const uint32
             }
             run = run * d;
             if (cur.valid) run.store(plane + (size_t)j * (32 * 12));
-            cur = nxt; nxt = nn;
         }
         cp_async_wait_0();
     }
@@ -621,11 +630,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, MINB) k_pair_level2(const uint32
     // ---------------- backward: one inverse per pair, then the affine addition ----------------
     {
         PairDesc cur = pair_load_desc((int64_t)T - 1, nv, dlane);
-        pair_issue<GATHER, true>(cur, ring, 0, lane, records);
+        pair_issue<GATHER, true>(cur, ring, 0, lane, records, 12);
         PairDesc nxt = pair_load_desc((int64_t)T - 2, nv, dlane);
         for (uint32_t k = 0; k < T; k++) {
             const uint32_t j = T - 1 - k;
-            pair_issue<GATHER, true>(nxt, ring, (int)((k + 1) & 1u), lane, records);
+            pair_issue<GATHER, true>(nxt, ring, (int)((k + 1) & 1u), lane, records, 12);
             PairDesc nn = pair_load_desc((int64_t)j - 2, nv, dlane);
             Fq pf = Fq::one();
             if (cur.valid && j != 0) pf = Fq::load(plane + (size_t)(j - 1) * (32 * 12));     // behind the first multiplication
