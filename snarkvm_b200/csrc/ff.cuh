@@ -109,6 +109,62 @@ FF_DEV void mont_step(uint32_t (&ev)[N], uint32_t (&od)[N], const uint32_t (&a)[
 }
 
 // ---------------------------------------------------------------------------
+// Plain H×H-limb product T[2H] = a·b (H even) for the Karatsuba multiplier below.  Products are accumulated by the
+// parity of their position i + j: E holds the even positions, O (offset by one limb) the odd ones, so within a row
+// the (lo, hi) register pairs of consecutive products tile the accumulator and form ONE carry chain; the carry out of
+// a row lands in a limb that holds at most another row's carry.  tests/manual/karatsuba_model.py is a
+// statement-level model of this code (and of mul_karatsuba) checked against big integers.
+// ---------------------------------------------------------------------------
+template <int H>
+FF_DEV void mul_wide(const uint32_t* a, const uint32_t* b, uint32_t (&T)[2 * H]) {
+    uint32_t E[2 * H], O[2 * H];
+#pragma unroll
+    for (int k = 0; k < 2 * H; k++) { E[k] = 0u; O[k] = 0u; }
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+        {   // even positions: j ≡ i (mod 2)
+#pragma unroll
+            for (int j = (i & 1); j < H; j += 2) {
+                const int p = i + j;
+                if (j == (i & 1)) E[p] = ptx_mad_lo_cc(a[j], b[i], E[p]);
+                else E[p] = ptx_madc_lo_cc(a[j], b[i], E[p]);
+                E[p + 1] = ptx_madc_hi_cc(a[j], b[i], E[p + 1]);
+                if (j + 2 >= H && p + 2 < 2 * H) E[p + 2] = ptx_addc(E[p + 2], 0u);
+            }
+        }
+        {   // odd positions: j ≢ i → O[p − 1], O[p]
+#pragma unroll
+            for (int j = 1 - (i & 1); j < H; j += 2) {
+                const int p = i + j;
+                if (j == 1 - (i & 1)) O[p - 1] = ptx_mad_lo_cc(a[j], b[i], O[p - 1]);
+                else O[p - 1] = ptx_madc_lo_cc(a[j], b[i], O[p - 1]);
+                O[p] = ptx_madc_hi_cc(a[j], b[i], O[p]);
+                if (j + 2 >= H && p + 1 < 2 * H - 1) O[p + 1] = ptx_addc(O[p + 1], 0u);
+            }
+        }
+    }
+    T[0] = E[0];
+    T[1] = ptx_add_cc(E[1], O[0]);
+#pragma unroll
+    for (int k = 2; k < 2 * H - 1; k++) T[k] = ptx_addc_cc(E[k], O[k - 1]);
+    T[2 * H - 1] = ptx_addc(E[2 * H - 1], O[2 * H - 2]);
+}
+// d = |x − y| over H limbs; returns 1 when x < y
+template <int H>
+FF_DEV uint32_t abs_diff(const uint32_t* x, const uint32_t* y, uint32_t (&d)[H]) {
+    d[0] = ptx_sub_cc(x[0], y[0]);
+#pragma unroll
+    for (int i = 1; i < H; i++) d[i] = ptx_subc_cc(x[i], y[i]);
+    const uint32_t m = ptx_subc(0u, 0u);               // 0xffffffff if x < y
+    // conditional two's complement: (d ^ m) + (m & 1)
+    d[0] = ptx_add_cc(d[0] ^ m, m & 1u);
+#pragma unroll
+    for (int i = 1; i < H - 1; i++) d[i] = ptx_addc_cc(d[i] ^ m, 0u);
+    d[H - 1] = ptx_addc(d[H - 1] ^ m, 0u);
+    return m & 1u;
+}
+
+// ---------------------------------------------------------------------------
 // Field element
 // ---------------------------------------------------------------------------
 template <class P>
@@ -191,13 +247,106 @@ struct Fp {
     }
     // Out-of-line copy (arguments and result travel in registers — checked in SASS).  Kernels whose hot
     // loop contains many multiplications call this one so the loop stays inside the instruction cache.
-    static __device__ __noinline__ Fp mul_call(Fp a, Fp b) { return mul_inline(a, b); }
+    // Karatsuba (below) trades 36 (Fq) / 16 (Fr) of the 32×32→64 multiplications for ≈ 220 / 110 ALU instructions.  Measured on
+    // B200 (profiles/r2h_ffbench_{schoolbook,karatsuba}.log): Fq 2.56·10^10 → 2.41·10^10 mul/s, Fr 5.71·10^10 → 5.02·10^10 —
+    // SLOWER: at 4 warps per scheduler the multiplier is bound by issue slots and the carry-chain latency as much as by the
+    // fmaheavy pipe, so the word-serial product stays the default; -DFF_KARATSUBA selects the other one.
+#ifdef FF_KARATSUBA
+    FF_DEV static Fp mul_best(const Fp& a, const Fp& b) { return mul_karatsuba(a, b); }
+#else
+    FF_DEV static Fp mul_best(const Fp& a, const Fp& b) { return mul_inline(a, b); }
+#endif
+    static __device__ __noinline__ Fp mul_call(Fp a, Fp b) { return mul_best(a, b); }
     FF_DEV friend Fp operator*(const Fp& a, const Fp& b) {
 #ifdef FF_CALL_MUL
         return mul_call(a, b);
 #else
-        return mul_inline(a, b);
+        return mul_best(a, b);
 #endif
+    }
+    // T·2^{-32N} mod p for a 2N-limb T < p·2^{32N} (the product of two reduced elements).
+    FF_DEV static Fp mont_reduce_wide(const uint32_t (&T)[2 * N]) {
+        // Montgomery reduction of the 2N-limb square: V = ev + od·2^32 starts as the low half; every step clears
+        // the low limb with m·p, shifts one limb down and lets the next high limb of T in at the top.
+        uint32_t ev[N], od[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) { ev[k] = T[k]; od[k] = 0u; }
+        uint32_t pm[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) pm[k] = P::mod(k);
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const uint32_t m = ev[0] * P::INV32;
+            row_mad<N>(od, &pm[1], m);
+            if (P::MOD0_IS_ONE) {
+                ev[0] = ptx_add_cc(ev[0], m);
+                ev[1] = ptx_addc_cc(ev[1], 0u);
+#pragma unroll
+                for (int j = 2; j < N; j += 2) { ev[j] = ptx_madc_lo_cc(pm[j], m, ev[j]); ev[j + 1] = ptx_madc_hi_cc(pm[j], m, ev[j + 1]); }
+            } else {
+                row_mad<N>(ev, &pm[0], m);
+            }
+            od[N - 1] = ptx_addc(od[N - 1], 0u);
+            // shift one limb: (ev, od) ← (od + ev[1], ev[2..] ‖ T[N+i] ‖ 0) with the carry of the first add rippling up
+            uint32_t nev[N], nod[N];
+            nev[0] = ptx_add_cc(od[0], ev[1]);
+#pragma unroll
+            for (int k = 0; k < N - 2; k++) nod[k] = ptx_addc_cc(ev[k + 2], 0u);
+            nod[N - 2] = ptx_addc_cc(T[N + i], 0u);
+            nod[N - 1] = ptx_addc(0u, 0u);
+#pragma unroll
+            for (int k = 1; k < N; k++) nev[k] = od[k];
+#pragma unroll
+            for (int k = 0; k < N; k++) { ev[k] = nev[k]; od[k] = nod[k]; }
+        }
+        Fp r;
+        r.v[0] = ev[0];
+        r.v[1] = ptx_add_cc(ev[1], od[0]);
+#pragma unroll
+        for (int k = 2; k < N; k++) r.v[k] = ptx_addc_cc(ev[k], od[k - 1]);
+        r.final_sub();
+        return r;
+    }
+    // Karatsuba (one level, subtractive): a·b = z0 + (z0 + z2 − (a0 − a1)(b0 − b1))·2^{16N} + z2·2^{32N} with three N/2-limb
+    // products — 3·(N/2)² = 108 (Fq) / 48 (Fr) 32×32→64 multiplications instead of N² = 144 / 64; the additions run on the
+    // ALU pipe, which the multiplier leaves idle.  Then the same N reduction rows as the squaring.
+    FF_DEV static Fp mul_karatsuba(const Fp& a, const Fp& b) {
+        constexpr int H = N / 2;
+        uint32_t T[2 * N];
+        uint32_t mid[N + 1];
+        {
+            uint32_t z0[N], z2[N];
+            mul_wide<H>(&a.v[0], &b.v[0], z0);
+            mul_wide<H>(&a.v[H], &b.v[H], z2);
+            mid[0] = ptx_add_cc(z0[0], z2[0]);
+#pragma unroll
+            for (int k = 1; k < N; k++) mid[k] = ptx_addc_cc(z0[k], z2[k]);
+            mid[N] = ptx_addc(0u, 0u);
+#pragma unroll
+            for (int k = 0; k < N; k++) { T[k] = z0[k]; T[N + k] = z2[k]; }
+        }
+        {
+            uint32_t da[H], db[H], zm[N];
+            const uint32_t sa = abs_diff<H>(&a.v[0], &a.v[H], da), sb = abs_diff<H>(&b.v[0], &b.v[H], db);
+            mul_wide<H>(da, db, zm);
+            // mid −= zm when the signs agree, += zm otherwise: add (zm ^ mask) and then the two's-complement +1
+            const uint32_t mask = (sa == sb) ? 0xffffffffu : 0u;
+            mid[0] = ptx_add_cc(mid[0], zm[0] ^ mask);
+#pragma unroll
+            for (int k = 1; k < N; k++) mid[k] = ptx_addc_cc(mid[k], zm[k] ^ mask);
+            mid[N] = ptx_addc(mid[N], mask);
+            mid[0] = ptx_add_cc(mid[0], mask & 1u);
+#pragma unroll
+            for (int k = 1; k < N; k++) mid[k] = ptx_addc_cc(mid[k], 0u);
+            mid[N] = ptx_addc(mid[N], 0u);
+        }
+        T[H] = ptx_add_cc(T[H], mid[0]);
+#pragma unroll
+        for (int k = 1; k <= N; k++) T[H + k] = ptx_addc_cc(T[H + k], mid[k]);
+#pragma unroll
+        for (int k = H + N + 1; k < 2 * N - 1; k++) T[k] = ptx_addc_cc(T[k], 0u);
+        T[2 * N - 1] = ptx_addc(T[2 * N - 1], 0u);
+        return mont_reduce_wide(T);
     }
     // Dedicated squaring: N(N−1)/2 cross products (doubled by a 1-bit shift) + N diagonal products instead of N²,
     // then N Montgomery reduction rows on the 2N-limb square.  Cross products use the same even/odd carry-chain
@@ -248,46 +397,7 @@ struct Fp {
         T[1] = ptx_madc_hi_cc(a.v[0], a.v[0], T[1]);
 #pragma unroll
         for (int i = 1; i < N; i++) { T[2 * i] = ptx_madc_lo_cc(a.v[i], a.v[i], T[2 * i]); T[2 * i + 1] = ptx_madc_hi_cc(a.v[i], a.v[i], T[2 * i + 1]); }
-        // Montgomery reduction of the 2N-limb square: V = ev + od·2^32 starts as the low half; every step clears
-        // the low limb with m·p, shifts one limb down and lets the next high limb of T in at the top.
-        uint32_t ev[N], od[N];
-#pragma unroll
-        for (int k = 0; k < N; k++) { ev[k] = T[k]; od[k] = 0u; }
-        uint32_t pm[N];
-#pragma unroll
-        for (int k = 0; k < N; k++) pm[k] = P::mod(k);
-#pragma unroll
-        for (int i = 0; i < N; i++) {
-            const uint32_t m = ev[0] * P::INV32;
-            row_mad<N>(od, &pm[1], m);
-            if (P::MOD0_IS_ONE) {
-                ev[0] = ptx_add_cc(ev[0], m);
-                ev[1] = ptx_addc_cc(ev[1], 0u);
-#pragma unroll
-                for (int j = 2; j < N; j += 2) { ev[j] = ptx_madc_lo_cc(pm[j], m, ev[j]); ev[j + 1] = ptx_madc_hi_cc(pm[j], m, ev[j + 1]); }
-            } else {
-                row_mad<N>(ev, &pm[0], m);
-            }
-            od[N - 1] = ptx_addc(od[N - 1], 0u);
-            // shift one limb: (ev, od) ← (od + ev[1], ev[2..] ‖ T[N+i] ‖ 0) with the carry of the first add rippling up
-            uint32_t nev[N], nod[N];
-            nev[0] = ptx_add_cc(od[0], ev[1]);
-#pragma unroll
-            for (int k = 0; k < N - 2; k++) nod[k] = ptx_addc_cc(ev[k + 2], 0u);
-            nod[N - 2] = ptx_addc_cc(T[N + i], 0u);
-            nod[N - 1] = ptx_addc(0u, 0u);
-#pragma unroll
-            for (int k = 1; k < N; k++) nev[k] = od[k];
-#pragma unroll
-            for (int k = 0; k < N; k++) { ev[k] = nev[k]; od[k] = nod[k]; }
-        }
-        Fp r;
-        r.v[0] = ev[0];
-        r.v[1] = ptx_add_cc(ev[1], od[0]);
-#pragma unroll
-        for (int k = 2; k < N; k++) r.v[k] = ptx_addc_cc(ev[k], od[k - 1]);
-        r.final_sub();
-        return r;
+        return mont_reduce_wide(T);
     }
     static __device__ __noinline__ Fp sqr_call(Fp a) { return sqr_inline(a); }
     FF_DEV Fp sqr() const {

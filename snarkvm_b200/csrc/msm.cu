@@ -13,6 +13,7 @@
 
 #define FF_CALL_MUL 1
 #include "ec.cuh"
+#include "cta_inverse.cuh"
 
 namespace b200 {
 
@@ -66,7 +67,7 @@ MsmPlan msm_make_plan(size_t npoints) {
     int lg = ceil_log2(npoints < 2 ? 2 : npoints);
     // Window bits from a sweep on B200 (tools/tune_msm.py, profiles/tune_msm_r1.log): wider windows mean fewer
     // bucket additions (n·W) but more buckets to reduce and shorter, more divergent bucket runs.
-    int c = lg <= 8 ? 4 : lg <= 12 ? lg - 4 : lg <= 18 ? 11 : lg == 19 ? 16 : lg == 20 ? 15 : lg <= 22 ? 16 : 17;
+    int c = lg <= 8 ? 4 : lg <= 12 ? lg - 4 : lg <= 18 ? 11 : lg == 19 ? 13 : lg == 20 ? 15 : lg <= 22 ? 16 : 17;
     if (const char* e = getenv("SNARKVM_B200_MSM_C")) { int v = atoi(e); if (v >= 2 && v <= 24) c = v; }
     p.c = c;
     p.nwin = 253 / c + 1;
@@ -80,7 +81,9 @@ MsmPlan msm_make_plan(size_t npoints) {
     p.cap = (uint32_t)cap;
     // Batched-affine pair levels before the XYZZ accumulation pay off only when every level still fills the
     // GPU (tools/ab_pair.py sweep after the CTA-shared inversion): none below 2^20 points, 1 at 2^20, 4 from 2^21.
-    int levels = lg >= 21 ? 4 : lg == 20 ? 1 : 0;
+    // (re-swept in round 2 with the record-scatter sort, profiles/r2g_ab_records.log, r2h_ab_karatsuba_build.log: 5 levels from
+    // 2^23, 4 at 2^21–2^22, 3 at 2^20, 2 at 2^19 with c = 13)
+    int levels = lg >= 23 ? 5 : lg >= 21 ? 4 : lg == 20 ? 3 : lg == 19 ? 2 : 0;
     while (levels > 0 && ((npoints >> (c - 1)) >> levels) < 2) levels--;
     if (const char* e = getenv("SNARKVM_B200_MSM_LEVELS")) { int v = atoi(e); if (v >= 0 && v <= 16) levels = v; }
     p.levels = levels;
@@ -94,7 +97,7 @@ MsmPlan msm_make_plan_batch(size_t max_n, size_t total_n) {
     MsmPlan p = msm_make_plan(max_n);
     if (total_n > max_n) {
         int lgt = ceil_log2(total_n < 2 ? 2 : total_n);
-        int levels = lgt >= 21 ? 4 : lgt == 20 ? 1 : 0;
+        int levels = lgt >= 23 ? 5 : lgt >= 21 ? 4 : lgt == 20 ? 3 : lgt == 19 ? 2 : 0;
         while (levels > 0 && ((max_n >> (p.c - 1)) >> levels) < 2) levels--;
         if (const char* e = getenv("SNARKVM_B200_MSM_LEVELS")) { int v = atoi(e); if (v >= 0 && v <= 16) levels = v; }
         if (levels > p.levels) p.levels = levels;
@@ -167,6 +170,82 @@ __global__ void k_items_per_bucket(const uint32_t* __restrict__ hist, uint32_t* 
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < total_buckets) items[i] = (hist[i] + cap - 1u) / cap;
     else if (i == total_buckets) items[i] = 0;
+}
+
+// Sort pass of the pair-level path (round 2): instead of an index array that level 0 would have to chase through a
+// random gather (ncu, profiles/r2f_*: the gathering level ran the multiplier at 57 % where the dense levels reach 83 % —
+// 32 DRAM lines per LDGSTS instruction, MIO and scoreboard stalls with only 4 warps per scheduler to hide them), the
+// scatter writes the RECORDS themselves: point i is read once, and for every window its 96-byte (x, ±y) image goes to the
+// slot the bucket cursor hands out.  Level 0 then reads a dense, already signed array exactly like the levels above it.
+// The CTA stages its 256 points (x, y, −y) in shared memory and writes each window's records cooperatively, six
+// consecutive lanes per record, so a store instruction touches 6 lines instead of 32.
+// Windows [w_lo, w_hi) of this segment belong to the current group of bucket sets; positions are relative to *pos_base.
+static constexpr uint32_t REC_NONE = 0xffffffffu;
+template <bool MONT>
+__global__ void __launch_bounds__(256) k_scatter_records(const uint32_t* __restrict__ scalars, size_t n, const uint8_t* __restrict__ points,
+                                                         size_t stride, int c, uint32_t nbuckets, uint32_t* __restrict__ cursors,
+                                                         uint32_t slot_base, int w_lo, int w_hi, const uint32_t* __restrict__ pos_base_ptr,
+                                                         uint4* __restrict__ dense0) {
+    __shared__ uint4 sh_rec[256 * 9];                       // per point: x (3 × 16 B), y (3), −y (3)
+    __shared__ uint32_t sh_pos[2][256];
+    const uint32_t tid = threadIdx.x;
+    const size_t i = (size_t)blockIdx.x * 256 + tid;
+    const bool live = i < n;
+    const uint32_t pos_base = __ldg(pos_base_ptr);
+    uint32_t s[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = 0u;
+    if (live) {
+        const uint4* q = reinterpret_cast<const uint4*>(scalars + 8 * i);
+        uint4 a = __ldg(q), b = __ldg(q + 1);
+        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+        if (MONT) {
+            Fr x;
+#pragma unroll
+            for (int k = 0; k < 8; k++) x.v[k] = s[k];
+            x = x.from_mont();
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = x.v[k];
+        }
+        AffinePoint pt = load_affine(points, stride, i);
+        Fq yn = pt.y.neg();
+        if (pt.inf) { pt.x = Fq::zero(); pt.y = Fq::zero(); yn = Fq::zero(); }      // (0, 0) is the dense encoding of infinity
+        uint4* r = sh_rec + tid * 9;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            r[k] = make_uint4(pt.x.v[4 * k], pt.x.v[4 * k + 1], pt.x.v[4 * k + 2], pt.x.v[4 * k + 3]);
+            r[3 + k] = make_uint4(pt.y.v[4 * k], pt.y.v[4 * k + 1], pt.y.v[4 * k + 2], pt.y.v[4 * k + 3]);
+            r[6 + k] = make_uint4(yn.v[4 * k], yn.v[4 * k + 1], yn.v[4 * k + 2], yn.v[4 * k + 3]);
+        }
+    }
+    const uint32_t half = 1u << (c - 1);
+    uint32_t carry = 0;
+    // One window at a time (issuing the cursor atomics of 8 windows back to back before one barrier was measured slower:
+    // 10.5 vs 9.0 ms at 2^24, profiles/r2h_ab_karatsuba_build.log — co-resident CTAs in different phases already overlap).
+    for (int w = 0; w < w_hi; w++) {
+        const int bit = w * c, wi = bit >> 5, sh = bit & 31;
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { if (k == wi) lo = s[k]; if (k == wi + 1) hi = s[k]; }
+        const uint32_t raw = (__funnelshift_r(lo, hi, sh) & ((1u << c) - 1u)) + carry;
+        const uint32_t neg = raw > half ? 1u : 0u;
+        const uint32_t mag = neg ? (1u << c) - raw : raw;
+        carry = neg;
+        if (w < w_lo) continue;
+        uint32_t pos = REC_NONE;
+        if (live && mag != 0u) pos = (atomicAdd(&cursors[slot_base + (uint32_t)w * nbuckets + (mag - 1u)], 1u) - pos_base) | (neg << 31);
+        uint32_t* my_pos = sh_pos[w & 1];
+        my_pos[tid] = pos;
+        __syncthreads();                                    // also orders the staging of sh_rec before the first window's reads
+        for (uint32_t k = tid; k < 256u * 6u; k += 256u) {
+            const uint32_t r = k / 6u, part = k - 6u * r;
+            const uint32_t pp = my_pos[r];
+            if (pp == REC_NONE) continue;
+            const uint32_t src = part < 3u ? part : ((pp >> 31) ? 3u : 0u) + part;       // x0..2 | y0..2 or (−y)0..2
+            dense0[(size_t)(pp & 0x7fffffffu) * 6u + part] = sh_rec[r * 9u + src];
+        }
+        // the next window writes the other half of sh_pos; its barrier orders this window's reads before the window after
+    }
 }
 
 // A dense base record: x, y (Montgomery) in one 128-byte line, infinity encoded as (0, 0) — written by k_densify_bases
@@ -275,77 +354,33 @@ __global__ void k_densify_bases(const uint8_t* __restrict__ points, size_t strid
     store_dense(out + i * BASE_WORDS, d);
 }
 // Precomputed tables for resident bases: record (w, i) = 2^{c·w}·P_i as a dense 128-byte affine record, w < nwin.
-// One thread per point walks the doubling chain in XYZZ and normalises every multiple (Fermat inversion each:
-// a one-off cost per SRS, ≈ 9k Fq mul per point).
-__global__ void __launch_bounds__(128) k_precompute_tables(const uint8_t* __restrict__ points, size_t stride, size_t n, int c, int nwin,
+// One thread per point walks the doubling chain in XYZZ; every multiple is normalised with ONE field inversion shared by
+// the 128 threads of the CTA (cta_inverse.cuh) instead of a Fermat ladder per record: ≈ 9·c + 12 Fq mul per record instead of
+// 9·c + 580 (round 1: 6.3 s for the 2^24-point tables).
+__global__ void __launch_bounds__(CTA_INV_THREADS) k_precompute_tables(const uint8_t* __restrict__ points, size_t stride, size_t n, int c, int nwin,
                                                             uint32_t* __restrict__ table) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    AffinePoint a = load_affine(points, stride, i);
+    __shared__ uint4 sh_inv[CTA_INV_SMEM_BYTES / 16];
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    AffinePoint a;
+    a.x = Fq::zero(); a.y = Fq::zero(); a.inf = true;
+    if (live) a = load_affine(points, stride, i);
     DensePoint d; d.x = a.x; d.y = a.y; d.inf = a.inf;
-    store_dense(table + i * BASE_WORDS, d);
+    if (live) store_dense(table + i * BASE_WORDS, d);
     XYZZ q = XYZZ::from_affine(a);
     for (int w = 1; w < nwin; w++) {
         for (int k = 0; k < c; k++) q.dbl();
-        AffinePoint t = q.to_affine();
-        d.x = t.x; d.y = t.y; d.inf = t.inf;
-        store_dense(table + ((size_t)w * n + i) * BASE_WORDS, d);
+        const bool inf = q.is_inf();
+        Fq z = inf ? Fq::one() : q.ZZ * q.ZZZ;
+        Fq iz = cta_shared_inverse_by(z, reinterpret_cast<uint32_t*>(sh_inv), w & 3);
+        __syncthreads();                                    // the next round overwrites the shared area
+        if (inf) { d.x = Fq::zero(); d.y = Fq::zero(); d.inf = true; }
+        else { d.x = q.X * (iz * q.ZZZ); d.y = q.Y * (iz * q.ZZ); d.inf = false; }
+        if (live) store_dense(table + ((size_t)w * n + i) * BASE_WORDS, d);
     }
 }
 
-static constexpr int PAIR_THREADS = 128;
-FF_DEV Fq shfl_up_fq(const Fq& a, int d) {
-    Fq r;
-#pragma unroll
-    for (int j = 0; j < 12; j++) r.v[j] = __shfl_up_sync(0xffffffffu, a.v[j], d);
-    return r;
-}
-FF_DEV Fq shfl_down_fq(const Fq& a, int d) {
-    Fq r;
-#pragma unroll
-    for (int j = 0; j < 12; j++) r.v[j] = __shfl_down_sync(0xffffffffu, a.v[j], d);
-    return r;
-}
-FF_DEV Fq shfl_idx_fq(const Fq& a, int l) {
-    Fq r;
-#pragma unroll
-    for (int j = 0; j < 12; j++) r.v[j] = __shfl_sync(0xffffffffu, a.v[j], l);
-    return r;
-}
-// One Fermat inversion per CTA instead of one per warp-lane: the 128 running products (all non-zero) go through shared memory,
-// ONE warp multiplies them together (4 per lane, then a shuffle scan across lanes), inverts the total and unwinds.  In SIMT
-// time an inversion costs a warp ≈ 515 Fq mul whether 1 or 32 lanes need it, so the per-thread version spends 4 × 515 per
-// CTA and this one ≈ 540.  The inverting warp rotates with blockIdx so co-resident CTAs load different SM sub-partitions.
-__device__ __noinline__ Fq cta_shared_inverse(const Fq& run, uint32_t* sh) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    run.store(sh + tid * 12);
-    __syncthreads();
-    if (warp == (int)(blockIdx.x & 3u)) {
-        uint32_t* mine = sh + lane * 48;
-        Fq a0 = Fq::load(mine), a1 = Fq::load(mine + 12), a2 = Fq::load(mine + 24), a3 = Fq::load(mine + 36);
-        Fq p1 = a0 * a1, p2 = p1 * a2, p3 = p2 * a3;
-        Fq incl = p3, suff = p3;                           // inclusive prefix / suffix products over lanes
-#pragma unroll 1
-        for (int d = 1; d < 32; d <<= 1) {
-            Fq up = shfl_up_fq(incl, d), dn = shfl_down_fq(suff, d);
-            if (lane >= d) incl = incl * up;
-            if (lane + d < 32) suff = suff * dn;
-        }
-        Fq tinv = shfl_idx_fq(incl, 31).inverse();
-        Fq before = shfl_up_fq(incl, 1), after = shfl_down_fq(suff, 1);
-        Fq ip3 = tinv;                                     // 1 / p3 of this lane = tinv · Π(other lanes)
-        if (lane > 0) ip3 = ip3 * before;
-        if (lane < 31) ip3 = ip3 * after;
-        Fq ip2 = ip3 * a3, ip1 = ip2 * a2;
-        (ip3 * p2).store(mine + 36);                       // 1/a3
-        (ip2 * p1).store(mine + 24);                       // 1/a2
-        (ip1 * a0).store(mine + 12);                       // 1/a1
-        (ip1 * a1).store(mine);                            // 1/a0
-    }
-    __syncthreads();
-    return Fq::load(sh + tid * 12);
-}
-
+static constexpr int PAIR_THREADS = CTA_INV_THREADS;
 enum PairKind { PAIR_COPY1 = 0, PAIR_COPY2 = 1, PAIR_INF = 2, PAIR_ADD = 3, PAIR_DBL = 4 };
 FF_DEV int classify_pair(const DensePoint& P, const DensePoint& Q, bool has2, Fq& d) {
     if (!has2 || Q.inf) return PAIR_COPY1;
@@ -473,7 +508,8 @@ FF_DEV Fq ring_fq(const uint4* slot) {                       // slot = &ring[(st
 static constexpr uint32_t PAIR_NONE = 0xffffffffu;
 template <bool GATHER>
 __global__ void __launch_bounds__(256) k_pair_desc(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off_in,
-                                                   const uint32_t* __restrict__ off_out, uint32_t total_buckets, uint2* __restrict__ desc) {
+                                                   const uint32_t* __restrict__ off_out, uint32_t total_buckets, uint2* __restrict__ desc,
+                                                   const uint32_t* __restrict__ in_base_ptr /* dense inputs: *in_base_ptr = position of element 0, or null */) {
     const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= __ldg(off_out + total_buckets)) return;
     uint32_t lo = 0, hi = total_buckets;                  // off_out[lo] <= o < off_out[hi]
@@ -483,7 +519,7 @@ __global__ void __launch_bounds__(256) k_pair_desc(const uint32_t* __restrict__ 
     const bool has2 = 2u * i + 1u < cnt;
     uint2 d;
     if (GATHER) { d.x = __ldg(sorted + idx); d.y = has2 ? __ldg(sorted + idx + 1) : PAIR_NONE; }
-    else { d.x = idx; d.y = has2 ? 0u : PAIR_NONE; }
+    else { d.x = idx - (in_base_ptr ? __ldg(in_base_ptr) : 0u); d.y = has2 ? 0u : PAIR_NONE; }
     desc[o] = d;
 }
 
@@ -529,37 +565,6 @@ FF_DEV int pair_classify_global(const PairDesc& d, const uint32_t* __restrict__ 
     DensePoint Q = load_dense(pair_src<GATHER>(d, 1, records));
     if (GATHER) { if ((d.p >> 31) && !P.inf) P.y = P.y.neg(); if ((d.q >> 31) && !Q.inf) Q.y = Q.y.neg(); }
     return classify_pair(P, Q, true, den);
-}
-
-// One Fermat inversion per CTA (see cta_shared_inverse above), here with the inverting warp chosen by the caller.
-__device__ __noinline__ Fq cta_shared_inverse_by(const Fq& run, uint32_t* sh, int inv_warp) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    run.store(sh + tid * 12);
-    __syncthreads();
-    if (warp == inv_warp) {
-        uint32_t* mine = sh + lane * 48;
-        Fq a0 = Fq::load(mine), a1 = Fq::load(mine + 12), a2 = Fq::load(mine + 24), a3 = Fq::load(mine + 36);
-        Fq p1 = a0 * a1, p2 = p1 * a2, p3 = p2 * a3;
-        Fq incl = p3, suff = p3;                           // inclusive prefix / suffix products over lanes
-#pragma unroll 1
-        for (int d = 1; d < 32; d <<= 1) {
-            Fq up = shfl_up_fq(incl, d), dn = shfl_down_fq(suff, d);
-            if (lane >= d) incl = incl * up;
-            if (lane + d < 32) suff = suff * dn;
-        }
-        Fq tinv = coop_inverse<FqParams>(shfl_idx_fq(incl, 31));   // one element, limb-per-lane: ≈ 4× fewer instructions than 32 redundant chains
-        Fq before = shfl_up_fq(incl, 1), after = shfl_down_fq(suff, 1);
-        Fq ip3 = tinv;                                     // 1 / p3 of this lane = tinv · Π(other lanes)
-        if (lane > 0) ip3 = ip3 * before;
-        if (lane < 31) ip3 = ip3 * after;
-        Fq ip2 = ip3 * a3, ip1 = ip2 * a2;
-        (ip3 * p2).store(mine + 36);                       // 1/a3
-        (ip2 * p1).store(mine + 24);                       // 1/a2
-        (ip1 * a0).store(mine + 12);                       // 1/a1
-        (ip1 * a1).store(mine);                            // 1/a0
-    }
-    __syncthreads();
-    return Fq::load(sh + tid * 12);
 }
 
 // The shared inversion is a bubble — one warp works while the CTA's other warps wait at the barrier, and CTAs that start
@@ -970,14 +975,39 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
     if (flat && table_n * (size_t)plan.nwin >= (1ull << 31)) return (int)cudaErrorInvalidValue;
     const int levels = plan.levels;
     const size_t set_cap = flat ? max_job_n * (size_t)plan.nwin : max_job_n;   // most entries one bucket set (or one bucket) can hold
+    // pair levels over plain bases: the sort scatters 96-byte records (k_scatter_records) and every level is dense;
+    // tables (flat) and the XYZZ-only path keep the index sort + gather
+    bool records = !flat && levels > 0;
+    if (const char* e = getenv("SNARKVM_B200_MSM_RECORDS")) records = records && atoi(e) != 0;
+    if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_V1")) { if (atoi(e) != 0) records = false; }      // the round-1 kernel gathers
+    // a scalar segment must lie inside one base array (the record scatter reads its points through one pointer)
+    std::vector<const uint8_t*> seg_points((size_t)nsegs, nullptr);
+    std::vector<size_t> seg_stride((size_t)nsegs, 0);
+    if (records) {
+        for (int i = 0; i < nsegs; i++) {
+            size_t off = 0; bool found = segs[i].n == 0;
+            for (int k = 0; k < nbases && !found; k++) {
+                if (segs[i].base0 >= off && (size_t)segs[i].base0 + segs[i].n <= off + bases[k].n) {
+                    seg_points[i] = (const uint8_t*)bases[k].d_points + ((size_t)segs[i].base0 - off) * bases[k].stride;
+                    seg_stride[i] = bases[k].stride;
+                    found = true;
+                }
+                off += bases[k].n;
+            }
+            if (!found) return (int)cudaErrorInvalidValue;
+        }
+    }
 
     // Everything after the bucket sort runs per GROUP of whole bucket sets, so the dense scratch of the pair levels
-    // (≈ 100 B per entry) stays inside a budget: 2^24 points → 15 windows in 3 groups of 5, a 2^26-point shard 1–2 windows at a time.
-    size_t budget = (size_t)12 << 30;
+    // (≈ 200 B per entry with the level-0 records) stays inside a budget: 2^24 points → 15 windows in one group (49 GB), a
+    // 2^26-point shard four windows at a time.
+    size_t budget = (size_t)64 << 30;
     if (const char* e = getenv("SNARKVM_B200_MSM_SCRATCH_GB")) { long v = atol(e); if (v >= 1) budget = (size_t)v << 30; }
+    if (const char* e = getenv("SNARKVM_B200_MSM_SCRATCH_MB")) { long v = atol(e); if (v >= 1) budget = (size_t)v << 20; }      // tests: force many groups
     uint32_t gw = nsets;
     if (levels > 0) {
-        size_t per_set = set_cap * (size_t)104 + 1;          // dense_a 48 + dense_b 24 + prefix 24 + descriptors 4, +4 sorted
+        // per entry: dense_a 48 + dense_b 24 + prefix 24 + descriptors 4, plus the 96-byte level-0 records or the 4-byte index
+        size_t per_set = set_cap * (size_t)(records ? 196 : 104) + 1;
         size_t fit = budget / per_set;
         if (fit < 1) fit = 1;
         if (fit < gw) {
@@ -988,6 +1018,7 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
     const uint32_t TBg = gw * plan.nbuckets;                      // buckets of the largest group
     size_t entries_g = set_cap * (size_t)gw;                      // most entries a group can hold
     if (entries_g > max_entries) entries_g = max_entries;
+    if (records && entries_g >= 0x7fffffffull) return (int)cudaErrorInvalidValue;      // record positions carry the sign in bit 31
     const size_t max_items = (size_t)TBg + entries_g / plan.cap + 1;
     const size_t dense_cap_a = entries_g / 2 + TBg + 1, dense_cap_b = entries_g / 4 + 2 * (size_t)TBg + 1;
 
@@ -1023,6 +1054,7 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
     // ---- one scratch block, carved up ----
     uint32_t *hist, *bucket_start, *cursors, *items, *item_start, *items2, *sorted, *partial, *partial2, *red_a, *red_b;
     uint32_t *off_a = nullptr, *off_b = nullptr, *dense_a = nullptr, *dense_b = nullptr, *prefix = nullptr, *dense_bases = nullptr, *sm_slots = nullptr;
+    uint32_t *dense0 = nullptr, *cnt_tmp = nullptr;
     uint2* desc = nullptr;
     uint8_t* cub_tmp;
     Arena ar;
@@ -1033,13 +1065,15 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
         items = a.take<uint32_t>((size_t)TBg + 1);
         item_start = a.take<uint32_t>((size_t)TBg + 1);
         items2 = a.take<uint32_t>((size_t)TBg + 1);
-        sorted = a.take<uint32_t>(max_entries);
+        sorted = records ? nullptr : a.take<uint32_t>(max_entries);
+        cnt_tmp = a.take<uint32_t>((size_t)TBg + 1);
         partial = a.take<uint32_t>(max_items * XYZZ_WORDS);
         partial2 = a.take<uint32_t>(((size_t)TBg + max_items / 32 + 2) * XYZZ_WORDS);
         red_a = a.take<uint32_t>((size_t)gw * chunks_per_set * XYZZ_WORDS);
         red_b = a.take<uint32_t>((size_t)gw * (chunks_per_set / tree + 1) * XYZZ_WORDS);
         cub_tmp = a.take<uint8_t>(cub_bytes);
-        if (!flat) dense_bases = a.take<uint32_t>(total_bases * (size_t)BASE_WORDS);
+        if (!flat && !records) dense_bases = a.take<uint32_t>(total_bases * (size_t)BASE_WORDS);
+        if (records) dense0 = a.take<uint32_t>(entries_g * (size_t)DENSE_WORDS);
         if (levels > 0) {
             off_a = a.take<uint32_t>((size_t)TBg + 1);
             off_b = a.take<uint32_t>((size_t)TBg + 1);
@@ -1064,7 +1098,7 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
         // ---- bucket sort of all jobs and windows: histogram → offsets → scatter ----
         {
             ProfScope sort_scope(PROF_MSM_SORT, stream);
-            for (int pass = 0; pass < 2; pass++) {
+            for (int pass = 0; pass < (records ? 1 : 2); pass++) {
                 for (int i = 0; i < nsegs; i++) {
                     const MsmSegment& sg = segs[i];
                     if (sg.n == 0) continue;
@@ -1089,7 +1123,7 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
             }
         }
         const uint32_t* gather_src = flat ? table : dense_bases;
-        if (!flat) {
+        if (!flat && !records) {
             ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
             size_t at = 0;
             for (int i = 0; i < nbases; i++) {
@@ -1122,17 +1156,36 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
                     gather_src, sorted, bs, item_start, tb, plan.cap, partial);
                 count_launch();
             } else {
+                if (records) {
+                    // this group's records: every segment re-derives its digits and emits the windows that fall into the group
+                    ProfScope sort_scope(PROF_MSM_SORT, stream);
+                    for (int i = 0; i < nsegs; i++) {
+                        const MsmSegment& sg = segs[i];
+                        if (sg.n == 0) continue;
+                        const int64_t first = (int64_t)sg.job * plan.nwin;                            // bucket set of the segment's window 0
+                        const int64_t lo_w = (int64_t)w0 - first, hi_w = (int64_t)w0 + wn - first;
+                        const int w_lo = lo_w < 0 ? 0 : (int)lo_w, w_hi = hi_w > plan.nwin ? plan.nwin : (int)hi_w;
+                        if (w_lo >= w_hi) continue;
+                        const unsigned grid = (unsigned)((sg.n + 255) / 256);
+                        const uint32_t slot_base = sg.job * sets_per_job * plan.nbuckets;
+                        if (sg.mont) k_scatter_records<true><<<grid, 256, 0, stream>>>((const uint32_t*)sg.d_scalars, sg.n, seg_points[i], seg_stride[i], plan.c, plan.nbuckets,
+                                                                                       cursors, slot_base, w_lo, w_hi, bs, (uint4*)dense0);
+                        else k_scatter_records<false><<<grid, 256, 0, stream>>>((const uint32_t*)sg.d_scalars, sg.n, seg_points[i], seg_stride[i], plan.c, plan.nbuckets,
+                                                                                cursors, slot_base, w_lo, w_hi, bs, (uint4*)dense0);
+                        count_launch();
+                    }
+                }
                 ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
                 const uint32_t* off_in = bs;
                 uint32_t* off_bufs[2] = {off_a, off_b};
                 uint32_t* dense_bufs[2] = {dense_a, dense_b};
-                const uint32_t* dense_in = nullptr;
+                const uint32_t* dense_in = records ? dense0 : nullptr;
                 size_t bound = entries;                                  // upper bound on the level's input count
                 for (int l = 0; l < levels; l++) {
                     uint32_t* off_out = off_bufs[l & 1];
                     uint32_t* dense_out = dense_bufs[l & 1];
-                    k_halve_counts<<<(tb + 256) / 256, 256, 0, stream>>>(off_in, cursors, tb);
-                    CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cursors, off_out, (int)(tb + 1), stream));
+                    k_halve_counts<<<(tb + 256) / 256, 256, 0, stream>>>(off_in, cnt_tmp, tb);
+                    CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cnt_tmp, off_out, (int)(tb + 1), stream));
                     bound = bound / 2 + tb;                              // Σ ceil(cnt/2) ≤ Σ cnt/2 + #buckets
                     // Whole waves: 148 SMs × 4 resident CTAs × 128 threads = 75776 lanes run at once; give every lane
                     // the same number T of outputs and launch an integer number of such waves, so no partial last wave
@@ -1146,18 +1199,18 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
                     // level 0 reads absolute positions of `sorted` (off_in = bs); its outputs and all later levels are
                     // group-relative (the scans start at 0)
                     if (pair_v1) {
-                        if (l == 0)
+                        if (l == 0 && !records)
                             k_pair_level<true><<<lgrid, 128, 0, stream>>>(gather_src, sorted, nullptr, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
                         else
                             k_pair_level<false><<<lgrid, 128, 0, stream>>>(nullptr, nullptr, dense_in, off_in, off_out, tb, (uint32_t)T, prefix, dense_out);
                     } else {
                         const unsigned dgrid = (unsigned)((bound + 255) / 256);
-                        if (l == 0) {
-                            k_pair_desc<true><<<dgrid, 256, 0, stream>>>(sorted, off_in, off_out, tb, desc);
+                        if (l == 0 && !records) {
+                            k_pair_desc<true><<<dgrid, 256, 0, stream>>>(sorted, off_in, off_out, tb, desc, nullptr);
                             if (pair_minb == 3) k_pair_level2<true, 3><<<lgrid, 128, PAIR2_SMEM, stream>>>(gather_src, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots);
                             else k_pair_level2<true, 4><<<lgrid, 128, PAIR2_SMEM, stream>>>(gather_src, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots);
                         } else {
-                            k_pair_desc<false><<<dgrid, 256, 0, stream>>>(nullptr, off_in, off_out, tb, desc);
+                            k_pair_desc<false><<<dgrid, 256, 0, stream>>>(nullptr, off_in, off_out, tb, desc, l == 0 ? bs : nullptr);
                             if (pair_minb == 3) k_pair_level2<false, 3><<<lgrid, 128, PAIR2_SMEM, stream>>>(dense_in, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots);
                             else k_pair_level2<false, 4><<<lgrid, 128, PAIR2_SMEM, stream>>>(dense_in, desc, off_out + tb, (uint32_t)T, prefix, dense_out, sm_slots);
                         }
@@ -1187,8 +1240,8 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
                 uint32_t* p_in = partial; uint32_t* p_out = partial2;
                 uint32_t* st_in = item_start; uint32_t* st_out = items2;
                 while (worst > 1) {
-                    k_group_counts<<<(tb + 256) / 256, 256, 0, stream>>>(st_in, cursors, tb);
-                    CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cursors, st_out, (int)(tb + 1), stream));
+                    k_group_counts<<<(tb + 256) / 256, 256, 0, stream>>>(st_in, cnt_tmp, tb);
+                    CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cnt_tmp, st_out, (int)(tb + 1), stream));
                     const size_t out_bound = (size_t)tb + total_bound / 32 + 1;
                     total_bound = out_bound;
                     k_partial_group_sum<<<(unsigned)((out_bound + 127) / 128), 128, 0, stream>>>(p_in, st_in, st_out, tb, p_out);
@@ -1380,6 +1433,33 @@ __global__ void __launch_bounds__(128) k_selftest_coop(uint32_t nwarps, uint64_t
     const Fq one = inv * a;
     if (a.is_zero()) bad = bad || !inv.is_zero();
     else bad = bad || (one != Fq::one()) || (inv != a.inverse());
+    // the Karatsuba multiplier against the word-serial schoolbook one, per lane, Fq and Fr: random operands, operands whose
+    // halves are equal / swapped (every sign combination of the middle term), 0, 1, p − 1
+    {
+        const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+        Fq x, y;
+        Fr u, v;
+#pragma unroll
+        for (int k = 0; k < 12; k += 2) {
+            uint64_t rx = splitmix64(seed * 3 + 0x1000ull * t + (uint64_t)k), ry = splitmix64(~seed * 5 + 0x1000ull * t + (uint64_t)k);
+            x.v[k] = (uint32_t)rx; x.v[k + 1] = (uint32_t)(rx >> 32); y.v[k] = (uint32_t)ry; y.v[k + 1] = (uint32_t)(ry >> 32);
+        }
+        x.v[11] &= 0x00ffffffu; y.v[11] &= 0x00ffffffu;
+        if ((t & 7u) == 1u) { for (int k = 0; k < 6; k++) { y.v[k] = x.v[k + 6]; y.v[k + 6] = x.v[k]; } y.v[11] &= 0x00ffffffu; y.v[5] = x.v[11]; }
+        if ((t & 7u) == 2u) { for (int k = 0; k < 6; k++) x.v[k + 6] = x.v[k]; x.v[11] &= 0x00ffffffu; }
+        if (t == 8u) x = Fq::zero();
+        if (t == 9u) y = Fq::one();
+        if (t == 10u) { x = Fq::zero() - Fq::one(); y = x; }
+        if (t == 11u) { x = Fq::zero() - Fq::one(); }
+#pragma unroll
+        for (int k = 0; k < 8; k++) { u.v[k] = x.v[k] ^ y.v[11 - k]; v.v[k] = y.v[k] + x.v[11 - k]; }
+        u.v[7] &= 0x0fffffffu; v.v[7] &= 0x0fffffffu;
+        if ((t & 7u) == 3u) { for (int k = 0; k < 4; k++) v.v[k + 4] = v.v[k]; v.v[7] &= 0x0fffffffu; }
+        if (t == 12u) { u = Fr::zero() - Fr::one(); v = u; }
+        bool bad2 = Fq::mul_karatsuba(x, y) != Fq::mul_inline(x, y) || Fq::mul_karatsuba(x, x) != Fq::sqr_inline(x);
+        bad2 = bad2 || Fr::mul_karatsuba(u, v) != Fr::mul_inline(u, v) || Fr::mul_karatsuba(v, v) != Fr::sqr_inline(v);
+        bad = bad || bad2;
+    }
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(mismatches, 1u);
 }
 int selftest_coop_device(uint32_t nwarps, uint64_t seed, uint32_t* d_mismatches, cudaStream_t stream) {

@@ -163,21 +163,28 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
     // [tile_elems + i]): consecutive threads then touch consecutive 16-byte words — conflict-free LDS/STS.128 — where
     // the 32-byte array-of-structures layout made every access a 2-way bank conflict (profiles/r1a_ntt_pass_metrics.csv).
     extern __shared__ uint4 smem_raw[];
+    // Column index XOR row index (low Q bits): the last pass fills the tile column by column (consecutive threads →
+    // consecutive ROWS, a stride of 2^Q 16-byte words = one bank group), which was an 8-way conflict per store
+    // (31.8 M conflicts in round 1's ncu of the last pass, 12× the other passes); with the swizzle consecutive rows land in
+    // different bank groups and row-wise accesses stay a permutation of one 128-byte line.
     struct Tile {
-        uint4* p; uint32_t n;
-        __device__ __forceinline__ Fr get(uint32_t i) const {
+        uint4* p; uint32_t n; uint32_t q, cmask;
+        __device__ __forceinline__ uint32_t sw(uint32_t i) const { return i ^ ((i >> q) & cmask); }
+        __device__ __forceinline__ Fr get(uint32_t i0) const {
+            const uint32_t i = sw(i0);
             uint4 a = p[i], b = p[n + i]; Fr r;
             r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
             return r;
         }
-        __device__ __forceinline__ void put(uint32_t i, const Fr& r) const {
+        __device__ __forceinline__ void put(uint32_t i0, const Fr& r) const {
+            const uint32_t i = sw(i0);
             p[i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]); p[n + i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
         }
     };
     const int S = a.S, Q = a.Q, lg = a.lg, t0 = a.t0;
     const int L = lg - t0 - S;                       // low index bits below the tile's row digit
     const uint32_t rows = 1u << S, cols = 1u << Q, tile_elems = rows << Q;
-    const Tile sm{smem_raw, tile_elems};
+    const Tile sm{smem_raw, tile_elems, (uint32_t)Q, cols - 1u};
     const size_t tile = blockIdx.x;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
 

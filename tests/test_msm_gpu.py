@@ -255,6 +255,41 @@ def test_msm_pair_levels_edge_cases(oracle_cpu, bases64k, monkeypatch, levels, c
     assert (VariableBase.msm(bases, np.zeros((n, 4), dtype=np.uint64)) == inf).all()
 
 
+@pytest.mark.parametrize("levels,c,mb", [(1, 9, 2), (3, 8, 9), (2, 11, 13)])
+def test_msm_record_scatter_window_groups(oracle_cpu, bases64k, monkeypatch, levels, c, mb):
+    """The record-scatter sort (k_scatter_records) with a scratch budget so small that the bucket sets are processed in many
+    groups: every group re-derives the digits and emits only its own windows; jobs of a batch and the hiding segment (second
+    base array) cross group boundaries too."""
+    from snarkvm_b200 import device
+    from snarkvm_b200.algorithms import KZG10, VariableBase
+    monkeypatch.setenv("SNARKVM_B200_MSM_LEVELS", str(levels))
+    monkeypatch.setenv("SNARKVM_B200_MSM_C", str(c))
+    monkeypatch.setenv("SNARKVM_B200_MSM_SCRATCH_MB", str(mb))
+    n = 20000
+    bases = bases64k[:n].copy()
+    scal = random_canonical_fr(n, seed=77 + levels)
+    scal[:40] = 0
+    bases[40:60, 96] = 1                                              # points at infinity
+    scal[100:400] = scal[99]                                          # a hot bucket in every window
+    assert (VariableBase.msm(bases, scal) == oracle_cpu.msm(bases, scal, 1)).all()
+    # a batch whose jobs straddle group boundaries, Montgomery coefficients, with blinding terms on a second base array
+    dbases = _dev(bases64k)
+    gamma = device.generate_bases(8, seed=99)
+    gamma_h = gamma.cpu().numpy()
+    lens, blens = [9000, 0, 20000, 1, 13000], [3, 2, 0, 0, 8]
+    polys = [random_canonical_fr(k, seed=300 + i) for i, k in enumerate(lens)]
+    blinds = [random_canonical_fr(k, seed=400 + i) if k else None for i, k in enumerate(blens)]
+    got = KZG10.batch_commit(dbases, [_dev(p) for p in polys], gamma, [None if b is None else _dev(b) for b in blinds])
+    for i, (p, b) in enumerate(zip(polys, blinds)):
+        want = oracle_cpu.msm(bases64k[:len(p)], oracle_cpu.fr_from_mont(p), 0)
+        if b is not None:
+            want = oracle_cpu.g1_add(want, oracle_cpu.msm(gamma_h[:len(b)], oracle_cpu.fr_from_mont(b), 0))
+        assert (got[i] == want).all(), i
+    # the index-sort + gather path must agree (A/B switch)
+    monkeypatch.setenv("SNARKVM_B200_MSM_RECORDS", "0")
+    assert (VariableBase.msm(bases, scal) == oracle_cpu.msm(bases, scal, 1)).all()
+
+
 def test_registered_bases(oracle_cpu, bases64k):
     """snarkvm_b200_register_bases: snarkvm_msm recognises the registered host pointer and skips the upload"""
     from snarkvm_b200 import CudaError, cuda

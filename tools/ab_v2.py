@@ -26,11 +26,15 @@ for lg in sizes:
     scal = torch.from_numpy(s.view(np.int64)).cuda()
     ref = None
     KEYS = ("SNARKVM_B200_MSM_PAIR_V1", "SNARKVM_B200_MSM_SCRATCH_GB", "SNARKVM_B200_MSM_LEVELS", "SNARKVM_B200_MSM_C", "SNARKVM_B200_MSM_PAIR_PARTS", "SNARKVM_B200_MSM_PAIR_MINB")
-    for tag, env in (("v1 40GB", {"SNARKVM_B200_MSM_PAIR_V1": "1", "SNARKVM_B200_MSM_SCRATCH_GB": "40"}),
-                     ("v4 minb4", {}), ("v4 minb3", {"SNARKVM_B200_MSM_PAIR_MINB": "3"}),
-                     ("v4 minb4 40GB", {"SNARKVM_B200_MSM_SCRATCH_GB": "40"}),
-                     ("v4 minb3 40GB", {"SNARKVM_B200_MSM_SCRATCH_GB": "40", "SNARKVM_B200_MSM_PAIR_MINB": "3"}),
-                     ("v4 minb3 40GB L5", {"SNARKVM_B200_MSM_SCRATCH_GB": "40", "SNARKVM_B200_MSM_PAIR_MINB": "3", "SNARKVM_B200_MSM_LEVELS": "5"})):
+    KEYS = KEYS + ("SNARKVM_B200_MSM_RECORDS",)
+    if lg >= 20:
+        variants = (("default", {}), ("minb3", {"SNARKVM_B200_MSM_PAIR_MINB": "3"}), ("L4", {"SNARKVM_B200_MSM_LEVELS": "4"}),
+                    ("L6", {"SNARKVM_B200_MSM_LEVELS": "6"}), ("c16", {"SNARKVM_B200_MSM_C": "16"}), ("c18", {"SNARKVM_B200_MSM_C": "18"}),
+                    ("40GB", {"SNARKVM_B200_MSM_SCRATCH_GB": "40"}))
+    else:
+        variants = (("default", {}), ("L2", {"SNARKVM_B200_MSM_LEVELS": "2"}), ("L3", {"SNARKVM_B200_MSM_LEVELS": "3"}),
+                    ("L3 c14", {"SNARKVM_B200_MSM_LEVELS": "3", "SNARKVM_B200_MSM_C": "14"}), ("L2 c13", {"SNARKVM_B200_MSM_LEVELS": "2", "SNARKVM_B200_MSM_C": "13"}))
+    for tag, env in variants:
         for k in KEYS: os.environ.pop(k, None)
         os.environ.update(env)
         got = device.msm(bases, scal)
