@@ -205,7 +205,7 @@ private:
         int active = 0;                                           // workers inside work(); guarded by mu_
     };
     CopyPool() {
-        int n = 6;
+        int n = 12;                                              // 2^24-point pageable snarkvm_msm: 6 → 128 ms, 12 → 114–120 ms, 24/48 no better (profiles/r2i_e2e_pageable.log)
         if (const char* e = getenv("SNARKVM_B200_COPY_THREADS")) { int v = atoi(e); if (v >= 0 && v <= 64) n = v; }
         nthreads_ = n;
         for (int i = 0; i < n; i++) std::thread([this] { loop(); }).detach();
@@ -427,10 +427,10 @@ snarkvm_error_t snarkvm_polymul(void* out, size_t pcount, const void* polynomial
 // Large host-buffer MSMs are cut into point ranges: range k+1 crosses PCIe on the thread's copy stream while range k is in
 // the Pippenger kernels (an MSM is a sum over points: every range is a complete MSM with its own plan and the results add).
 // 2^24 points: 2.28 GB of upload, ≈ 40 ms, of which only the first range's share stays exposed — so the first range is small
-// (1/8 of the points), then 3/8, then 1/2.  SNARKVM_B200_MSM_CHUNKS = "1", "2" (equal parts) or weights like "1:3:4".
+// (1/16 of the points), then 1/8, 1/4 and the rest (swept in profiles/r2i_e2e_pageable.log).  SNARKVM_B200_MSM_CHUNKS = "1", "2" (equal parts) or weights like "1:3:4".
 static std::vector<size_t> msm_ranges(size_t npoints) {
     std::vector<size_t> w;
-    if (npoints >= ((size_t)1 << 23)) w = {1, 3, 4};
+    if (npoints >= ((size_t)1 << 23)) w = {1, 2, 4, 9};
     if (const char* e = getenv("SNARKVM_B200_MSM_CHUNKS")) {
         std::vector<size_t> v;
         for (const char* p = e; *p;) {

@@ -170,6 +170,7 @@ FF_DEV uint32_t abs_diff(const uint32_t* x, const uint32_t* y, uint32_t (&d)[H])
 template <class P>
 struct Fp {
     static constexpr int N = P::N;
+    static constexpr int WORDS = P::N;
     uint32_t v[N];
 
     FF_DEV static Fp zero() { Fp r;

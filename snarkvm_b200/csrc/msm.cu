@@ -172,6 +172,20 @@ __global__ void k_items_per_bucket(const uint32_t* __restrict__ hist, uint32_t* 
     else if (i == total_buckets) items[i] = 0;
 }
 
+// Dense points are 96 B (x, y Montgomery); infinity is encoded as (0, 0), which is not on y² = x³ + 1.
+static constexpr int DENSE_WORDS = 24;
+static constexpr int BASE_WORDS = 32;       // level-0 copy of the bases: 96 B padded to one 128-byte line per point
+
+struct DensePoint { Fq x, y; bool inf; };
+FF_DEV DensePoint load_dense(const uint32_t* p) {
+    DensePoint d; d.x = Fq::load_ldg(p); d.y = Fq::load_ldg(p + 12);
+    d.inf = d.x.is_zero() && d.y.is_zero();
+    return d;
+}
+FF_DEV void store_dense(uint32_t* p, const DensePoint& d) {
+    if (d.inf) { Fq z = Fq::zero(); z.store(p); z.store(p + 12); }
+    else { d.x.store(p); d.y.store(p + 12); }
+}
 // Sort pass of the pair-level path (round 2): instead of an index array that level 0 would have to chase through a
 // random gather (ncu, profiles/r2f_*: the gathering level ran the multiplier at 57 % where the dense levels reach 83 % —
 // 32 DRAM lines per LDGSTS instruction, MIO and scoreboard stalls with only 4 warps per scheduler to hide them), the
@@ -181,11 +195,13 @@ __global__ void k_items_per_bucket(const uint32_t* __restrict__ hist, uint32_t* 
 // consecutive lanes per record, so a store instruction touches 6 lines instead of 32.
 // Windows [w_lo, w_hi) of this segment belong to the current group of bucket sets; positions are relative to *pos_base.
 static constexpr uint32_t REC_NONE = 0xffffffffu;
-template <bool MONT>
+// FLAT (precomputed tables): window w of point i takes record w·table_n + i of the table (staged per window) and every window
+// feeds the job's single bucket set.
+template <bool MONT, bool FLAT>
 __global__ void __launch_bounds__(256) k_scatter_records(const uint32_t* __restrict__ scalars, size_t n, const uint8_t* __restrict__ points,
-                                                         size_t stride, int c, uint32_t nbuckets, uint32_t* __restrict__ cursors,
-                                                         uint32_t slot_base, int w_lo, int w_hi, const uint32_t* __restrict__ pos_base_ptr,
-                                                         uint4* __restrict__ dense0) {
+                                                         size_t stride, const uint32_t* __restrict__ table, size_t table_n, int c, uint32_t nbuckets,
+                                                         uint32_t* __restrict__ cursors, uint32_t slot_base, int w_lo, int w_hi,
+                                                         const uint32_t* __restrict__ pos_base_ptr, uint4* __restrict__ dense0) {
     __shared__ uint4 sh_rec[256 * 9];                       // per point: x (3 × 16 B), y (3), −y (3)
     __shared__ uint32_t sh_pos[2][256];
     const uint32_t tid = threadIdx.x;
@@ -195,6 +211,17 @@ __global__ void __launch_bounds__(256) k_scatter_records(const uint32_t* __restr
     uint32_t s[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) s[k] = 0u;
+    auto stage = [&](Fq x, Fq y, bool inf) {
+        Fq yn = y.neg();
+        if (inf) { x = Fq::zero(); y = Fq::zero(); yn = Fq::zero(); }      // (0, 0) is the dense encoding of infinity
+        uint4* r = sh_rec + tid * 9;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            r[k] = make_uint4(x.v[4 * k], x.v[4 * k + 1], x.v[4 * k + 2], x.v[4 * k + 3]);
+            r[3 + k] = make_uint4(y.v[4 * k], y.v[4 * k + 1], y.v[4 * k + 2], y.v[4 * k + 3]);
+            r[6 + k] = make_uint4(yn.v[4 * k], yn.v[4 * k + 1], yn.v[4 * k + 2], yn.v[4 * k + 3]);
+        }
+    };
     if (live) {
         const uint4* q = reinterpret_cast<const uint4*>(scalars + 8 * i);
         uint4 a = __ldg(q), b = __ldg(q + 1);
@@ -207,15 +234,9 @@ __global__ void __launch_bounds__(256) k_scatter_records(const uint32_t* __restr
 #pragma unroll
             for (int k = 0; k < 8; k++) s[k] = x.v[k];
         }
-        AffinePoint pt = load_affine(points, stride, i);
-        Fq yn = pt.y.neg();
-        if (pt.inf) { pt.x = Fq::zero(); pt.y = Fq::zero(); yn = Fq::zero(); }      // (0, 0) is the dense encoding of infinity
-        uint4* r = sh_rec + tid * 9;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            r[k] = make_uint4(pt.x.v[4 * k], pt.x.v[4 * k + 1], pt.x.v[4 * k + 2], pt.x.v[4 * k + 3]);
-            r[3 + k] = make_uint4(pt.y.v[4 * k], pt.y.v[4 * k + 1], pt.y.v[4 * k + 2], pt.y.v[4 * k + 3]);
-            r[6 + k] = make_uint4(yn.v[4 * k], yn.v[4 * k + 1], yn.v[4 * k + 2], yn.v[4 * k + 3]);
+        if (!FLAT) {
+            AffinePoint pt = load_affine(points, stride, i);
+            stage(pt.x, pt.y, pt.inf);
         }
     }
     const uint32_t half = 1u << (c - 1);
@@ -232,11 +253,18 @@ __global__ void __launch_bounds__(256) k_scatter_records(const uint32_t* __restr
         const uint32_t mag = neg ? (1u << c) - raw : raw;
         carry = neg;
         if (w < w_lo) continue;
+        if (FLAT) {
+            if (w > w_lo) __syncthreads();                  // the previous window's records have been written out
+            if (live && mag != 0u) {
+                const DensePoint d = load_dense(table + ((size_t)w * table_n + i) * BASE_WORDS);
+                stage(d.x, d.y, d.inf);
+            }
+        }
         uint32_t pos = REC_NONE;
-        if (live && mag != 0u) pos = (atomicAdd(&cursors[slot_base + (uint32_t)w * nbuckets + (mag - 1u)], 1u) - pos_base) | (neg << 31);
+        if (live && mag != 0u) pos = (atomicAdd(&cursors[slot_base + (FLAT ? 0u : (uint32_t)w * nbuckets) + (mag - 1u)], 1u) - pos_base) | (neg << 31);
         uint32_t* my_pos = sh_pos[w & 1];
         my_pos[tid] = pos;
-        __syncthreads();                                    // also orders the staging of sh_rec before the first window's reads
+        __syncthreads();                                    // also orders the staging of sh_rec before the reads
         for (uint32_t k = tid; k < 256u * 6u; k += 256u) {
             const uint32_t r = k / 6u, part = k - 6u * r;
             const uint32_t pp = my_pos[r];
@@ -310,19 +338,6 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, MSM_ACC_MINBLOCKS) k_bucket_a
 // backward peeling off one inverse per pair: 6 Fq mul per addition instead of 10 for an XYZZ mixed add.
 // Dense points are 96 B (x, y Montgomery); infinity is encoded as (0, 0), which is not on y² = x³ + 1.
 // =================================================================================================
-static constexpr int DENSE_WORDS = 24;
-static constexpr int BASE_WORDS = 32;       // level-0 copy of the bases: 96 B padded to one 128-byte line per point
-
-struct DensePoint { Fq x, y; bool inf; };
-FF_DEV DensePoint load_dense(const uint32_t* p) {
-    DensePoint d; d.x = Fq::load_ldg(p); d.y = Fq::load_ldg(p + 12);
-    d.inf = d.x.is_zero() && d.y.is_zero();
-    return d;
-}
-FF_DEV void store_dense(uint32_t* p, const DensePoint& d) {
-    if (d.inf) { Fq z = Fq::zero(); z.store(p); z.store(p + 12); }
-    else { d.x.store(p); d.y.store(p + 12); }
-}
 // Level-0 inputs are gathered through `sorted` from a dense, 128-byte-aligned copy of the bases made once
 // per call by k_densify_bases: a gathered point then costs one DRAM line instead of the two or three that
 // the reference's 104-byte stride straddles.
@@ -803,6 +818,112 @@ __global__ void __launch_bounds__(128) k_group_sum(const uint32_t* __restrict__ 
     s.store(out + (size_t)t * XYZZ_WORDS);
 }
 
+// =================================================================================================
+// Latency path for small MSMs (≤ 2^18 points: a few thousand buckets, every kernel a handful of CTAs).  A lone thread needs
+// ≈ 0.55 µs per Fq multiplication, so a chain of 16 mixed additions per work item, 32 + 24 per reduction chunk and 8 per tree
+// level added up to > 1 ms of pure dependency latency at 2^12–2^16 points.  Here the chains are cut with warp shuffles:
+//   * k_bucket_accumulate_g8 — EIGHT lanes per work item: each lane adds every 8th entry, then a 3-step shuffle butterfly;
+//   * k_bucket_reduce_warp   — one warp per 32 buckets: a 5-step suffix scan gives the running sums Σ_{b' ≥ b} S_b', a 5-step
+//                              reduction of those gives Σ (b − lo + 1)·S_b (the reference's running-sum trick,
+//                              batched.rs:356-361, as a parallel scan);
+//   * k_window_combine_warp  — one warp per bucket set folds its ≤ 32 chunk results: Σ acc_j + 32·Σ j·run_j, the weighted sum
+//                              again as scan + reduction, the factor 32 as five doublings.
+// =================================================================================================
+FF_DEV XYZZ shfl_xor_xyzz(const XYZZ& a, int m) {
+    XYZZ r;
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        r.X.v[j] = __shfl_xor_sync(0xffffffffu, a.X.v[j], m); r.Y.v[j] = __shfl_xor_sync(0xffffffffu, a.Y.v[j], m);
+        r.ZZ.v[j] = __shfl_xor_sync(0xffffffffu, a.ZZ.v[j], m); r.ZZZ.v[j] = __shfl_xor_sync(0xffffffffu, a.ZZZ.v[j], m);
+    }
+    return r;
+}
+FF_DEV XYZZ shfl_down_xyzz(const XYZZ& a, int d) {
+    XYZZ r;
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        r.X.v[j] = __shfl_down_sync(0xffffffffu, a.X.v[j], d); r.Y.v[j] = __shfl_down_sync(0xffffffffu, a.Y.v[j], d);
+        r.ZZ.v[j] = __shfl_down_sync(0xffffffffu, a.ZZ.v[j], d); r.ZZZ.v[j] = __shfl_down_sync(0xffffffffu, a.ZZZ.v[j], d);
+    }
+    return r;
+}
+// every lane ends with Σ over the warp (butterfly: the two partners of a step compute the same sum)
+FF_DEV XYZZ warp_sum_xyzz(XYZZ a) {
+#pragma unroll 1
+    for (int m = 16; m >= 1; m >>= 1) { XYZZ o = shfl_xor_xyzz(a, m); a.add(o); }
+    return a;
+}
+// lane l ends with Σ_{l' ≥ l} a_l'
+FF_DEV XYZZ warp_suffix_scan_xyzz(XYZZ a, int lane) {
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) { XYZZ o = shfl_down_xyzz(a, d); if (lane + d < 32) a.add(o); }
+    return a;
+}
+
+static constexpr int ACC_G = 8;
+__global__ void __launch_bounds__(128, 4) k_bucket_accumulate_g8(const uint32_t* __restrict__ records, const uint32_t* __restrict__ sorted,
+                                                                 const uint32_t* __restrict__ bucket_start, const uint32_t* __restrict__ item_start,
+                                                                 uint32_t total_buckets, uint32_t cap, uint32_t* __restrict__ partial) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, item = t / ACC_G, sub = t % ACC_G;
+    const bool valid = item < item_start[total_buckets];
+    XYZZ acc = XYZZ::infinity();
+    if (valid) {
+        uint32_t lo = 0, hi = total_buckets;          // item_start[lo] <= item < item_start[hi]
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (item_start[mid] <= item) lo = mid; else hi = mid; }
+        const uint32_t seg = item - item_start[lo];
+        const uint32_t b0 = bucket_start[lo], b1 = bucket_start[lo + 1];
+        const uint32_t s0 = b0 + seg * cap, s1 = s0 + cap < b1 ? s0 + cap : b1;
+        uint32_t k = s0 + sub;
+        if (k < s1) {
+            uint32_t e = sorted[k];
+            AffinePoint p = load_record(records, e & 0x7fffffffu);
+            for (; k < s1; k += ACC_G) {
+                const uint32_t e_cur = e;
+                const AffinePoint p_cur = p;
+                if (k + ACC_G < s1) { e = sorted[k + ACC_G]; p = load_record(records, e & 0x7fffffffu); }
+                acc.add_affine(p_cur, (e_cur >> 31) != 0u);
+            }
+        }
+    }
+#pragma unroll 1
+    for (int m = ACC_G / 2; m >= 1; m >>= 1) { XYZZ o = shfl_xor_xyzz(acc, m); acc.add(o); }
+    if (valid && sub == 0) acc.store(partial + (size_t)item * XYZZ_WORDS);
+}
+
+// out[(set·chunks + chunk)·2] = Σ_l (l + 1)·S_{32·chunk + l},  out[… + 1] = Σ_l S_{32·chunk + l}
+__global__ void __launch_bounds__(128) k_bucket_reduce_warp(const uint32_t* __restrict__ partial, const uint32_t* __restrict__ item_start,
+                                                            uint32_t nbuckets, uint32_t chunks, uint32_t nsets, uint32_t* __restrict__ out) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (warp >= nsets * chunks) return;                                 // whole warps only
+    const uint32_t set = warp / chunks, ch = warp % chunks, b = ch * 32u + lane;
+    XYZZ s = XYZZ::infinity();
+    if (b < nbuckets) s = bucket_sum(partial, item_start, set * nbuckets + b);
+    const XYZZ run = warp_suffix_scan_xyzz(s, (int)lane);
+    const XYZZ acc = warp_sum_xyzz(run);
+    if (lane == 0) {
+        acc.store(out + (size_t)warp * 2 * XYZZ_WORDS);
+        run.store(out + ((size_t)warp * 2 + 1) * XYZZ_WORDS);
+    }
+}
+// window sum = Σ_j acc_j + 32·Σ_j j·run_j over the set's chunks (chunks ≤ 32)
+__global__ void __launch_bounds__(32) k_window_combine_warp(const uint32_t* __restrict__ in, uint32_t chunks, uint32_t* __restrict__ out) {
+    const uint32_t set = blockIdx.x, lane = threadIdx.x;
+    XYZZ a = XYZZ::infinity(), r = XYZZ::infinity();
+    if (lane < chunks) {
+        a = XYZZ::load(in + ((size_t)set * chunks + lane) * 2 * XYZZ_WORDS);
+        r = XYZZ::load(in + (((size_t)set * chunks + lane) * 2 + 1) * XYZZ_WORDS);
+    }
+    XYZZ total = warp_sum_xyzz(a);
+    if (chunks > 1) {
+        XYZZ suf = warp_suffix_scan_xyzz(r, (int)lane);                 // Σ_{i ≥ j} run_i
+        if (lane == 0) suf = XYZZ::infinity();                          // Σ_{j ≥ 1} suffix_j = Σ_j j·run_j
+        XYZZ w = warp_sum_xyzz(suf);
+        for (int k = 0; k < 5; k++) w.dbl();
+        total.add(w);
+    }
+    if (lane == 0) total.store(out + (size_t)set * XYZZ_WORDS);
+}
+
 __global__ void k_xyzz_sum_ranks(const uint32_t* __restrict__ in, int nranks, int count, uint32_t* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -977,13 +1098,13 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
     const size_t set_cap = flat ? max_job_n * (size_t)plan.nwin : max_job_n;   // most entries one bucket set (or one bucket) can hold
     // pair levels over plain bases: the sort scatters 96-byte records (k_scatter_records) and every level is dense;
     // tables (flat) and the XYZZ-only path keep the index sort + gather
-    bool records = !flat && levels > 0;
+    bool records = levels > 0;
     if (const char* e = getenv("SNARKVM_B200_MSM_RECORDS")) records = records && atoi(e) != 0;
     if (const char* e = getenv("SNARKVM_B200_MSM_PAIR_V1")) { if (atoi(e) != 0) records = false; }      // the round-1 kernel gathers
     // a scalar segment must lie inside one base array (the record scatter reads its points through one pointer)
     std::vector<const uint8_t*> seg_points((size_t)nsegs, nullptr);
     std::vector<size_t> seg_stride((size_t)nsegs, 0);
-    if (records) {
+    if (records && !flat) {
         for (int i = 0; i < nsegs; i++) {
             size_t off = 0; bool found = segs[i].n == 0;
             for (int k = 0; k < nbases && !found; k++) {
@@ -1019,7 +1140,22 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
     size_t entries_g = set_cap * (size_t)gw;                      // most entries a group can hold
     if (entries_g > max_entries) entries_g = max_entries;
     if (records && entries_g >= 0x7fffffffull) return (int)cudaErrorInvalidValue;      // record positions carry the sign in bit 31
-    const size_t max_items = (size_t)TBg + entries_g / plan.cap + 1;
+    // small problems take the shuffle-based latency path (see k_bucket_reduce_warp)
+    bool warp_reduce = plan.nbuckets <= 1024u;
+    // (measured, profiles/r2i_ab.log: the shuffle reduction wins at every size it applies to — 1.05 → 0.5 ms; eight lanes per
+    // item win only while the whole problem is a few CTAs — 2^10: 0.20 → 0.10 ms, 2^12 equal, 2^14 and up lose to the butterfly's
+    // extra additions)
+    bool acc_g8 = levels == 0 && max_entries <= 100000;
+    if (const char* e = getenv("SNARKVM_B200_MSM_WARP_PATH")) { if (atoi(e) == 0) { warp_reduce = false; acc_g8 = false; } }
+    uint32_t item_cap = plan.cap;                                  // points per work item of the XYZZ accumulation
+    if (acc_g8) {                                                  // eight lanes per item: 8 × (4 … 16) points
+        size_t per_lane = max_entries / 300000 + 1;
+        if (per_lane < 4) per_lane = 4;
+        if (per_lane > 16) per_lane = 16;
+        item_cap = (uint32_t)per_lane * 8u;
+        if (const char* e = getenv("SNARKVM_B200_MSM_CAP")) { long v = atol(e); if (v >= 1) item_cap = (uint32_t)v; }
+    }
+    const size_t max_items = (size_t)TBg + entries_g / (item_cap < plan.cap ? item_cap : plan.cap) + 1;
     const size_t dense_cap_a = entries_g / 2 + TBg + 1, dense_cap_b = entries_g / 4 + 2 * (size_t)TBg + 1;
 
     size_t pair_waves = 0;                       // 0 = fewest whole waves with T ≤ 1024 outputs per lane
@@ -1069,7 +1205,7 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
         cnt_tmp = a.take<uint32_t>((size_t)TBg + 1);
         partial = a.take<uint32_t>(max_items * XYZZ_WORDS);
         partial2 = a.take<uint32_t>(((size_t)TBg + max_items / 32 + 2) * XYZZ_WORDS);
-        red_a = a.take<uint32_t>((size_t)gw * chunks_per_set * XYZZ_WORDS);
+        red_a = a.take<uint32_t>((size_t)gw * (chunks_per_set > 2 * ((plan.nbuckets + 31u) / 32u) ? chunks_per_set : 2 * ((plan.nbuckets + 31u) / 32u)) * XYZZ_WORDS);
         red_b = a.take<uint32_t>((size_t)gw * (chunks_per_set / tree + 1) * XYZZ_WORDS);
         cub_tmp = a.take<uint8_t>(cub_bytes);
         if (!flat && !records) dense_bases = a.take<uint32_t>(total_bases * (size_t)BASE_WORDS);
@@ -1145,15 +1281,19 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
             const uint32_t* final_partial = nullptr;
             const uint32_t* final_start = nullptr;
             if (levels == 0) {
-                k_items_per_bucket<<<(tb + 256) / 256, 256, 0, stream>>>(hist + (size_t)w0 * plan.nbuckets, items, tb, plan.cap);
+                const uint32_t cap = acc_g8 ? item_cap : plan.cap;
+                k_items_per_bucket<<<(tb + 256) / 256, 256, 0, stream>>>(hist + (size_t)w0 * plan.nbuckets, items, tb, cap);
                 CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(tb + 1), stream));
                 count_launch(2);
-                const size_t group_items = (size_t)tb + entries / plan.cap + 1;
-                items_bound = set_cap / plan.cap + 1;
+                const size_t group_items = (size_t)tb + entries / cap + 1;
+                items_bound = set_cap / cap + 1;
                 items_launched = group_items;
                 ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
-                k_bucket_accumulate<<<(unsigned)((group_items + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
-                    gather_src, sorted, bs, item_start, tb, plan.cap, partial);
+                if (acc_g8)
+                    k_bucket_accumulate_g8<<<(unsigned)((group_items * ACC_G + 127) / 128), 128, 0, stream>>>(gather_src, sorted, bs, item_start, tb, cap, partial);
+                else
+                    k_bucket_accumulate<<<(unsigned)((group_items + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
+                        gather_src, sorted, bs, item_start, tb, plan.cap, partial);
                 count_launch();
             } else {
                 if (records) {
@@ -1162,16 +1302,27 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
                     for (int i = 0; i < nsegs; i++) {
                         const MsmSegment& sg = segs[i];
                         if (sg.n == 0) continue;
-                        const int64_t first = (int64_t)sg.job * plan.nwin;                            // bucket set of the segment's window 0
-                        const int64_t lo_w = (int64_t)w0 - first, hi_w = (int64_t)w0 + wn - first;
-                        const int w_lo = lo_w < 0 ? 0 : (int)lo_w, w_hi = hi_w > plan.nwin ? plan.nwin : (int)hi_w;
-                        if (w_lo >= w_hi) continue;
+                        // windows of this segment inside the group: its job's bucket sets are [job·sets, (job+1)·sets)
+                        const int64_t first = (int64_t)sg.job * sets_per_job;
+                        int w_lo, w_hi;
+                        if (flat) {                                                                   // one set per job: all windows or none
+                            if (first < (int64_t)w0 || first >= (int64_t)w0 + wn) continue;
+                            w_lo = 0; w_hi = plan.nwin;
+                        } else {
+                            const int64_t lo_w = (int64_t)w0 - first, hi_w = (int64_t)w0 + wn - first;
+                            w_lo = lo_w < 0 ? 0 : (int)lo_w; w_hi = hi_w > plan.nwin ? plan.nwin : (int)hi_w;
+                            if (w_lo >= w_hi) continue;
+                        }
                         const unsigned grid = (unsigned)((sg.n + 255) / 256);
                         const uint32_t slot_base = sg.job * sets_per_job * plan.nbuckets;
-                        if (sg.mont) k_scatter_records<true><<<grid, 256, 0, stream>>>((const uint32_t*)sg.d_scalars, sg.n, seg_points[i], seg_stride[i], plan.c, plan.nbuckets,
-                                                                                       cursors, slot_base, w_lo, w_hi, bs, (uint4*)dense0);
-                        else k_scatter_records<false><<<grid, 256, 0, stream>>>((const uint32_t*)sg.d_scalars, sg.n, seg_points[i], seg_stride[i], plan.c, plan.nbuckets,
-                                                                                cursors, slot_base, w_lo, w_hi, bs, (uint4*)dense0);
+                        const uint32_t* sc = (const uint32_t*)sg.d_scalars;
+                        if (flat) {
+                            if (sg.mont) k_scatter_records<true, true><<<grid, 256, 0, stream>>>(sc, sg.n, nullptr, 0, table, table_n, plan.c, plan.nbuckets, cursors, slot_base, w_lo, w_hi, bs, (uint4*)dense0);
+                            else k_scatter_records<false, true><<<grid, 256, 0, stream>>>(sc, sg.n, nullptr, 0, table, table_n, plan.c, plan.nbuckets, cursors, slot_base, w_lo, w_hi, bs, (uint4*)dense0);
+                        } else {
+                            if (sg.mont) k_scatter_records<true, false><<<grid, 256, 0, stream>>>(sc, sg.n, seg_points[i], seg_stride[i], nullptr, 0, plan.c, plan.nbuckets, cursors, slot_base, w_lo, w_hi, bs, (uint4*)dense0);
+                            else k_scatter_records<false, false><<<grid, 256, 0, stream>>>(sc, sg.n, seg_points[i], seg_stride[i], nullptr, 0, plan.c, plan.nbuckets, cursors, slot_base, w_lo, w_hi, bs, (uint4*)dense0);
+                        }
                         count_launch();
                     }
                 }
@@ -1253,6 +1404,13 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
                 final_partial = p_in; final_start = st_in;
             }
             uint32_t* group_sums = d_window_sums + (size_t)w0 * XYZZ_WORDS;
+            if (warp_reduce) {
+                const uint32_t wchunks = (plan.nbuckets + 31u) / 32u;
+                k_bucket_reduce_warp<<<(wn * wchunks * 32u + 127u) / 128u, 128, 0, stream>>>(final_partial, final_start, plan.nbuckets, wchunks, wn, red_a);
+                k_window_combine_warp<<<wn, 32, 0, stream>>>(red_a, wchunks, group_sums);
+                count_launch(2);
+                continue;
+            }
             const uint32_t nthreads = chunks_per_set * wn;
             k_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, stream>>>(final_partial, final_start, plan.nbuckets, chunk, chunks_per_set, wn, red_a);
             count_launch(1);
@@ -1289,9 +1447,10 @@ int msm_window_sums_device(uint32_t* d_window_sums, uint32_t* d_flags, const Msm
 MsmPlan msm_make_plan_precomputed(size_t npoints) {
     MsmPlan p;
     int lg = ceil_log2(npoints < 2 ? 2 : npoints);
-    // one bucket set for all windows ⇒ the bucket reduction is paid once and wide windows are cheap: c = 22 at 2^24
-    // (12 windows instead of 15).  Swept on a B200 with tools/tune_precomputed.py (profiles/tune_precomputed_r1.log).
-    int c = lg >= 24 ? 22 : lg >= 22 ? lg - 2 : lg >= 20 ? lg - 3 : lg >= 8 ? lg - 2 : 6;
+    // one bucket set for all windows ⇒ the bucket reduction is paid once and wide windows are cheap.  Re-swept in round 2 with
+    // the record scatter feeding dense pair levels (tools/tune_precomputed.py, profiles/r2j_tune_pre.log): c = 20 from 2^22
+    // (13 windows; 80.8 ms at 2^24 against 90.9 ms without tables), c = 17 at 2^20–2^21.
+    int c = lg >= 22 ? 20 : lg >= 20 ? 17 : lg >= 8 ? lg - 2 : 6;
     if (const char* e = getenv("SNARKVM_B200_MSM_PRE_C")) { int v = atoi(e); if (v >= 2 && v <= 24) c = v; }
     p.c = c;
     p.nwin = 253 / c + 1;
@@ -1300,7 +1459,7 @@ MsmPlan msm_make_plan_precomputed(size_t npoints) {
     size_t cap = total / 300000 + 1;
     if (cap < 16) cap = 16;
     p.cap = (uint32_t)cap;
-    int levels = lg >= 24 ? 3 : lg >= 22 ? 2 : 1;
+    int levels = lg >= 24 ? 5 : lg >= 22 ? 4 : lg >= 20 ? 3 : 1;
     if (const char* e = getenv("SNARKVM_B200_MSM_PRE_LEVELS")) { int v = atoi(e); if (v >= 1 && v <= 16) levels = v; }
     p.levels = levels;
     return p;

@@ -141,6 +141,9 @@ static int get_coset_tables(int lg, int inverse, CosetTables* out) {
 // ---------------------------------------------------------------------------
 // One pass = stages [t0, t0+S) of the DIF network on a 2^S × 2^Q tile in shared memory.
 // ---------------------------------------------------------------------------
+#ifndef NTT_SMEM_TW
+#define NTT_SMEM_TW 1
+#endif
 struct PassArgs {
     const Fr* in;
     Fr* out;
@@ -169,7 +172,11 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
     // different bank groups and row-wise accesses stay a permutation of one 128-byte line.
     struct Tile {
         uint4* p; uint32_t n; uint32_t q, cmask;
+#ifdef NTT_NO_SWIZZLE
+        __device__ __forceinline__ uint32_t sw(uint32_t i) const { return i; }
+#else
         __device__ __forceinline__ uint32_t sw(uint32_t i) const { return i ^ ((i >> q) & cmask); }
+#endif
         __device__ __forceinline__ Fr get(uint32_t i0) const {
             const uint32_t i = sw(i0);
             uint4 a = p[i], b = p[n + i]; Fr r;
@@ -192,6 +199,17 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
     if (!a.last) { H = tile >> (L - Q); low_base = (tile & (((size_t)1 << (L - Q)) - 1)) << Q; }
     else hprime_base = tile << Q;
 
+    // ---- last pass: its stages use only 2^(S-1) ≤ 128 distinct twiddles ω^{k·2^t0} — staged once per CTA in shared memory ----
+    uint4* sm_tw = smem_raw + 2 * tile_elems;
+    if (NTT_SMEM_TW && a.last && S > 0) {
+        const size_t halfn = (size_t)1 << (lg - 1);
+        for (uint32_t k = tid; k < (1u << (S - 1)); k += nthr) {
+            Fr w = Fr::one();
+            if (k) { const size_t ex = (size_t)k << t0; w = Fr::load(a.tw + ((a.inverse ? halfn - ex : ex) << (a.lgN - lg))); }
+            sm_tw[2 * k] = make_uint4(w.v[0], w.v[1], w.v[2], w.v[3]);
+            sm_tw[2 * k + 1] = make_uint4(w.v[4], w.v[5], w.v[6], w.v[7]);
+        }
+    }
     // ---- load (+ optional coset pre-scale) ----
     for (uint32_t e = tid; e < tile_elems; e += nthr) {
         uint32_t d, c;
@@ -241,7 +259,13 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
                 x[k] = sm.get(il[k]); y[k] = sm.get(ih[k]);
                 if (ex != 0) {
                     tw[k] = true;
-                    w[k] = Fr::load(a.tw + ((a.inverse ? (((size_t)1 << (lg - 1)) - ex) : ex) << tw_shift));
+                    if (NTT_SMEM_TW && a.last) {
+                        const uint4 w0 = sm_tw[2 * (r_lo << u)], w1 = sm_tw[2 * (r_lo << u) + 1];
+                        w[k].v[0] = w0.x; w[k].v[1] = w0.y; w[k].v[2] = w0.z; w[k].v[3] = w0.w;
+                        w[k].v[4] = w1.x; w[k].v[5] = w1.y; w[k].v[6] = w1.z; w[k].v[7] = w1.w;
+                    } else {
+                        w[k] = Fr::load(a.tw + ((a.inverse ? (((size_t)1 << (lg - 1)) - ex) : ex) << tw_shift));
+                    }
                 }
             }
 #pragma unroll
@@ -316,6 +340,9 @@ int fr_to_mont_device(void* d_out, const void* d_in, size_t n, cudaStream_t stre
 
 static constexpr int MAX_STAGES = 8;    // rows per tile ≤ 256
 static constexpr int TILE_LG = 11;      // 2^11 elements × 32 B = 64 KiB of shared memory per CTA
+// + the last pass's 2^(S-1) twiddles: ≤ 128 for a multi-pass transform, up to 1024 when a whole transform of ≤ 2^11
+// elements is one pass
+static inline size_t tw_smem_bytes(int S, bool last) { return last && S > 0 ? ((size_t)32 << (S - 1)) : 0; }
 
 int ntt_device(void* d_inout, uint32_t lg, int direction, int type, void* d_scratch, cudaStream_t stream) {
     if (lg > NTT_MAX_LG) return (int)cudaErrorInvalidValue;
@@ -336,7 +363,7 @@ int ntt_device(void* d_inout, uint32_t lg, int direction, int type, void* d_scra
     {
         int dev = 0; cudaGetDevice(&dev);
         std::call_once(smem_once[dev & 63], [] {
-            cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << TILE_LG) * (int)sizeof(Fr));
+            cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << TILE_LG) * (int)sizeof(Fr) + (int)tw_smem_bytes(TILE_LG, true));
         });
     }
     {
@@ -365,7 +392,7 @@ int ntt_device(void* d_inout, uint32_t lg, int direction, int type, void* d_scra
             a.in = (p == 0) ? A : B;
             a.out = (P == 1) ? A : (a.last ? A : B);
             size_t tiles = ((size_t)1 << lg) >> (S + Q);
-            size_t smem = ((size_t)1 << (S + Q)) * sizeof(Fr);
+            size_t smem = ((size_t)1 << (S + Q)) * sizeof(Fr) + tw_smem_bytes(S, a.last != 0);
             {
                 ProfScope pass_scope(PROF_NTT_PASS, stream);
                 k_ntt_pass<<<(unsigned)tiles, 256, smem, stream>>>(a);

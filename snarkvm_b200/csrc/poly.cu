@@ -228,34 +228,112 @@ int poly_divide_by_linear_device(void* d_q, const void* d_p, size_t m, const voi
 // z_M = M·z for a sparse R1CS matrix in CSR form — inner_product (snark/varuna/ahp/prover/round_functions/mod.rs:169-189),
 // the per-row loop the prover runs for A, B and C (:128-152).  One thread per row (rows hold a handful of entries).
 // ---------------------------------------------------------------------------------------------------------------------
+// Rows longer than SPMV_LONG entries (a hot variable: the constant one, or — transposed — a variable every constraint uses;
+// the reference's TestCircuit puts 2^20 entries of B in ONE column) would serialise a thread: 2.6 s for M(α, ·) of a
+// 2^20-constraint circuit.  They leave the thread-per-row kernel through a device-side work list — no host round trip —
+// and are cut into segments of SPMV_SEG entries, one CTA per segment, then one CTA per long row adds its segments.
+static constexpr uint32_t SPMV_LONG = 256, SPMV_SEG = 2048;
+struct SpmvLong { uint32_t row, base, nseg; };
 __global__ void k_sparse_matvec(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ cols, const uint32_t* __restrict__ vals,
-                                size_t nrows, const uint32_t* __restrict__ x, size_t nvars, uint32_t* __restrict__ out, int* __restrict__ bad) {
+                                size_t nrows, const uint32_t* __restrict__ x, size_t nvars, uint32_t* __restrict__ out, int* __restrict__ bad,
+                                uint32_t* __restrict__ ctr /* [0] long rows, [1] work items */, SpmvLong* __restrict__ long_rows,
+                                uint2* __restrict__ items) {
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrows) return;
+    const uint32_t e0 = row_ptr[r], e1 = row_ptr[r + 1];
+    if (e1 - e0 > SPMV_LONG) {
+        const uint32_t nseg = (e1 - e0 + SPMV_SEG - 1) / SPMV_SEG;
+        const uint32_t base = atomicAdd(&ctr[1], nseg), slot = atomicAdd(&ctr[0], 1u);
+        long_rows[slot] = SpmvLong{(uint32_t)r, base, nseg};
+        for (uint32_t j = 0; j < nseg; j++) items[base + j] = make_uint2((uint32_t)r, j);
+        return;
+    }
     Fr acc = Fr::zero();
-    for (uint32_t e = row_ptr[r]; e < row_ptr[r + 1]; e++) {
+    for (uint32_t e = e0; e < e1; e++) {
         const uint32_t c = cols[e];
         if (c >= nvars) { *bad = 1; continue; }              // out-of-range column: reported, never read
         acc = acc + Fr::load_ldg(x + (size_t)c * 8) * Fr::load_ldg(vals + (size_t)e * 8);
     }
     acc.store(out + r * 8);
 }
+// Σ over the 256 threads of a CTA (shared memory tree); the result is valid in thread 0
+FF_DEV Fr cta_sum_fr(Fr v, uint4* sh) {
+    const uint32_t t = threadIdx.x;
+    sh[2 * t] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]); sh[2 * t + 1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+    __syncthreads();
+    for (uint32_t d = 128; d >= 1; d >>= 1) {
+        if (t < d) {
+            Fr a = Fr::load(sh + 2 * t), b = Fr::load(sh + 2 * (t + d));
+            a = a + b;
+            a.store(sh + 2 * t);
+        }
+        __syncthreads();
+    }
+    return Fr::load(sh);
+}
+__global__ void __launch_bounds__(256) k_spmv_segments(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ cols,
+                                                       const uint32_t* __restrict__ vals, const uint32_t* __restrict__ x, size_t nvars,
+                                                       const uint32_t* __restrict__ ctr, const uint2* __restrict__ items,
+                                                       uint32_t* __restrict__ partial, int* __restrict__ bad) {
+    __shared__ uint4 sh[512];
+    const uint32_t nitems = ctr[1];
+    for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const uint2 w = items[it];
+        const uint32_t e0 = row_ptr[w.x] + w.y * SPMV_SEG, rend = row_ptr[w.x + 1], e1 = e0 + SPMV_SEG < rend ? e0 + SPMV_SEG : rend;
+        Fr acc = Fr::zero();
+        for (uint32_t e = e0 + threadIdx.x; e < e1; e += 256) {
+            const uint32_t c = cols[e];
+            if (c >= nvars) { *bad = 1; continue; }
+            acc = acc + Fr::load_ldg(x + (size_t)c * 8) * Fr::load_ldg(vals + (size_t)e * 8);
+        }
+        const Fr tot = cta_sum_fr(acc, sh);
+        if (threadIdx.x == 0) tot.store(partial + (size_t)it * 8);
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_spmv_long_rows(const uint32_t* __restrict__ ctr, const SpmvLong* __restrict__ long_rows,
+                                                        const uint32_t* __restrict__ partial, uint32_t* __restrict__ out) {
+    __shared__ uint4 sh[512];
+    const uint32_t nlong = ctr[0];
+    for (uint32_t k = blockIdx.x; k < nlong; k += gridDim.x) {
+        const SpmvLong L = long_rows[k];
+        Fr acc = Fr::zero();
+        for (uint32_t j = threadIdx.x; j < L.nseg; j += 256) acc = acc + Fr::load(partial + (size_t)(L.base + j) * 8);
+        const Fr tot = cta_sum_fr(acc, sh);
+        if (threadIdx.x == 0) tot.store(out + (size_t)L.row * 8);
+        __syncthreads();
+    }
+}
 
 int sparse_matvec_device(void* d_out, const void* d_row_ptr, const void* d_cols, const void* d_vals, size_t nrows, const void* d_x,
                          size_t nvars, cudaStream_t stream) {
     if (nrows == 0) return 0;
     if (!d_out || !d_row_ptr || !d_x) return (int)cudaErrorInvalidValue;
-    int* bad = nullptr;
-    cudaError_t e = pool_alloc(&bad, sizeof(int), stream);
+    // the number of entries sizes the work lists of the long rows
+    uint32_t nnz = 0;
+    int rc = (int)cudaMemcpyAsync(&nnz, (const uint32_t*)d_row_ptr + nrows, 4, cudaMemcpyDeviceToHost, stream);
+    if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
+    if (rc != 0) return rc;
+    const size_t max_long = (size_t)nnz / SPMV_LONG + 1, max_items = (size_t)nnz / SPMV_SEG + max_long + 1;
+    uint8_t* scratch = nullptr;
+    const size_t off_long = 256, off_items = off_long + ((max_long * sizeof(SpmvLong) + 255) & ~(size_t)255),
+                 off_partial = off_items + ((max_items * sizeof(uint2) + 255) & ~(size_t)255), total = off_partial + max_items * 32;
+    cudaError_t e = pool_alloc(&scratch, total, stream);
     if (e != cudaSuccess) return (int)e;
-    int rc = (int)cudaMemsetAsync(bad, 0, sizeof(int), stream);
+    int* bad = (int*)scratch;                                     // [0] bad flag, [1..2] counters
+    uint32_t* ctr = (uint32_t*)scratch + 1;
+    rc = (int)cudaMemsetAsync(scratch, 0, 256, stream);
     k_sparse_matvec<<<(unsigned)((nrows + 127) / 128), 128, 0, stream>>>((const uint32_t*)d_row_ptr, (const uint32_t*)d_cols, (const uint32_t*)d_vals,
-                                                                         nrows, (const uint32_t*)d_x, nvars, (uint32_t*)d_out, bad);
-    count_launch();
+                                                                         nrows, (const uint32_t*)d_x, nvars, (uint32_t*)d_out, bad, ctr,
+                                                                         (SpmvLong*)(scratch + off_long), (uint2*)(scratch + off_items));
+    k_spmv_segments<<<592, 256, 0, stream>>>((const uint32_t*)d_row_ptr, (const uint32_t*)d_cols, (const uint32_t*)d_vals, (const uint32_t*)d_x, nvars,
+                                             ctr, (const uint2*)(scratch + off_items), (uint32_t*)(scratch + off_partial), bad);
+    k_spmv_long_rows<<<148, 256, 0, stream>>>(ctr, (const SpmvLong*)(scratch + off_long), (const uint32_t*)(scratch + off_partial), (uint32_t*)d_out);
+    count_launch(3);
     if (rc == 0) rc = (int)cudaGetLastError();
     int h_bad = 0;
     if (rc == 0) rc = (int)cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, stream);
-    cudaFreeAsync(bad, stream);
+    cudaFreeAsync(scratch, stream);
     if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
     if (rc == 0 && h_bad) rc = (int)cudaErrorInvalidValue;
     return rc;

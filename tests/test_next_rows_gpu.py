@@ -182,6 +182,8 @@ def test_sparse_matvec_vs_oracle(oracle_cpu):
     nrows, npub, nprv = 5000, 17, 4000
     counts = rng.integers(0, 9, size=nrows)
     counts[7] = 0
+    # hot rows (a variable every constraint uses, transposed): they leave the thread-per-row kernel and are cut into segments
+    counts[100], counts[101], counts[2000], counts[2001], counts[4999] = 256, 257, 2048, 2049, 30000
     row_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
     nnz = int(row_ptr[-1])
     cols = rng.integers(0, npub + nprv, size=nnz).astype(np.uint32)
@@ -191,9 +193,10 @@ def test_sparse_matvec_vs_oracle(oracle_cpu):
     x = np.concatenate([pub, prv])
     got = device.sparse_matvec(torch.from_numpy(row_ptr.view(np.int32)).cuda(), torch.from_numpy(cols.view(np.int32)).cuda(), _dev(vals), _dev(x))
     assert (_host_u64(got).reshape(-1, 4) == oracle_cpu.sparse_matvec(row_ptr, cols, vals, pub, prv)).all()
-    bad = cols.copy(); bad[5] = npub + nprv
-    with pytest.raises(CudaError):
-        device.sparse_matvec(torch.from_numpy(row_ptr.view(np.int32)).cuda(), torch.from_numpy(bad.view(np.int32)).cuda(), _dev(vals), _dev(x))
+    for where in (5, int(row_ptr[4999]) + 12345):                   # an out-of-range column in a short row / inside a long row's segment
+        bad = cols.copy(); bad[where] = npub + nprv
+        with pytest.raises(CudaError):
+            device.sparse_matvec(torch.from_numpy(row_ptr.view(np.int32)).cuda(), torch.from_numpy(bad.view(np.int32)).cuda(), _dev(vals), _dev(x))
 
 
 def test_fr_vec_ops_and_domain_elements(oracle_cpu):

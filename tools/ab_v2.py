@@ -28,12 +28,9 @@ for lg in sizes:
     KEYS = ("SNARKVM_B200_MSM_PAIR_V1", "SNARKVM_B200_MSM_SCRATCH_GB", "SNARKVM_B200_MSM_LEVELS", "SNARKVM_B200_MSM_C", "SNARKVM_B200_MSM_PAIR_PARTS", "SNARKVM_B200_MSM_PAIR_MINB")
     KEYS = KEYS + ("SNARKVM_B200_MSM_RECORDS",)
     if lg >= 20:
-        variants = (("default", {}), ("minb3", {"SNARKVM_B200_MSM_PAIR_MINB": "3"}), ("L4", {"SNARKVM_B200_MSM_LEVELS": "4"}),
-                    ("L6", {"SNARKVM_B200_MSM_LEVELS": "6"}), ("c16", {"SNARKVM_B200_MSM_C": "16"}), ("c18", {"SNARKVM_B200_MSM_C": "18"}),
-                    ("40GB", {"SNARKVM_B200_MSM_SCRATCH_GB": "40"}))
+        variants = (("default", {}), ("gather (r1 sort)", {"SNARKVM_B200_MSM_RECORDS": "0"}))
     else:
-        variants = (("default", {}), ("L2", {"SNARKVM_B200_MSM_LEVELS": "2"}), ("L3", {"SNARKVM_B200_MSM_LEVELS": "3"}),
-                    ("L3 c14", {"SNARKVM_B200_MSM_LEVELS": "3", "SNARKVM_B200_MSM_C": "14"}), ("L2 c13", {"SNARKVM_B200_MSM_LEVELS": "2", "SNARKVM_B200_MSM_C": "13"}))
+        variants = (("default", {}), ("L0 c16", {"SNARKVM_B200_MSM_LEVELS": "0", "SNARKVM_B200_MSM_C": "16"}))
     for tag, env in variants:
         for k in KEYS: os.environ.pop(k, None)
         os.environ.update(env)
@@ -44,11 +41,18 @@ for lg in sizes:
     for k in KEYS: os.environ.pop(k, None)
     del bases, scal
     torch.cuda.empty_cache()
-for lg in (12, 14, 16, 18):
+for lg in (10, 12, 14, 16, 18):
     n = 1 << lg
     bases = device.generate_bases(n, 7)
     s = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64); s[:, 3] &= np.uint64((1 << 60) - 1)
     scal = torch.from_numpy(s.view(np.int64)).cuda()
-    ms, ph = run(lambda: device.msm(bases, scal), 20)
-    print(f"lg={lg} default          {ms:8.3f} ms  sort {ph[0]:6.3f}  accumulate {ph[1]:7.3f}  reduce {ph[2]:6.3f}", flush=True)
+    ref = None
+    for tag, env in (("thread path", {"SNARKVM_B200_MSM_WARP_PATH": "0"}), ("warp path", {})):
+        os.environ.pop("SNARKVM_B200_MSM_WARP_PATH", None)
+        os.environ.update(env)
+        got = device.msm(bases, scal)
+        if ref is None: ref = got
+        ms, ph = run(lambda: device.msm(bases, scal), 20)
+        print(f"lg={lg} {tag:12s} {ms:8.3f} ms  sort {ph[0]:6.3f}  accumulate {ph[1]:7.3f}  reduce {ph[2]:6.3f}  {'ok' if (got == ref).all() else 'MISMATCH'}", flush=True)
+    os.environ.pop("SNARKVM_B200_MSM_WARP_PATH", None)
 print("scratch:", device.msm_scratch_stats())
