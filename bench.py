@@ -552,6 +552,33 @@ def run_product(args, rank, world, local_rank):
         lb_ms, _ = timed(lambda: device.lagrange_basis(gp), 1)
         kzg["lagrange_basis"] = {"ms": lb_ms, "workload": f"ifft of 2^{args.g1_ntt_lg} G1 points per GPU", "unit": "ms"}
 
+    # ---- BASELINE config 5b: Varuna prover rounds + round commitments on a synthetic R1CS, polynomials resident ----
+    varuna_line = None
+    if world == 1 and args.varuna_lg > 0:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("bench_varuna", os.path.join(ROOT, "tools", "bench_varuna.py"))
+        bv = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bv)
+        varuna_line = bv.run(args.varuna_lg, reps=2)
+
+    # ---- G2 (north_star "G1/G2"): VariableBase::msm over Affine<G2>, standard::msm semantics, closed-form check ----
+    g2_line = None
+    if world == 1 and args.g2_lg > 0:
+        from oracle import g2 as og2
+        ng2 = 1 << args.g2_lg
+        g2seed = 0x62 + rank
+        g2b = device.generate_bases_g2(ng2, g2seed, device=dev)
+        g2s = random_scalars(ng2, 777)
+        g2sd = torch.from_numpy(g2s.view(np.int64)).to(dev)
+        got2 = device.msm_g2(g2b, g2sd)
+        want2 = np.frombuffer(og2.g2_projective_bytes_normalised(og2.g2_mul(og2.G2_GEN, chk.dot(g2s, g2seed))), dtype=np.uint64)
+        checks["g2_msm"] = bool((got2 == want2).all())
+        assert checks["g2_msm"], "G2 MSM differs from the closed form"
+        g2_ms, _ = timed(lambda: device.msm_g2(g2b, g2sd), 3)
+        g2_line = {"metric": "bls12_377_g2_msm_points_per_sec", "value": ng2 / (g2_ms * 1e-3), "unit": "points/s", "ms_per_msm": g2_ms,
+                   "checked": True, "workload": f"2^{args.g2_lg}-point VariableBase::msm over Affine<G2> (Fq2 coordinates, 200-byte images), resident"}
+        del g2b, g2sd
+
     if rank != 0:
         return
 
@@ -571,7 +598,7 @@ def run_product(args, rank, world, local_rank):
                                    "sample": f"one 2^{args.cpu_ntt_lg} forward fft_in_place ({ndt:.2f} s), best team size of 16/32/64/all"}
 
     plan = device.msm_plan(n)
-    plan_levels = 4 if args.lg >= 21 else 1 if args.lg == 20 else 0      # msm_make_plan (csrc/msm.cu)
+    plan_levels = plan["levels"]
     cfg = workload_config(args, world)
     line = {
         "metric": "bls12_377_g1_msm_points_per_sec", "value": value, "unit": "points/s", "n_gpus": world,
@@ -579,8 +606,8 @@ def run_product(args, rank, world, local_rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (Montgomery integer arithmetic, IMAD pipe)",
         "data": "synthetic", "config": cfg,
         "plan": {"window_bits": plan["c"], "windows": plan["nwin"], "pair_levels": plan_levels,
-                 "l2": f"inputs ({n * 136 / 1e9:.2f} GB/step) plus {n * plan['nwin'] * 4 / 1e9:.2f} GB of sorted entries and the dense pair-level "
-                       f"scratch stream through the 126 MB L2 every step — no flush needed"},
+                 "l2": f"inputs ({n * 136 / 1e9:.2f} GB/step) plus {n * plan['nwin'] * 96 / 1e9:.1f} GB of scattered level-0 records and the dense "
+                       f"pair-level scratch stream through the 126 MB L2 every step — no flush needed"},
         "checked": all(checks.values()), "checks": checks,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * (104 + 32) * world,
@@ -592,7 +619,7 @@ def run_product(args, rank, world, local_rank):
         "e2e_registered_bases": e2e_resident,
         "sharded_total": strong,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "bucket accumulation phase: k_densify_bases + k_pair_level2 x%d + k_bucket_accumulate%s" % (
+        "roofline": {"bound": "hbm", "kernel": "bucket accumulation phase: k_pair_level2 x%d + k_bucket_accumulate%s (level-0 records written by k_scatter_records in the sort phase)" % (
                          plan_levels, "_dense" if plan_levels else ""),
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": load_traffic("msm_bucket_accumulation_phase") if args.lg == 24 else None,
@@ -603,6 +630,8 @@ def run_product(args, rank, world, local_rank):
         "cpu_baseline": cpu_baseline,
         "ntt": ntt,
         "kzg_commit": kzg,
+        "varuna": varuna_line,
+        "g2_msm": g2_line,
     }
     print(json.dumps(line), flush=True)
 
@@ -622,7 +651,9 @@ def main():
     ap.add_argument("--ref-lg", type=int, default=22, help="--impl reference: points per step (bounded sample)")
     ap.add_argument("--ref-ntt-lg", type=int, default=22)
     ap.add_argument("--kzg-lg", type=int, default=22)
-    ap.add_argument("--g1-ntt-lg", type=int, default=12, help="size of the G1 iFFT (lagrange_basis) timed inside the KZG extra")
+    ap.add_argument("--varuna-lg", type=int, default=18, help="log2 constraints of the Varuna prover-rounds extra (0 = skip)")
+    ap.add_argument("--g2-lg", type=int, default=16, help="log2 points of the G2 MSM extra (0 = skip)")
+    ap.add_argument("--g1-ntt-lg", type=int, default=16, help="size of the G1 iFFT (lagrange_basis) timed inside the KZG extra")
     ap.add_argument("--skip-kzg", action="store_true")
     ap.add_argument("--skip-ntt", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

@@ -93,6 +93,8 @@ SNARKVM_API int snarkvm_b200_polymul_device(void* d_out, size_t pcount, const vo
 
 /* Window/bucket plan the MSM will use for npoints (signed c-bit digits). */
 SNARKVM_API int snarkvm_b200_msm_plan(size_t npoints, int* c, int* nwin, uint32_t* cap);
+/* batched-affine pair levels the plan for `npoints` runs before the XYZZ accumulation (0 = gather + XYZZ only) */
+SNARKVM_API int snarkvm_b200_msm_plan_levels(size_t npoints);
 
 /* Full MSM with bases and scalars resident in HBM; out144 is HOST memory (normalised projective). */
 SNARKVM_API int snarkvm_b200_msm_device(void* out144, const void* d_points, size_t npoints, const void* d_scalars,
@@ -226,6 +228,16 @@ SNARKVM_API int snarkvm_b200_profile_collect(int kind, double* total_ms, uint64_
 SNARKVM_API int snarkvm_b200_selftest_coop(uint32_t nwarps, uint64_t seed, uint32_t* mismatches, void* stream);
 
 /* Deterministic synthetic bases P_i = h(seed, i) * G written in the reference affine layout. */
+/* ---- G2 (points over Fq2) ----------------------------------------------------------------------------------------------
+ * VariableBase::msm for Affine<G2> — the type the reference dispatches to standard::msm
+ * (algorithms/src/msm/variable_base/mod.rs:44-47, standard.rs:79-118).  Point layout: x.c0 x.c1 y.c0 y.c1 (4 × 48 B Montgomery
+ * Fq), infinity flag, padding: stride ≥ 200 (curves/src/templates/short_weierstrass_jacobian/affine.rs:41-46 over Fq2);
+ * scalars: canonical 32-byte integers.  Result: 288 bytes, Projective<G2> X Y Z over Fq2, normalised (Z = 1, or (0, 1, 0)). */
+SNARKVM_API snarkvm_error_t snarkvm_b200_msm_g2(void* out288, const void* points, size_t npoints, const void* scalars, size_t ffi_affine_sz);
+SNARKVM_API int snarkvm_b200_msm_g2_device(void* out288, const void* d_points, size_t npoints, const void* d_scalars, size_t stride, void* stream);
+/* test / bench input: P_i = h(seed, i)·G2 with the multipliers of snarkvm_b200_generate_bases_device */
+SNARKVM_API int snarkvm_b200_generate_bases_g2_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, void* stream);
+
 SNARKVM_API int snarkvm_b200_generate_bases_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, void* stream);
 
 #ifdef __cplusplus

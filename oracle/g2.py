@@ -21,11 +21,13 @@ from .bls12_377 import FQ_MONT_R, Q_MOD, R_MOD, fq_from_mont, fq_to_mont
 
 NONRESIDUE = Q_MOD - 5
 G2_B = (0, 155198655607781456406391640216936120121836107652948796323930557600032281009004493664981332883744016074664192874906)
+# G2_GENERATOR_{X,Y}_{C0,C1} of curves/src/bls12_377/g2.rs:228-282, converted out of Montgomery form (tests/test_oracle_golden.py
+# redoes the conversion from the limbs extracted by tests/golden/make_golden.py)
 G2_GEN = (
-    (233578398248691099356572568220835526895379068987715365179118596935057653620464273615301663571204657964920925606294,
-     140913150380207355837477652521042157274541796891053068589147167627541651775299824604154852141315666357241556069118),
-    (63160294768292073209381361943935198908131692476676907196754037919244929611450776219210369229519898517858833747423,
-     149157405641012693445398062341192467754805999074082136895788947234480009303640899064710353187729182149407503257491),
+    (170590608266080109581922461902299092015242589883741236963254737235977648828052995125541529645051927918098146183295,
+     83407003718128594709087171351153471074446327721872642659202721143408712182996929763094113874399921859453255070254),
+    (1843833842842620867708835993770650838640642469700861403869757682057607397502738488921663703124647238454792872005,
+     33145532013610981697337930729788870077912093258611421158732879580766461459275194744385880708057348608045241477209),
 )
 G2_AFFINE_STRIDE = 200
 G2_PROJECTIVE_BYTES = 288

@@ -29,7 +29,7 @@ SYMBOLS = (
     "snarkvm_b200_fr_vec_op_device", "snarkvm_b200_fr_vec_scalar_op_device", "snarkvm_b200_domain_elements_device",
     "snarkvm_b200_register_bases_precomputed",
     "snarkvm_b200_msm_batch_device", "snarkvm_b200_msm_window_sums_plan_device", "snarkvm_b200_kzg_commit_batch_hiding_device",
-    "snarkvm_b200_kzg_commit_batch_precomputed_device", "snarkvm_b200_msm_scratch_stats", "snarkvm_b200_msm_set_scratch_limit", "snarkvm_b200_msm_window_sums_host", "snarkvm_b200_selftest_coop",
+    "snarkvm_b200_kzg_commit_batch_precomputed_device", "snarkvm_b200_msm_scratch_stats", "snarkvm_b200_msm_set_scratch_limit", "snarkvm_b200_msm_window_sums_host", "snarkvm_b200_selftest_coop", "snarkvm_b200_msm_plan_levels", "snarkvm_b200_msm_g2", "snarkvm_b200_msm_g2_device", "snarkvm_b200_generate_bases_g2_device",
 )
 
 
@@ -88,6 +88,10 @@ def lib():
     L.snarkvm_b200_profile_enable.argtypes = [i32]
     L.snarkvm_b200_profile_collect.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]
     L.snarkvm_b200_generate_bases_device.argtypes = [vp, sz, sz, u64, vp]
+    L.snarkvm_b200_generate_bases_g2_device.argtypes = [vp, sz, sz, u64, vp]
+    L.snarkvm_b200_msm_plan_levels.argtypes = [sz]
+    L.snarkvm_b200_msm_g2_device.argtypes = [vp, vp, sz, vp, sz, vp]
+    L.snarkvm_b200_msm_g2.argtypes = [vp, vp, sz, vp, sz]
     L.snarkvm_b200_msm_precompute_device.argtypes = [ctypes.POINTER(vp), vp, sz, sz, vp]
     L.snarkvm_b200_msm_precomputed_free.argtypes = [vp]
     L.snarkvm_b200_msm_precomputed_info.argtypes = [vp, ctypes.POINTER(sz), ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(sz)]
@@ -115,6 +119,7 @@ def lib():
     for s in SYMBOLS[5:]:
         getattr(L, s).restype = i32
     L.snarkvm_b200_launch_count.restype = u64
+    L.snarkvm_b200_msm_g2.restype = _RustError
     _libc = ctypes.CDLL(None)
     _libc.free.argtypes = [ctypes.c_void_p]
     _lib = L

@@ -32,10 +32,13 @@ class VariableBase:
 
         The reference dispatches G1-377 to the GPU only when len > 1024 (mod.rs:35) and otherwise runs
         batched::msm on the CPU; this backend has no CPU path, so every size runs on the device."""
+        # the reference dispatches on the point TYPE (TypeId, mod.rs:33,44): here the image size stands for it —
+        # 104-byte Affine<G1> rows take the batched-affine path, 200-byte Affine<G2> rows the generic Pippenger (standard::msm)
+        g2 = getattr(bases, "ndim", 0) == 2 and bases.shape[1] == 200
         if _is_torch(bases):
             from . import device
-            return device.msm(bases, scalars)
-        return cuda.msm(bases, scalars)
+            return device.msm_g2(bases, scalars) if g2 else device.msm(bases, scalars)
+        return cuda.msm_g2(bases, scalars) if g2 else cuda.msm(bases, scalars)
 
 
 class EvaluationDomain:

@@ -556,6 +556,8 @@ int snarkvm_b200_msm_plan(size_t npoints, int* c, int* nwin, uint32_t* cap) {
     return 0;
 }
 
+int snarkvm_b200_msm_plan_levels(size_t npoints) { return msm_make_plan(npoints).levels; }
+
 int snarkvm_b200_msm_device(void* out144, const void* d_points, size_t npoints, const void* d_scalars, size_t stride,
                             void* stream) {
     if (!out144) return (int)cudaErrorInvalidValue;
@@ -809,6 +811,61 @@ int snarkvm_b200_kzg_commit_batch_hiding_device(void* out144s, const void* d_pow
                                                 const size_t* ncoeffs, const void* d_gamma_powers, const void* const* d_blinding_mont,
                                                 const size_t* nblinding, size_t count, void* stream) {
     return msm_batch_impl(out144s, d_powers, stride, d_coeffs_mont, ncoeffs, count, 1, d_gamma_powers, d_blinding_mont, nblinding, (cudaStream_t)stream);
+}
+
+// VariableBase::msm for G2 (Affine<G2> images: x.c0 x.c1 y.c0 y.c1 infinity, stride ≥ 200; canonical scalars) — the curves the
+// reference routes to standard::msm (msm/variable_base/mod.rs:44-47).  out288: HOST memory, the normalised projective image
+// (x, y, 1) or (0, 1, 0) over Fq2.
+static int msm_g2_impl(void* out288, const void* d_points, size_t npoints, const void* d_scalars, size_t stride, cudaStream_t stream) {
+    if (!out288) return (int)cudaErrorInvalidValue;
+    if (npoints == 0) { host::Xyzz2 inf = host::xyzz_inf_t<host::Fq2>(); host::xyzz_to_normalised_projective(inf, (uint64_t*)out288); return 0; }
+    if (!d_points || !d_scalars || stride < 200 || (stride & 7)) return (int)cudaErrorInvalidValue;
+    MsmPlan plan = msm_make_plan(npoints);
+    const size_t nw = (size_t)plan.nwin;
+    uint32_t* d_buf = nullptr;
+    cudaError_t e = pool_alloc(&d_buf, nw * 384 + 256, stream);
+    if (e != cudaSuccess) return (int)e;
+    uint32_t* d_flags = d_buf + nw * 96;
+    int rc = (int)cudaMemsetAsync(d_flags, 0, 256, stream);
+    if (rc == 0) rc = msm_g2_window_sums_device(d_buf, d_flags, plan, d_points, stride, d_scalars, npoints, 0, stream);
+    std::vector<host::Xyzz2> sums(nw + 1);
+    if (rc == 0) rc = (int)cudaMemcpyAsync(sums.data(), d_buf, nw * 384 + 256, cudaMemcpyDeviceToHost, stream);
+    cudaFreeAsync(d_buf, stream);
+    if (rc == 0) rc = (int)cudaStreamSynchronize(stream);
+    if (rc != 0) return rc;
+    uint32_t flags = 0;
+    memcpy(&flags, sums.data() + nw, 4);
+    if (flags & 1u) return (int)cudaErrorInvalidValue;
+    host::Xyzz2 total = host::horner_windows(sums.data(), plan.nwin, plan.c);
+    host::xyzz_to_normalised_projective(total, (uint64_t*)out288);
+    return 0;
+}
+int snarkvm_b200_msm_g2_device(void* out288, const void* d_points, size_t npoints, const void* d_scalars, size_t stride, void* stream) {
+    return msm_g2_impl(out288, d_points, npoints, d_scalars, stride, (cudaStream_t)stream);
+}
+// host-buffer form with the drop-in symbol's contract (outputs untouched on failure, error struct by value)
+snarkvm_error_t snarkvm_b200_msm_g2(void* out, const void* points, size_t npoints, const void* scalars, size_t ffi_affine_sz) {
+    if (!out) return make_error((int)cudaErrorInvalidValue);
+    uint64_t result[36];
+    if (npoints == 0) { int rc0 = msm_g2_impl(result, nullptr, 0, nullptr, 200, nullptr); if (rc0 == 0) memcpy(out, result, 288); return make_error(rc0); }
+    if (!points || !scalars || ffi_affine_sz < 200 || (ffi_affine_sz & 7)) return make_error((int)cudaErrorInvalidValue);
+    cudaStream_t stream;
+    int rc = thread_stream(&stream);
+    if (rc) return make_error(rc);
+    void *d_points = nullptr, *d_scalars = nullptr;
+    rc = (int)pool_alloc(&d_points, npoints * ffi_affine_sz, stream);
+    if (rc == 0) rc = (int)pool_alloc(&d_scalars, npoints * 32, stream);
+    if (rc == 0) rc = upload(d_scalars, scalars, npoints * 32, stream, host_is_pinned(scalars));
+    if (rc == 0) rc = upload(d_points, points, npoints * ffi_affine_sz, stream, host_is_pinned(points));
+    if (rc == 0) rc = msm_g2_impl(result, d_points, npoints, d_scalars, ffi_affine_sz, stream);
+    if (d_points) cudaFreeAsync(d_points, stream);
+    if (d_scalars) cudaFreeAsync(d_scalars, stream);
+    int rs = (int)cudaStreamSynchronize(stream);
+    if (rc == 0 && rs == 0) memcpy(out, result, 288);
+    return make_error(rc ? rc : rs);
+}
+int snarkvm_b200_generate_bases_g2_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, void* stream) {
+    return msm_generate_bases_g2_device(d_points, npoints, stride, seed, (cudaStream_t)stream);
 }
 
 int snarkvm_b200_g1_ntt_device(void* d_out, size_t out_stride, const void* d_in, size_t in_stride, uint32_t lg, int direction, void* stream) {

@@ -1,4 +1,4 @@
-// Host-side BLS12-377 Fq / G1 arithmetic used ONLY for the O(windows) tail of an MSM:
+// Host-side BLS12-377 Fq / Fq2 and G1 / G2 arithmetic used ONLY for the O(windows) tail of an MSM:
 // summing the per-window bucket sums with Horner doublings and normalising the
 // result (one inversion).  This mirrors where the reference's own CUDA plugin
 // finishes on the host (algorithms/cuda/cuda/snarkvm.cu:290-295 adds the per-GPU
@@ -72,40 +72,80 @@ inline Fq fq_inverse(const Fq& a) {            // a^{q-2}
     return acc;
 }
 
-struct Xyzz {
-    Fq X, Y, ZZ, ZZZ;
+// Fq2 = Fq[u]/(u² + 5) (curves/src/bls12_377/fq2.rs:29-65), the base field of G2
+struct Fq2 {
+    Fq c0, c1;
 };
-inline Xyzz xyzz_inf() { Xyzz r; r.X = r.Y = r.ZZ = r.ZZZ = fq_zero(); return r; }
-inline bool xyzz_is_inf(const Xyzz& p) { return fq_is_zero(p.ZZ); }
-inline void xyzz_dbl(Xyzz& p) {
-    if (xyzz_is_inf(p)) return;
-    Fq U = fq_dbl(p.Y), V = fq_sqr(U), W = fq_mul(U, V), S = fq_mul(p.X, V);
-    Fq XX = fq_sqr(p.X), M = fq_add(fq_dbl(XX), XX);
-    Fq X3 = fq_sub(fq_sqr(M), fq_dbl(S));
-    Fq Y3 = fq_sub(fq_mul(M, fq_sub(S, X3)), fq_mul(W, p.Y));
-    p.X = X3; p.Y = Y3; p.ZZ = fq_mul(V, p.ZZ); p.ZZZ = fq_mul(W, p.ZZZ);
+inline Fq fq_times5(const Fq& x) { Fq t = fq_dbl(fq_dbl(x)); return fq_add(t, x); }
+// one overload set per field so that the group law below is written once
+inline Fq f_zero(const Fq*) { return fq_zero(); }
+inline Fq f_one(const Fq*) { return fq_one(); }
+inline bool f_is_zero(const Fq& a) { return fq_is_zero(a); }
+inline Fq f_add(const Fq& a, const Fq& b) { return fq_add(a, b); }
+inline Fq f_sub(const Fq& a, const Fq& b) { return fq_sub(a, b); }
+inline Fq f_dbl(const Fq& a) { return fq_dbl(a); }
+inline Fq f_mul(const Fq& a, const Fq& b) { return fq_mul(a, b); }
+inline Fq f_sqr(const Fq& a) { return fq_sqr(a); }
+inline Fq f_inverse(const Fq& a) { return fq_inverse(a); }
+inline Fq2 f_zero(const Fq2*) { Fq2 r; r.c0 = fq_zero(); r.c1 = fq_zero(); return r; }
+inline Fq2 f_one(const Fq2*) { Fq2 r; r.c0 = fq_one(); r.c1 = fq_zero(); return r; }
+inline bool f_is_zero(const Fq2& a) { return fq_is_zero(a.c0) && fq_is_zero(a.c1); }
+inline Fq2 f_add(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = fq_add(a.c0, b.c0); r.c1 = fq_add(a.c1, b.c1); return r; }
+inline Fq2 f_sub(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = fq_sub(a.c0, b.c0); r.c1 = fq_sub(a.c1, b.c1); return r; }
+inline Fq2 f_dbl(const Fq2& a) { return f_add(a, a); }
+inline Fq2 f_mul(const Fq2& a, const Fq2& b) {
+    Fq v0 = fq_mul(a.c0, b.c0), v1 = fq_mul(a.c1, b.c1);
+    Fq2 r;
+    r.c1 = fq_sub(fq_sub(fq_mul(fq_add(a.c0, a.c1), fq_add(b.c0, b.c1)), v0), v1);
+    r.c0 = fq_sub(v0, fq_times5(v1));
+    return r;
 }
-inline void xyzz_add(Xyzz& p, const Xyzz& o) {
+inline Fq2 f_sqr(const Fq2& a) { return f_mul(a, a); }
+inline Fq2 f_inverse(const Fq2& a) {
+    Fq n = fq_inverse(fq_add(fq_sqr(a.c0), fq_times5(fq_sqr(a.c1))));
+    Fq2 r; r.c0 = fq_mul(a.c0, n); r.c1 = fq_sub(fq_zero(), fq_mul(a.c1, n));
+    return r;
+}
+
+template <class F>
+struct XyzzT {
+    F X, Y, ZZ, ZZZ;
+};
+typedef XyzzT<Fq> Xyzz;        // 192 bytes: the device's XYZZ image
+typedef XyzzT<Fq2> Xyzz2;      // 384 bytes: the device's XYZZ2 image
+template <class F> inline XyzzT<F> xyzz_inf_t() { XyzzT<F> r; r.X = r.Y = r.ZZ = r.ZZZ = f_zero((const F*)nullptr); return r; }
+inline Xyzz xyzz_inf() { return xyzz_inf_t<Fq>(); }
+template <class F> inline bool xyzz_is_inf(const XyzzT<F>& p) { return f_is_zero(p.ZZ); }
+template <class F> inline void xyzz_dbl(XyzzT<F>& p) {
+    if (xyzz_is_inf(p)) return;
+    F U = f_dbl(p.Y), V = f_sqr(U), W = f_mul(U, V), S = f_mul(p.X, V);
+    F XX = f_sqr(p.X), M = f_add(f_dbl(XX), XX);
+    F X3 = f_sub(f_sqr(M), f_dbl(S));
+    F Y3 = f_sub(f_mul(M, f_sub(S, X3)), f_mul(W, p.Y));
+    p.X = X3; p.Y = Y3; p.ZZ = f_mul(V, p.ZZ); p.ZZZ = f_mul(W, p.ZZZ);
+}
+template <class F> inline void xyzz_add(XyzzT<F>& p, const XyzzT<F>& o) {
     if (xyzz_is_inf(o)) return;
     if (xyzz_is_inf(p)) { p = o; return; }
-    Fq U1 = fq_mul(p.X, o.ZZ), U2 = fq_mul(o.X, p.ZZ), S1 = fq_mul(p.Y, o.ZZZ), S2 = fq_mul(o.Y, p.ZZZ);
-    Fq P = fq_sub(U2, U1), R = fq_sub(S2, S1);
-    if (fq_is_zero(P)) { if (fq_is_zero(R)) xyzz_dbl(p); else p = xyzz_inf(); return; }
-    Fq PP = fq_sqr(P), PPP = fq_mul(P, PP), Q = fq_mul(U1, PP);
-    Fq X3 = fq_sub(fq_sub(fq_sqr(R), PPP), fq_dbl(Q));
-    p.Y = fq_sub(fq_mul(R, fq_sub(Q, X3)), fq_mul(S1, PPP));
+    F U1 = f_mul(p.X, o.ZZ), U2 = f_mul(o.X, p.ZZ), S1 = f_mul(p.Y, o.ZZZ), S2 = f_mul(o.Y, p.ZZZ);
+    F P = f_sub(U2, U1), R = f_sub(S2, S1);
+    if (f_is_zero(P)) { if (f_is_zero(R)) xyzz_dbl(p); else p = xyzz_inf_t<F>(); return; }
+    F PP = f_sqr(P), PPP = f_mul(P, PP), Q = f_mul(U1, PP);
+    F X3 = f_sub(f_sub(f_sqr(R), PPP), f_dbl(Q));
+    p.Y = f_sub(f_mul(R, f_sub(Q, X3)), f_mul(S1, PPP));
     p.X = X3;
-    p.ZZ = fq_mul(fq_mul(p.ZZ, o.ZZ), PP);
-    p.ZZZ = fq_mul(fq_mul(p.ZZZ, o.ZZZ), PPP);
+    p.ZZ = f_mul(f_mul(p.ZZ, o.ZZ), PP);
+    p.ZZZ = f_mul(f_mul(p.ZZZ, o.ZZZ), PPP);
 }
-// Writes the 144-byte image of `result.to_affine().to_projective()`:
-// (x, y, R) or (0, R, 0) for infinity — projective.rs:51-54, 507-512; affine.rs:331-353.
-inline void xyzz_to_normalised_projective(const Xyzz& p, uint64_t out[18]) {
-    Fq one = fq_one();
-    if (xyzz_is_inf(p)) { memset(out, 0, 144); memcpy(out + 6, one.l, 48); return; }
-    Fq i = fq_inverse(fq_mul(p.ZZ, p.ZZZ));
-    Fq x = fq_mul(p.X, fq_mul(i, p.ZZZ)), y = fq_mul(p.Y, fq_mul(i, p.ZZ));
-    memcpy(out, x.l, 48); memcpy(out + 6, y.l, 48); memcpy(out + 12, one.l, 48);
+// Writes the image of `result.to_affine().to_projective()`: (x, y, 1) or (0, 1, 0) for infinity —
+// projective.rs:51-54, 507-512; affine.rs:331-353.  144 bytes for G1 (out[18]), 288 for G2 (out[36]).
+template <class F> inline void xyzz_to_normalised_projective(const XyzzT<F>& p, uint64_t* out) {
+    const size_t fb = sizeof(F);
+    F one = f_one((const F*)nullptr);
+    if (xyzz_is_inf(p)) { memset(out, 0, 3 * fb); memcpy((uint8_t*)out + fb, &one, fb); return; }
+    F i = f_inverse(f_mul(p.ZZ, p.ZZZ));
+    F x = f_mul(p.X, f_mul(i, p.ZZZ)), y = f_mul(p.Y, f_mul(i, p.ZZ));
+    memcpy(out, &x, fb); memcpy((uint8_t*)out + fb, &y, fb); memcpy((uint8_t*)out + 2 * fb, &one, fb);
 }
 // Jacobian (X, Y, Z) image -> XYZZ (ZZ = Z^2, ZZZ = Z^3)
 inline Xyzz xyzz_from_projective(const uint64_t in[18]) {
@@ -115,9 +155,9 @@ inline Xyzz xyzz_from_projective(const uint64_t in[18]) {
     if (fq_is_zero(Z)) p = xyzz_inf();
     return p;
 }
-// Σ_w 2^{c·w} · window_sum[w]  (Horner from the top window; batched.rs:404-413)
-inline Xyzz horner_windows(const Xyzz* sums, int nwin, int c) {
-    Xyzz total = xyzz_inf();
+// Σ_w 2^{c·w} · window_sum[w]  (Horner from the top window; batched.rs:404-413, standard.rs:107-117)
+template <class F> inline XyzzT<F> horner_windows(const XyzzT<F>* sums, int nwin, int c) {
+    XyzzT<F> total = xyzz_inf_t<F>();
     for (int w = nwin - 1; w >= 0; w--) {
         for (int k = 0; k < c; k++) xyzz_dbl(total);
         xyzz_add(total, sums[w]);

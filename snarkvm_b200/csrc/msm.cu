@@ -1437,6 +1437,43 @@ done:
     return rc;
 }
 
+// ---- building blocks shared with the G2 path (msm_g2.cu): the curve-independent half of Pippenger ----
+size_t msm_scan_bytes(size_t count) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)count);
+    return bytes < 16 ? 16 : bytes;
+}
+int msm_exclusive_scan(void* tmp, size_t tmp_bytes, const uint32_t* in, uint32_t* out, size_t count, cudaStream_t stream) {
+    count_launch(2);
+    return (int)cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int)count, stream);
+}
+int msm_sort_indices(const MsmPlan& plan, const void* d_scalars, size_t n, int mont, uint32_t* hist, uint32_t* bucket_start, uint32_t* cursors,
+                     uint32_t* sorted, void* cub_tmp, size_t cub_bytes, uint32_t* d_flags, cudaStream_t stream) {
+    const uint32_t TB = (uint32_t)plan.nwin * plan.nbuckets;
+    int rc = (int)cudaMemsetAsync(hist, 0, (size_t)(TB + 1) * 4, stream);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    const uint32_t* sc = (const uint32_t*)d_scalars;
+    if (mont) k_digits<false, true><<<grid, 256, 0, stream>>>(sc, n, plan.c, plan.nwin, plan.nbuckets, hist, nullptr, 0, 0u, 0u, d_flags);
+    else k_digits<false, false><<<grid, 256, 0, stream>>>(sc, n, plan.c, plan.nwin, plan.nbuckets, hist, nullptr, 0, 0u, 0u, d_flags);
+    if ((rc = msm_exclusive_scan(cub_tmp, cub_bytes, hist, bucket_start, (size_t)TB + 1, stream)) != 0) return rc;
+    if ((rc = (int)cudaMemcpyAsync(cursors, bucket_start, (size_t)(TB + 1) * 4, cudaMemcpyDeviceToDevice, stream)) != 0) return rc;
+    if (mont) k_digits<true, true><<<grid, 256, 0, stream>>>(sc, n, plan.c, plan.nwin, plan.nbuckets, cursors, sorted, 0, 0u, 0u, d_flags);
+    else k_digits<true, false><<<grid, 256, 0, stream>>>(sc, n, plan.c, plan.nwin, plan.nbuckets, cursors, sorted, 0, 0u, 0u, d_flags);
+    count_launch(3);
+    return (int)cudaGetLastError();
+}
+int msm_items_per_bucket(const uint32_t* hist, uint32_t* items, uint32_t total_buckets, uint32_t cap, cudaStream_t stream) {
+    k_items_per_bucket<<<(total_buckets + 256) / 256, 256, 0, stream>>>(hist, items, total_buckets, cap);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+int msm_group_counts(const uint32_t* start_in, uint32_t* cnt_out, uint32_t total_buckets, cudaStream_t stream) {
+    k_group_counts<<<(total_buckets + 256) / 256, 256, 0, stream>>>(start_in, cnt_out, total_buckets);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 int msm_window_sums_device(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, const void* d_points, size_t stride,
                            const void* d_scalars, size_t npoints, cudaStream_t stream) {
     MsmBases b{d_points, stride, npoints};

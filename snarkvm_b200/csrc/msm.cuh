@@ -65,6 +65,23 @@ int msm_precompute_tables_device(uint32_t* d_table, const MsmPlan& plan, const v
 int msm_precomputed_sum_device(uint32_t* d_sum, uint32_t* d_flags, const MsmPlan& plan, const uint32_t* d_table, size_t table_n, const void* d_scalars,
                                size_t nscalars, int mont, cudaStream_t stream);
 
+// Curve-independent building blocks (signed-digit bucket sort, scans, work-item counts), shared with the G2 path:
+size_t msm_scan_bytes(size_t count);
+int msm_exclusive_scan(void* tmp, size_t tmp_bytes, const uint32_t* in, uint32_t* out, size_t count, cudaStream_t stream);
+// hist / bucket_start / cursors: nwin·nbuckets + 1 u32 each; sorted: n·nwin u32 (point index | sign << 31, grouped by (window, bucket))
+int msm_sort_indices(const MsmPlan& plan, const void* d_scalars, size_t n, int mont, uint32_t* hist, uint32_t* bucket_start, uint32_t* cursors,
+                     uint32_t* sorted, void* cub_tmp, size_t cub_bytes, uint32_t* d_flags, cudaStream_t stream);
+int msm_items_per_bucket(const uint32_t* hist, uint32_t* items, uint32_t total_buckets, uint32_t cap, cudaStream_t stream);
+int msm_group_counts(const uint32_t* start_in, uint32_t* cnt_out, uint32_t total_buckets, cudaStream_t stream);
+
+// BLS12-377 G2 (points over Fq2; the curves the reference sends to standard::msm, msm/variable_base/standard.rs:79-118):
+// per-window sums Σ_b b·S_{w,b} as XYZZ points over Fq2 (96 words each) into d_window_sums[plan.nwin][96].
+// d_points: the reference's Affine<G2> images (x.c0 x.c1 y.c0 y.c1 infinity, stride ≥ 200).
+int msm_g2_window_sums_device(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, const void* d_points, size_t stride,
+                              const void* d_scalars, size_t npoints, int mont, cudaStream_t stream);
+// P_i = h(seed, i)·G2 (same multipliers as the G1 generator)
+int msm_generate_bases_g2_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, cudaStream_t stream);
+
 // Deterministic test/bench input: P_i = h(seed, i)·G with a 64-bit multiplier h
 // (every point is in the prime-order subgroup because G is).  Writes the reference
 // affine layout with the given stride.

@@ -72,14 +72,69 @@ __global__ void k_divide_by_vanishing(const uint32_t* __restrict__ p, size_t m, 
     if (i < rlen) (acc + Fr::load_ldg(p + i * 8)).store(r + i * 8);
 }
 
+// The loop above costs m/n additions per output: fine for the quotient by a large domain (m/n ≤ a few), quadratic for a SMALL
+// one — Varuna's first round divides a |C|-coefficient polynomial by the vanishing polynomial of the input domain (n = 4 … 64),
+// 2.7·10^11 additions at |C| = 2^20.  View p as rows of n coefficients: q is the exclusive suffix sum DOWN each column.  Blocks of
+// RB rows: (1) per-block column sums, (2) a suffix scan over the blocks of each column, (3) every block walks its rows once more
+// with its offset — 2m additions, depth RB + #blocks ≈ 2·sqrt(m/n).
+__global__ void k_dbv_block_sums(const uint32_t* __restrict__ p, size_t m, size_t n, size_t rb, size_t nblocks, uint32_t* __restrict__ S) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nblocks * n) return;
+    const size_t b = t / n, c = t % n;
+    Fr acc = Fr::zero();
+    for (size_t k = b * rb; k < (b + 1) * rb; k++) { const size_t j = k * n + c; if (j < m) acc = acc + Fr::load_ldg(p + j * 8); }
+    acc.store(S + t * 8);
+}
+__global__ void k_dbv_block_scan(uint32_t* __restrict__ S, size_t n, size_t nblocks) {     // in place: S[b][c] ← Σ_{b' > b} S[b'][c]
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    Fr run = Fr::zero();
+    for (size_t b = nblocks; b-- > 0;) {
+        const Fr v = Fr::load(S + (b * n + c) * 8);
+        run.store(S + (b * n + c) * 8);
+        run = run + v;
+    }
+}
+__global__ void k_dbv_finish(const uint32_t* __restrict__ p, size_t m, size_t n, size_t rb, size_t nblocks, const uint32_t* __restrict__ T,
+                             uint32_t* __restrict__ q, uint32_t* __restrict__ r) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nblocks * n) return;
+    const size_t b = t / n, c = t % n, qlen = m > n ? m - n : 0, rlen = m < n ? m : n;
+    Fr run = Fr::load(T + t * 8);                                                          // Σ of the rows below this block
+    for (size_t k = (b + 1) * rb; k-- > b * rb;) {
+        const size_t j = k * n + c;
+        if (j >= m) continue;
+        const Fr v = Fr::load_ldg(p + j * 8);
+        if (j < qlen) run.store(q + j * 8);
+        if (j < rlen) (run + v).store(r + j * 8);
+        run = run + v;
+    }
+}
+
 int poly_divide_by_vanishing_device(void* d_q, void* d_r, const void* d_p, size_t m, size_t n, cudaStream_t stream) {
     if (n == 0) return (int)cudaErrorInvalidValue;
     if (m == 0) return 0;
     const size_t qlen = m > n ? m - n : 0, rlen = m < n ? m : n, work = qlen > rlen ? qlen : rlen;
     if (!d_p || !d_r || (qlen && !d_q)) return (int)cudaErrorInvalidValue;
-    k_divide_by_vanishing<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>((const uint32_t*)d_p, m, n, (uint32_t*)d_q, (uint32_t*)d_r);
-    count_launch();
-    return (int)cudaGetLastError();
+    const size_t rows = (m + n - 1) / n;
+    if (rows <= 64) {
+        k_divide_by_vanishing<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>((const uint32_t*)d_p, m, n, (uint32_t*)d_q, (uint32_t*)d_r);
+        count_launch();
+        return (int)cudaGetLastError();
+    }
+    size_t rb = 1;
+    while (rb * rb < rows) rb <<= 1;                                                       // ≈ sqrt(rows), a power of two
+    const size_t nblocks = (rows + rb - 1) / rb, cells = nblocks * n;
+    uint32_t* S = nullptr;
+    cudaError_t e = pool_alloc(&S, cells * 32, stream);
+    if (e != cudaSuccess) return (int)e;
+    k_dbv_block_sums<<<(unsigned)((cells + 127) / 128), 128, 0, stream>>>((const uint32_t*)d_p, m, n, rb, nblocks, S);
+    k_dbv_block_scan<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(S, n, nblocks);
+    k_dbv_finish<<<(unsigned)((cells + 127) / 128), 128, 0, stream>>>((const uint32_t*)d_p, m, n, rb, nblocks, S, (uint32_t*)d_q, (uint32_t*)d_r);
+    count_launch(3);
+    int rc = (int)cudaGetLastError();
+    cudaFreeAsync(S, stream);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

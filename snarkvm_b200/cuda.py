@@ -89,6 +89,23 @@ def msm(points: np.ndarray, scalars: np.ndarray) -> np.ndarray:
     return out
 
 
+def msm_g2(points: np.ndarray, scalars: np.ndarray) -> np.ndarray:
+    """Σ scalars[i]·points[i] over G2: points uint8 [n, 200] (Affine<G2> images), scalars uint64 [m, 4] canonical → the 288-byte
+    Projective<G2> image as uint64[36] (normalised).  Same length / error contract as `msm`."""
+    if not (isinstance(points, np.ndarray) and points.dtype == np.uint8 and points.ndim == 2 and points.flags["C_CONTIGUOUS"]):
+        raise TypeError("points must be a C-contiguous uint8 array [n, ffi_affine_sz]")
+    if not (isinstance(scalars, np.ndarray) and scalars.dtype == np.uint64 and scalars.ndim == 2 and scalars.shape[1] == 4
+            and scalars.flags["C_CONTIGUOUS"]):
+        raise TypeError("scalars must be a C-contiguous uint64 array [m, 4]")
+    npoints = scalars.shape[0]
+    if npoints > points.shape[0]:
+        raise ValueError(f"length mismatch {points.shape[0]} points < {npoints} scalars")
+    out = np.zeros(36, dtype=np.uint64)
+    err = _lib.lib().snarkvm_b200_msm_g2(out.ctypes.data, points.ctypes.data, npoints, scalars.ctypes.data, points.shape[1])
+    _lib.check_rust_error(err)
+    return out
+
+
 def register_bases(points: np.ndarray) -> None:
     """Extension: keep `points` resident on the current device; later msm(points, …) calls with this same array skip
     the upload (the array must stay alive and unmodified until unregister_bases)."""

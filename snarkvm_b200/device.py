@@ -70,7 +70,7 @@ def polymul(polys: list, evals: list, lg: int) -> torch.Tensor:
 def msm_plan(npoints: int) -> dict:
     c, nwin, cap = ctypes.c_int(), ctypes.c_int(), ctypes.c_uint32()
     _lib.check(_lib.lib().snarkvm_b200_msm_plan(npoints, ctypes.byref(c), ctypes.byref(nwin), ctypes.byref(cap)))
-    return {"c": c.value, "nwin": nwin.value, "cap": cap.value}
+    return {"c": c.value, "nwin": nwin.value, "cap": cap.value, "levels": int(_lib.lib().snarkvm_b200_msm_plan_levels(npoints))}
 
 
 def _msm_args(bases: torch.Tensor, scalars: torch.Tensor, stride: int):
@@ -90,6 +90,28 @@ def msm(bases: torch.Tensor, scalars: torch.Tensor, stride: int = AFFINE_STRIDE)
         _lib.check(_lib.lib().snarkvm_b200_msm_device(out.ctypes.data, _check(bases, "bases"), npoints,
                                                        _check(scalars, "scalars"), stride, _stream()))
     return out
+
+
+G2_AFFINE_STRIDE = 200       # Affine<G2>: x.c0 x.c1 y.c0 y.c1 (4 × 48 B) infinity pad
+
+
+def msm_g2(bases: torch.Tensor, scalars: torch.Tensor, stride: int = G2_AFFINE_STRIDE) -> np.ndarray:
+    """VariableBase::msm over G2 (standard::msm semantics) with bases and scalars resident in HBM → normalised Projective<G2>
+    image uint64[36] (X, Y, Z over Fq2)."""
+    npoints = _msm_args(bases, scalars, stride)
+    out = np.zeros(36, dtype=np.uint64)
+    with torch.cuda.device(bases.device):
+        _lib.check(_lib.lib().snarkvm_b200_msm_g2_device(out.ctypes.data, _check(bases, "bases"), npoints,
+                                                          _check(scalars, "scalars"), stride, _stream()))
+    return out
+
+
+def generate_bases_g2(npoints: int, seed: int, device="cuda", stride: int = G2_AFFINE_STRIDE) -> torch.Tensor:
+    """Synthetic G2 bases P_i = h(seed, i)·G2 in the reference Affine<G2> layout, generated in HBM."""
+    t = torch.empty((npoints, stride), dtype=torch.uint8, device=device)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.lib().snarkvm_b200_generate_bases_g2_device(t.data_ptr(), npoints, stride, seed & (2**64 - 1), _stream()))
+    return t
 
 
 def msm_window_sums(bases: torch.Tensor, scalars: torch.Tensor, stride: int = AFFINE_STRIDE, plan_npoints: int | None = None,

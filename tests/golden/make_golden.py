@@ -68,6 +68,20 @@ golden["g1"] = {
     "GENERATOR_X_DEC": re.search(r"G1_GENERATOR_X =\s*\n///\s*(\d+)", g1).group(1),
     "GENERATOR_Y_DEC": re.search(r"G1_GENERATOR_Y =\s*\n///\s*(\d+)", g1).group(1),
 }
+g2src = read("curves/src/bls12_377/g2.rs")
+fq2src = read("curves/src/bls12_377/fq2.rs")
+def _new_limbs(src, name):
+    body = re.search(r"pub const " + name + r"\b.*?new\(\[(.*?)\]\)", src, re.S).group(1)
+    return [int(t) for t in body.replace("\n", " ").split(",") if t.strip()]
+golden["g2"] = {
+    "source": "curves/src/bls12_377/g2.rs:38-107,228-282 (WEIERSTRASS_B, COFACTOR, generator; Montgomery limbs) and "
+              "curves/src/bls12_377/fq2.rs:29-65 (NONRESIDUE); KAT curves/src/bls12_377/tests.rs:673-678 (generator on curve, order r)",
+    "GENERATOR_X_C0_MONT": _new_limbs(g2src, "G2_GENERATOR_X_C0"), "GENERATOR_X_C1_MONT": _new_limbs(g2src, "G2_GENERATOR_X_C1"),
+    "GENERATOR_Y_C0_MONT": _new_limbs(g2src, "G2_GENERATOR_Y_C0"), "GENERATOR_Y_C1_MONT": _new_limbs(g2src, "G2_GENERATOR_Y_C1"),
+    "WEIERSTRASS_B_MONT": bigints(g2src, "WEIERSTRASS_B"),
+    "COFACTOR": bigints(g2src, "COFACTOR")[0],
+    "NONRESIDUE_MONT": bigints(fq2src, "NONRESIDUE")[0],
+}
 dom = {}
 for name in ("R", "C", "K"):
     txt = read(f"algorithms/src/snark/varuna/resources/circuit_0/domain/{name}.txt")

@@ -101,7 +101,8 @@ def test_batch_inversion_and_mul(oracle_cpu, n):
     assert (back[:16] == want).all()
 
 
-@pytest.mark.parametrize("m,n", [(5, 8), (8, 8), (9, 8), (40, 8), (4096, 1024), (3 * 4096 - 5, 4096), (100, 4), (1, 1)])
+@pytest.mark.parametrize("m,n", [(5, 8), (8, 8), (9, 8), (40, 8), (4096, 1024), (3 * 4096 - 5, 4096), (100, 4), (1, 1),
+                                 (70000, 4), (65 * 8, 8), (65 * 8 + 3, 8), (100001, 1), (50000, 64)])   # many rows per column: the blocked suffix scan
 def test_divide_by_vanishing_poly_and_evaluate(oracle_cpu, m, n):
     from snarkvm_b200.algorithms import DensePolynomial, EvaluationDomain
     p = random_fr_mont(m, seed=m + n)

@@ -99,6 +99,49 @@ def test_g1_generator(golden, oracle_cpu):
     assert out.tobytes() == py.projective_bytes_normalised(None)
 
 
+def test_g2_constants_and_generator(golden):
+    """The G2 oracle's numbers are the reference's (g2.rs, fq2.rs): NONRESIDUE = −5, B' = (0, b1), the generator's four Fq
+    coordinates converted out of Montgomery form; the generator is on the curve and has order r (bls12_377/tests.rs:673-678);
+    the cofactor times r is the curve order implied by … at least #E'(Fq2) = cofactor·r kills a random curve point."""
+    from oracle import g2
+    g = golden["g2"]
+    assert py.fq_from_mont(py.from_limbs(g["NONRESIDUE_MONT"])) == g2.NONRESIDUE == py.Q_MOD - 5
+    b0, b1 = (py.fq_from_mont(py.from_limbs(l)) for l in g["WEIERSTRASS_B_MONT"])
+    assert (b0, b1) == g2.G2_B
+    gen = ((py.fq_from_mont(py.from_limbs(g["GENERATOR_X_C0_MONT"])), py.fq_from_mont(py.from_limbs(g["GENERATOR_X_C1_MONT"]))),
+           (py.fq_from_mont(py.from_limbs(g["GENERATOR_Y_C0_MONT"])), py.fq_from_mont(py.from_limbs(g["GENERATOR_Y_C1_MONT"]))))
+    assert gen == g2.G2_GEN
+    assert g2.g2_is_on_curve(gen)
+    assert g2.g2_mul(gen, py.R_MOD - 1) == g2.g2_neg(gen) and g2.g2_add(g2.g2_mul(gen, py.R_MOD - 1), gen) is None
+    # Fq2 arithmetic: u² = −5, inverses
+    assert g2.f2_mul((0, 1), (0, 1)) == (py.Q_MOD - 5, 0)
+    x = (123456789, 987654321)
+    assert g2.f2_mul(x, g2.f2_inv(x)) == (1, 0)
+    # layouts round-trip and have the reference sizes
+    img = g2.g2_affine_bytes(gen)
+    assert len(img) == 200 and g2.g2_affine_from_bytes(img) == gen and len(g2.g2_projective_bytes_normalised(gen)) == 288
+    assert g2.g2_affine_from_bytes(g2.g2_affine_bytes(None)) is None
+
+
+def test_g2_standard_msm_matches_naive_sum():
+    """standard::msm restated (standard.rs:24-118) against Σ s_i·P_i by double-and-add (msm_naive, mod.rs:52-57) — the check the
+    reference's own test makes (mod.rs:90-119) — incl. scalars 0, 1 (the unit-scalar shortcut), r − 1, repeated and opposite points"""
+    import random
+    from oracle import g2
+    rnd = random.Random(11)
+    for n in (1, 7, 40):
+        ks = [rnd.randrange(1, 1 << 30) for _ in range(n)]
+        bases = [g2.g2_mul(g2.G2_GEN, k) for k in ks]
+        sc = [rnd.randrange(py.R_MOD) for _ in range(n)]
+        if n >= 7:
+            sc[0], sc[1], sc[2] = 0, 1, py.R_MOD - 1
+            bases[3] = bases[4]; ks[3] = ks[4]
+            bases[5] = g2.g2_neg(bases[6]); ks[5] = -ks[6]; sc[5] = sc[6]
+        want = g2.g2_mul(g2.G2_GEN, sum(k * s for k, s in zip(ks, sc)) % py.R_MOD)
+        assert g2.standard_msm(bases, sc) == want
+        assert g2.msm_naive(bases, sc) == want
+
+
 def _srs_points(count):
     with open(os.path.join(HERE, "golden", "powers_of_beta_15_first512.usrs"), "rb") as f:
         return py.parse_usrs_points(f.read(), count)

@@ -54,11 +54,11 @@ def run(lg, reps=2, mul_depth=3):
            "phases_ms": {k: round(v * 1e3, 2) for k, v in best.items() if k != "total"},
            "workload": f"TestCircuit 2^{lg} constraints × 2^{lg} variables, 1 instance, non-hiding; rounds 1–5 + one batched KZG commit pass per round; "
                        "sponge and batch opening not included"}
-    print(json.dumps(out), flush=True)
     del powers
     torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":
     for lg in [int(a) for a in sys.argv[1:]] or [16, 18, 20]:
-        run(lg)
+        print(json.dumps(run(lg)), flush=True)
