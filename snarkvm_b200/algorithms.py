@@ -100,6 +100,10 @@ class EvaluationDomain:
     def coset_ifft_in_place(self, evals):
         return self._run(evals, NTTDirection.Inverse, NTTType.Coset)              # domain.rs:216-221
 
+    def evaluate_all_lagrange_coefficients(self, tau: int, dev="cuda"):
+        """fft/domain.rs:258-292 → CUDA tensor [size, 4] (Montgomery)"""
+        return _lagrange_coefficients(self, tau % _R_MOD, dev)
+
     def fft(self, coeffs):
         return self.fft_in_place(coeffs.clone() if _is_torch(coeffs) else np.array(coeffs, copy=True))
 
@@ -111,6 +115,101 @@ class EvaluationDomain:
 
     def coset_ifft(self, evals):
         return self.coset_ifft_in_place(evals.clone() if _is_torch(evals) else np.array(evals, copy=True))
+
+
+def _lagrange_coefficients(domain: "EvaluationDomain", tau: int, dev):
+    """EvaluationDomain::evaluate_all_lagrange_coefficients (fft/domain.rs:258-292) on the device → CUDA tensor [n, 4] Montgomery"""
+    import torch
+    from . import device
+    n = domain.size
+    t_size = pow(tau, n, _R_MOD)
+    elems = device.domain_elements(domain.log_size_of_group, dev)
+    one = torch.from_numpy(_fr_int_to_mont(1).view(np.int64)).to(dev)
+    if t_size == 1:
+        # tau is a domain element: the indicator vector of its position (domain.rs:264-275)
+        tm = torch.from_numpy(_fr_int_to_mont(tau % _R_MOD).view(np.int64)).to(dev)
+        out = torch.zeros((n, 4), dtype=torch.int64, device=dev)
+        out[(elems == tm).all(dim=1)] = one
+        return out
+    # u_i = l·ω^i / (τ − ω^i), l = (τ^n − 1)/n: invert (ω^i − τ) with coefficient −l, multiply by ω^i (domain.rs:277-291)
+    l = (t_size - 1) * pow(n, -1, _R_MOD) % _R_MOD
+    u = device.fr_vec_op(elems, _fr_int_to_mont(tau % _R_MOD), device.FR_SUB)
+    device.fr_batch_inversion_and_mul(u, _fr_int_to_mont((-l) % _R_MOD))
+    return device.fr_vec_op(u, elems, device.FR_MUL)
+
+
+class Evaluations:
+    """fft/evaluations.rs:31-218 with the values resident in HBM: `evaluations` is a CUDA tensor [domain.size, 4] int64 (Montgomery
+    Fr).  The reference's IFFTPrecomputation arguments have no counterpart: the twiddle table is cached per device inside the library."""
+
+    def __init__(self, evaluations, domain: "EvaluationDomain"):
+        self.evaluations, self._domain = evaluations, domain
+
+    @classmethod
+    def from_vec_and_domain(cls, evaluations, domain: "EvaluationDomain"):
+        """evaluations.rs:40-43: resized (zero-padded or truncated) to the domain"""
+        import torch
+        n = domain.size
+        if evaluations.shape[0] != n:
+            e = torch.zeros((n, 4), dtype=evaluations.dtype, device=evaluations.device)
+            k = min(n, evaluations.shape[0])
+            e[:k] = evaluations[:k]
+            evaluations = e
+        return cls(evaluations.contiguous(), domain)
+
+    def domain(self) -> "EvaluationDomain":
+        return self._domain
+
+    def interpolate_by_ref(self) -> "DensePolynomial":
+        """evaluations.rs:46-48 (the input is kept)"""
+        return DensePolynomial(self._domain.ifft_in_place(self.evaluations.clone()))
+
+    def interpolate(self) -> "DensePolynomial":
+        """evaluations.rs:59-63: consumes the evaluations (transformed in place)"""
+        coeffs = self._domain.ifft_in_place(self.evaluations)
+        self.evaluations = None
+        return DensePolynomial(coeffs)
+
+    def evaluate_with_coeffs(self, lagrange_coefficients_at_point):
+        """evaluations.rs:91-93: Σ eval_i·L_i(point) → 32-byte Montgomery image (uint64[4])"""
+        from . import device
+        prod = device.fr_vec_op(self.evaluations, lagrange_coefficients_at_point, device.FR_MUL)
+        return device.poly_evaluate(prod, _fr_int_to_mont(1))                      # Σ c_i·1^i
+
+    def evaluate(self, point_mont):
+        """evaluations.rs:86-89"""
+        tau = _fr_mont_to_int(point_mont)
+        return self.evaluate_with_coeffs(_lagrange_coefficients(self._domain, tau, self.evaluations.device))
+
+    def _zip(self, other: "Evaluations", op):
+        from . import device
+        if self._domain.size != other._domain.size:
+            raise ValueError("domains are unequal")                               # evaluations.rs:119,141,163,186
+        return Evaluations(device.fr_vec_op(self.evaluations, other.evaluations, op), self._domain)
+
+    def __mul__(self, other):
+        from . import device
+        return self._zip(other, device.FR_MUL)
+
+    def __add__(self, other):
+        from . import device
+        return self._zip(other, device.FR_ADD)
+
+    def __sub__(self, other):
+        from . import device
+        return self._zip(other, device.FR_SUB)
+
+    def __truediv__(self, other):
+        """evaluations.rs:181-189: elementwise a / b — one batched inversion of the divisor, then a product; a zero divisor
+        panics in the reference (Field division) and raises here"""
+        from . import device
+        if self._domain.size != other._domain.size:
+            raise ValueError("domains are unequal")
+        if bool((other.evaluations == 0).all(dim=1).any()):
+            raise ZeroDivisionError("division by a zero evaluation")
+        inv = other.evaluations.clone()
+        device.fr_batch_inversion_and_mul(inv, _fr_int_to_mont(1))
+        return Evaluations(device.fr_vec_op(self.evaluations, inv, device.FR_MUL), self._domain)
 
 
 class PolyMultiplier:

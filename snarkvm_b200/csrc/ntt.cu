@@ -141,8 +141,15 @@ static int get_coset_tables(int lg, int inverse, CosetTables* out) {
 // ---------------------------------------------------------------------------
 // One pass = stages [t0, t0+S) of the DIF network on a 2^S × 2^Q tile in shared memory.
 // ---------------------------------------------------------------------------
+// Two layout variants measured and left OFF (tools/bin A/B builds, profiles/r2l_ntt_variants.log, 2^24 forward): the XOR
+// swizzle that removes the last pass's transposed-store bank conflicts 4.065 → 4.089 ms, the last pass's ≤ 128 twiddles staged
+// in shared memory 4.065 → 4.119 ms, both 4.216 ms — the conflicts and the L1-resident twiddle loads were never on the
+// critical path (the butterflies are bound by the multiplier), the extra index arithmetic and shared-memory traffic are.
 #ifndef NTT_SMEM_TW
-#define NTT_SMEM_TW 1
+#define NTT_SMEM_TW 0
+#endif
+#ifndef NTT_SWIZZLE
+#define NTT_SWIZZLE 0
 #endif
 struct PassArgs {
     const Fr* in;
@@ -172,10 +179,10 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
     // different bank groups and row-wise accesses stay a permutation of one 128-byte line.
     struct Tile {
         uint4* p; uint32_t n; uint32_t q, cmask;
-#ifdef NTT_NO_SWIZZLE
-        __device__ __forceinline__ uint32_t sw(uint32_t i) const { return i; }
-#else
+#if NTT_SWIZZLE
         __device__ __forceinline__ uint32_t sw(uint32_t i) const { return i ^ ((i >> q) & cmask); }
+#else
+        __device__ __forceinline__ uint32_t sw(uint32_t i) const { return i; }
 #endif
         __device__ __forceinline__ Fr get(uint32_t i0) const {
             const uint32_t i = sw(i0);
@@ -342,7 +349,7 @@ static constexpr int MAX_STAGES = 8;    // rows per tile ≤ 256
 static constexpr int TILE_LG = 11;      // 2^11 elements × 32 B = 64 KiB of shared memory per CTA
 // + the last pass's 2^(S-1) twiddles: ≤ 128 for a multi-pass transform, up to 1024 when a whole transform of ≤ 2^11
 // elements is one pass
-static inline size_t tw_smem_bytes(int S, bool last) { return last && S > 0 ? ((size_t)32 << (S - 1)) : 0; }
+static inline size_t tw_smem_bytes(int S, bool last) { return NTT_SMEM_TW && last && S > 0 ? ((size_t)32 << (S - 1)) : 0; }
 
 int ntt_device(void* d_inout, uint32_t lg, int direction, int type, void* d_scratch, cudaStream_t stream) {
     if (lg > NTT_MAX_LG) return (int)cudaErrorInvalidValue;

@@ -252,21 +252,7 @@ class Prover:
     # ---- evaluate_all_lagrange_coefficients (fft/domain.rs:258-292) on the device ----
     @staticmethod
     def lagrange_coefficients(domain: EvaluationDomain, tau: int, dev) -> torch.Tensor:
-        n = domain.size
-        t_size = pow(tau, n, R_MOD)
-        elems = device.domain_elements(domain.log_size_of_group, dev)
-        if t_size == 1:
-            # tau is a domain element: the indicator vector of its position
-            tm = torch.from_numpy(_mont(tau).view(np.int64)).to(dev)
-            hit = (elems == tm).all(dim=1)
-            out = _zeros(n, dev)
-            out[hit] = torch.from_numpy(_mont(1).view(np.int64)).to(dev)
-            return out
-        # u_i = l·ω^i / (τ − ω^i), l = (τ^n − 1)/n: invert (ω^i − τ) with coefficient −l, multiply by ω^i
-        l = (t_size - 1) * pow(n, -1, R_MOD) % R_MOD
-        u = device.fr_vec_op(elems, _mont(tau), device.FR_SUB)
-        device.fr_batch_inversion_and_mul(u, _mont(-l))
-        return device.fr_vec_op(u, elems, device.FR_MUL)
+        return domain.evaluate_all_lagrange_coefficients(tau, dev)
 
     # ---- round 3: lineval sumcheck (third.rs:126-205, 266-326) ----
     def third_round(self, alpha: int, eta_b: int, eta_c: int, circuit_combiner: int = 1, instance_combiners=None):

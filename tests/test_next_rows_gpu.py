@@ -8,7 +8,7 @@ import pytest
 
 from oracle import bls12_377 as py
 
-from helpers import affine_array, fr_ints_to_mont_array, oracle_bases, random_canonical_fr, random_fr_mont
+from helpers import affine_array, fr_ints_to_mont_array, mont_array_to_fr_ints, oracle_bases, random_canonical_fr, random_fr_mont
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -117,6 +117,35 @@ def test_divide_by_vanishing_poly_and_evaluate(oracle_cpu, m, n):
         assert (poly.evaluate(z) == oracle_cpu.poly_evaluate(p, z)).all()
     zero = np.zeros(4, dtype=np.uint64)
     assert (poly.evaluate(zero) == p[0]).all()                 # dense.rs:101-102
+
+
+@pytest.mark.parametrize("n", [8, 1024])
+def test_evaluations_type(oracle_cpu, n):
+    """Evaluations (fft/evaluations.rs): interpolate ∘ evaluate_over_domain = id, evaluate(point) equals the interpolated polynomial at
+    the point (through evaluate_all_lagrange_coefficients, also for a point INSIDE the domain), elementwise * + − / against big ints,
+    unequal domains and zero divisors are rejected"""
+    from snarkvm_b200.algorithms import DensePolynomial, EvaluationDomain, Evaluations
+    dom = EvaluationDomain.new(n)
+    a, b = random_fr_mont(n, seed=n + 1), random_fr_mont(n, seed=n + 2)
+    ea, eb = Evaluations.from_vec_and_domain(_dev(a), dom), Evaluations.from_vec_and_domain(_dev(b), dom)
+    ai, bi = mont_array_to_fr_ints(a), mont_array_to_fr_ints(b)
+    for got, op in ((ea * eb, lambda x, y: x * y), (ea + eb, lambda x, y: x + y), (ea - eb, lambda x, y: x - y),
+                    (ea / eb, lambda x, y: x * pow(y, -1, py.R_MOD))):
+        assert mont_array_to_fr_ints(_host_u64(got.evaluations)) == [op(x, y) % py.R_MOD for x, y in zip(ai, bi)]
+    poly = ea.interpolate_by_ref()
+    assert (_host_u64(poly.coeffs) == oracle_cpu.ntt(a, oracle_cpu.INVERSE)).all()
+    assert (_host_u64(poly.evaluate_over_domain(dom)) == a).all()
+    z = random_fr_mont(1, seed=99)[0]
+    assert (ea.evaluate(z) == oracle_cpu.poly_evaluate(_host_u64(poly.coeffs).reshape(-1, 4), z)).all()
+    w5 = fr_ints_to_mont_array([pow(py.fr_root_of_unity(n), 5, py.R_MOD)])[0]            # a domain element: the indicator branch
+    assert (ea.evaluate(w5) == a[5]).all()
+    short = Evaluations.from_vec_and_domain(_dev(a[: n // 2 + 1]), dom)                    # resize: zero-padded
+    assert (_host_u64(short.evaluations)[n // 2 + 1:] == 0).all() and short.evaluations.shape[0] == n
+    with pytest.raises(ValueError):
+        ea * Evaluations.from_vec_and_domain(_dev(a), EvaluationDomain.new(2 * n))
+    zb = b.copy(); zb[3] = 0
+    with pytest.raises(ZeroDivisionError):
+        ea / Evaluations.from_vec_and_domain(_dev(zb), dom)
 
 
 def test_evaluate_large_and_over_domain(oracle_cpu):

@@ -3,7 +3,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 import numpy as np, torch
 from snarkvm_b200 import device
 from snarkvm_b200.cuda import NTTDirection, NTTType
-for lg in (16, 20, 22, 24):
+import sys
+for lg in ([int(a) for a in sys.argv[1:]] or (16, 20, 22, 24)):
     n = 1 << lg
     x = torch.from_numpy(np.random.default_rng(0).integers(0, 2**60, size=(n, 4), dtype=np.int64)).cuda()
     sc = torch.empty_like(x)
