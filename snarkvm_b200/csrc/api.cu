@@ -206,6 +206,11 @@ private:
     };
     CopyPool() {
         int n = 12;                                              // 2^24-point pageable snarkvm_msm: 6 → 128 ms, 12 → 114–120 ms, 24/48 no better (profiles/r2i_e2e_pageable.log)
+        // one process per GPU on a shared host (torchrun exports LOCAL_WORLD_SIZE): do not oversubscribe the cores with copy threads
+        if (const char* lws = getenv("LOCAL_WORLD_SIZE")) {
+            const int procs = atoi(lws), cores = (int)std::thread::hardware_concurrency();
+            if (procs > 1 && cores > 0) { int per = cores / procs - 1; if (per < 2) per = 2; if (per < n) n = per; }
+        }
         if (const char* e = getenv("SNARKVM_B200_COPY_THREADS")) { int v = atoi(e); if (v >= 0 && v <= 64) n = v; }
         nthreads_ = n;
         for (int i = 0; i < n; i++) std::thread([this] { loop(); }).detach();
