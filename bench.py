@@ -474,8 +474,13 @@ def run_product(args, rank, world, local_rank):
         xs_pin_t = torch.from_numpy(xs_page.view(np.int64).copy()).pin_memory()
         xs_pin = xs_pin_t.numpy().view(np.uint64)
         ntt_e2e = {}
+        e2e_in = torch.from_numpy(xs_page.view(np.int64)).to(dev)
+        e2e_want = device.ntt_(e2e_in, NTTDirection.Forward, NTTType.Standard, scratch).cpu().numpy().view(np.uint64)   # the path checked against the oracle above
+        del e2e_in
         for name, buf in (("pageable", xs_page), ("pinned", xs_pin)):
             shim.NTT(nn, buf, shim.NTTInputOutputOrder.NN, shim.NTTDirection.Forward, shim.NTTType.Standard)
+            checks["ntt_e2e_" + name] = bool((buf == e2e_want).all())
+            assert checks["ntt_e2e_" + name], "snarkvm_ntt (host buffer) differs from the device-resident transform"
             ms, _ = wall_timed(lambda: shim.NTT(nn, buf, shim.NTTInputOutputOrder.NN, shim.NTTDirection.Forward, shim.NTTType.Standard), 2)
             ntt_e2e[name] = ms
         per_pass_ms = pass_ms / max(1, pass_n)

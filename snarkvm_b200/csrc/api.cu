@@ -187,6 +187,20 @@ public:
         Batch batch;
         batch.dst = (uint8_t*)dst; batch.src = (const uint8_t*)src; batch.bytes = bytes; batch.piece = piece;
         batch.npieces = (bytes + piece - 1) / piece;
+        run(batch);
+    }
+    // `rows` rows of `width` bytes, row r at dst + r·dpitch ← src + r·spitch (a column range of a row-major matrix)
+    void parallel_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows) {
+        if (rows == 0 || width == 0) return;
+        Batch batch;
+        batch.dst = (uint8_t*)dst; batch.src = (const uint8_t*)src; batch.bytes = rows * width; batch.piece = width;
+        batch.npieces = rows; batch.dpitch = dpitch; batch.spitch = spitch; batch.rows = true;
+        if (nthreads_ == 0) { work(batch); return; }
+        run(batch);
+    }
+private:
+    struct Batch;
+    void run(Batch& batch) {
         {
             std::lock_guard<std::mutex> lock(mu_);
             queue_.push_back(&batch);
@@ -198,9 +212,10 @@ public:
         // no worker can pick the batch up any more; wait for the ones inside it
         done_cv_.wait(lock, [&] { return batch.active == 0; });
     }
-private:
     struct Batch {
         uint8_t* dst; const uint8_t* src; size_t bytes, piece, npieces;
+        size_t dpitch = 0, spitch = 0;
+        bool rows = false;
         std::atomic<size_t> next{0};
         int active = 0;                                           // workers inside work(); guarded by mu_
     };
@@ -219,6 +234,7 @@ private:
         for (;;) {
             size_t k = b.next.fetch_add(1);
             if (k >= b.npieces) return;
+            if (b.rows) { memcpy(b.dst + k * b.dpitch, b.src + k * b.spitch, b.piece); continue; }
             size_t off = k * b.piece, len = b.bytes - off < b.piece ? b.bytes - off : b.piece;
             memcpy(b.dst + off, b.src + off, len);
         }
@@ -329,6 +345,98 @@ int ntt_ordered(void* d, uint32_t lg, int order, int dir, int type, void* scratc
     return rc;
 }
 
+// snarkvm_ntt for large NN transforms: the host buffer crosses PCIe by COLUMN RANGES underneath the first and the last pass.
+// Pass 0 works on tiles that are column ranges of the 2^S0 × 2^(lg−S0) row-major view of the input, the last pass produces
+// column ranges of the 2^SL × 2^t0 view of the output (ntt.cu): range k + 1 is uploaded while pass 0 runs on range k, and range
+// k is downloaded while the last pass runs on range k + 1.  A 2^24 transform is 2 × 9.6 ms of PCIe around 4.1 ms of kernels; this
+// hides the 2.7 ms of the two outer passes.  Pageable buffers go through the thread's pinned ring, row by row.
+// The passes before the last are checked for errors BEFORE the first byte is written back (the Rust caller falls back to its CPU
+// path on an error code and needs its input intact).
+int ntt_host_pipelined(void* inout, uint32_t lg, int dir, int type, cudaStream_t stream, bool pinned) {
+    NttPass passes[8];
+    int P = 0, rc = ntt_make_passes(lg, passes, &P);
+    if (rc) return rc;
+    const size_t n = (size_t)1 << lg, bytes = n * 32;
+    const NttPass &p0 = passes[0], &pl = passes[P - 1];
+    const size_t rows0 = (size_t)1 << p0.S, cols0 = n >> p0.S, rowsL = (size_t)1 << pl.S, colsL = n >> pl.S;
+    // chunks: whole tiles, ≤ one staging slot per chunk for pageable buffers
+    size_t K = 8;
+    while ((bytes / K) > StageRing::SLOT_BYTES && !pinned) K <<= 1;
+    while (K > 1 && ((p0.tiles % K) || (pl.tiles % K))) K >>= 1;
+    if (P < 2 || K < 2 || (!pinned && bytes / K > StageRing::SLOT_BYTES)) return -1;       // not applicable: the caller takes the plain path
+    cudaStream_t copy = nullptr;
+    void *d = nullptr, *scratch = nullptr;
+    std::vector<cudaEvent_t> ev(2 * K + 1, nullptr);
+    rc = thread_copy_stream(&copy);
+    if (rc == 0) rc = (int)pool_alloc(&d, bytes, stream);
+    if (rc == 0) rc = (int)pool_alloc(&scratch, bytes, stream);
+    for (auto& e : ev) if (rc == 0) rc = (int)cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (rc == 0 && !pinned) rc = t_ring.init();
+    if (rc == 0) rc = (int)cudaEventRecord(ev[2 * K], stream);                       // the allocations are ordered on `stream`
+    if (rc == 0) rc = (int)cudaStreamWaitEvent(copy, ev[2 * K], 0);
+    uint8_t* h = (uint8_t*)inout;
+    // ---- upload by column ranges, pass 0 right behind each ----
+    for (size_t k = 0; k < K && rc == 0; k++) {
+        const size_t c0 = cols0 / K * k, nc = cols0 / K, width = nc * 32, pitch = cols0 * 32;
+        if (pinned) {
+            rc = (int)cudaMemcpy2DAsync((uint8_t*)d + c0 * 32, pitch, h + c0 * 32, pitch, width, rows0, cudaMemcpyHostToDevice, copy);
+        } else {
+            const int sl = t_ring.next;
+            t_ring.next = (sl + 1) % StageRing::SLOTS;
+            if (t_ring.used[sl]) rc = (int)cudaEventSynchronize(t_ring.ev[sl]);
+            if (rc == 0) {
+                CopyPool::get().parallel_rows(t_ring.buf[sl], width, h + c0 * 32, pitch, width, rows0);
+                rc = (int)cudaMemcpy2DAsync((uint8_t*)d + c0 * 32, pitch, t_ring.buf[sl], width, width, rows0, cudaMemcpyHostToDevice, copy);
+            }
+            if (rc == 0) rc = (int)cudaEventRecord(t_ring.ev[sl], copy);
+            t_ring.used[sl] = true;
+        }
+        if (rc == 0) rc = (int)cudaEventRecord(ev[k], copy);
+        if (rc == 0) rc = (int)cudaStreamWaitEvent(stream, ev[k], 0);
+        if (rc == 0) rc = ntt_launch_pass(d, scratch, lg, dir, type, 0, p0.tiles / K * k, p0.tiles / K, stream);
+    }
+    for (int p = 1; p + 1 < P && rc == 0; p++) rc = ntt_launch_pass(d, scratch, lg, dir, type, p, 0, passes[p].tiles, stream);
+    if (rc == 0) rc = (int)cudaStreamSynchronize(stream);                            // everything so far succeeded: the output may start to land
+    // ---- last pass by column ranges, download right behind each ----
+    struct Pending { int slot; size_t c0; };
+    std::deque<Pending> pending;                                                      // pageable: slots whose DMA is in flight, oldest first
+    const size_t ncL = colsL / K, widthL = ncL * 32, pitchL = colsL * 32;
+    auto unstage = [&](const Pending& pd) -> int {
+        int r = (int)cudaEventSynchronize(t_ring.ev[pd.slot]);
+        if (r == 0) CopyPool::get().parallel_rows(h + pd.c0 * 32, pitchL, t_ring.buf[pd.slot], widthL, widthL, rowsL);
+        t_ring.used[pd.slot] = false;
+        return r;
+    };
+    if (rc == 0 && !pinned)
+        for (int i = 0; i < StageRing::SLOTS && rc == 0; i++) { if (t_ring.used[i]) rc = (int)cudaEventSynchronize(t_ring.ev[i]); t_ring.used[i] = false; }
+    for (size_t k = 0; k < K && rc == 0; k++) {
+        const size_t c0 = ncL * k;
+        rc = ntt_launch_pass(d, scratch, lg, dir, type, P - 1, pl.tiles / K * k, pl.tiles / K, stream);
+        if (rc == 0) rc = (int)cudaEventRecord(ev[K + k], stream);
+        if (rc == 0) rc = (int)cudaStreamWaitEvent(copy, ev[K + k], 0);
+        if (rc != 0) break;
+        if (pinned) {
+            rc = (int)cudaMemcpy2DAsync(h + c0 * 32, pitchL, (uint8_t*)d + c0 * 32, pitchL, widthL, rowsL, cudaMemcpyDeviceToHost, copy);
+        } else {
+            if ((int)pending.size() == StageRing::SLOTS) { rc = unstage(pending.front()); pending.pop_front(); if (rc) break; }
+            int sl = -1;
+            for (int i = 0; i < StageRing::SLOTS; i++) if (!t_ring.used[i]) { sl = i; break; }
+            rc = (int)cudaMemcpy2DAsync(t_ring.buf[sl], widthL, (uint8_t*)d + c0 * 32, pitchL, widthL, rowsL, cudaMemcpyDeviceToHost, copy);
+            if (rc == 0) rc = (int)cudaEventRecord(t_ring.ev[sl], copy);
+            t_ring.used[sl] = true;
+            pending.push_back(Pending{sl, c0});
+        }
+    }
+    while (rc == 0 && !pending.empty()) { rc = unstage(pending.front()); pending.pop_front(); }
+    if (copy) { int rs = (int)cudaStreamSynchronize(copy); if (rc == 0) rc = rs; }
+    { int rs = (int)cudaStreamSynchronize(stream); if (rc == 0) rc = rs; }
+    if (!pinned) for (int i = 0; i < StageRing::SLOTS; i++) t_ring.used[i] = false;
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (d) cudaFreeAsync(d, stream);
+    if (scratch) cudaFreeAsync(scratch, stream);
+    return rc;
+}
+
 int polymul_device_impl(void* d_out, size_t pcount, const void* const* d_polys, const size_t* plens, size_t ecount,
                         const void* const* d_evals, const size_t* elens, uint32_t lg, cudaStream_t stream) {
     const size_t n = (size_t)1 << lg, bytes = n * 32;
@@ -378,6 +486,15 @@ snarkvm_error_t snarkvm_ntt(void* inout, uint32_t lg, snarkvm_ntt_order_t order,
     if (rc) return make_error(rc);
     const size_t bytes = ((size_t)1 << lg) * 32;
     const bool pinned = host_is_pinned(inout);
+    static const bool no_pipe = getenv("SNARKVM_B200_NTT_NO_PIPELINE") != nullptr;
+    if (lg >= 20 && order == SNARKVM_NTT_NN && !no_pipe) {
+        rc = ntt_host_pipelined(inout, lg, (int)dir, (int)type, stream, pinned);
+        if (rc != -1) {
+            int rs = (int)cudaStreamSynchronize(stream);
+            return make_error(rc ? rc : rs);
+        }
+        rc = 0;
+    }
     void *d = nullptr, *scratch = nullptr;
     rc = (int)pool_alloc(&d, bytes, stream);
     if (rc == 0) rc = (int)pool_alloc(&scratch, bytes, stream);

@@ -162,6 +162,7 @@ struct PassArgs {
     int t0, S, Q;
     int last;            // 1: rows are contiguous sub-arrays, output is bit-reversed scatter
     int inverse;
+    uint32_t tile0;      // first tile of this launch (a pass may be launched in column ranges)
     int pre;             // 1: multiply input j by coset_lo/hi (forward coset)
     int post;            // 0 none, 1: × n^{-1}, 2: × coset_lo/hi[k] (hi already carries n^{-1})
 };
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
     const int L = lg - t0 - S;                       // low index bits below the tile's row digit
     const uint32_t rows = 1u << S, cols = 1u << Q, tile_elems = rows << Q;
     const Tile sm{smem_raw, tile_elems, (uint32_t)Q, cols - 1u};
-    const size_t tile = blockIdx.x;
+    const size_t tile = (size_t)blockIdx.x + a.tile0;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
 
     size_t H = 0, low_base = 0, hprime_base = 0;
@@ -351,20 +352,44 @@ static constexpr int TILE_LG = 11;      // 2^11 elements × 32 B = 64 KiB of sha
 // elements is one pass
 static inline size_t tw_smem_bytes(int S, bool last) { return NTT_SMEM_TW && last && S > 0 ? ((size_t)32 << (S - 1)) : 0; }
 
-int ntt_device(void* d_inout, uint32_t lg, int direction, int type, void* d_scratch, cudaStream_t stream) {
-    if (lg > NTT_MAX_LG) return (int)cudaErrorInvalidValue;
-    if (direction != NTT_FORWARD && direction != NTT_INVERSE) return (int)cudaErrorInvalidValue;
-    if (type != NTT_STANDARD && type != NTT_COSET) return (int)cudaErrorInvalidValue;
-    int rc = 0;
-    Fr* A = (Fr*)d_inout;
-    Fr* B = (Fr*)d_scratch;
-    bool own_scratch = false;
+// The passes of one transform: stages [t0, t0 + S) on tiles of 2^S rows × 2^Q columns.
+int ntt_make_passes(uint32_t lg, NttPass* out, int* npasses) {
+    if (lg > NTT_MAX_LG || !out || !npasses) return (int)cudaErrorInvalidValue;
+    const int P = lg <= (uint32_t)TILE_LG ? 1 : (int)((lg + MAX_STAGES - 1) / MAX_STAGES);
+    int t0 = 0;
+    for (int p = 0; p < P; p++) {
+        const int remaining = (int)lg - t0;
+        const int S = (remaining + (P - p) - 1) / (P - p);
+        const bool last = p == P - 1;
+        int Q = TILE_LG - S;
+        if (Q > 3) Q = 3;
+        if (last) { if (Q > t0) Q = t0; }
+        else { const int L = (int)lg - t0 - S; if (Q > L) Q = L; }
+        out[p].t0 = t0; out[p].S = S; out[p].Q = Q;
+        out[p].tiles = ((size_t)1 << lg) >> (S + Q);
+        t0 += S;
+    }
+    *npasses = P;
+    return 0;
+}
+
+// Tiles [tile0, tile0 + ntiles) of pass `p`.  Pass 0 reads A; the last pass writes A; everything in between lives in B.
+// Tile t of pass 0 holds columns [t·2^Q, (t+1)·2^Q) of the 2^S × 2^(lg−S) row-major view of the input; tile t of the last pass
+// produces the same column range of the 2^S × 2^t0 view of the (natural-order) output — which is what lets a host-buffer
+// transform upload / download by column ranges underneath those two passes (snarkvm_ntt in api.cu).
+int ntt_launch_pass(void* d_A, void* d_B, uint32_t lg, int direction, int type, int p, size_t tile0, size_t ntiles, cudaStream_t stream) {
+    if (lg > NTT_MAX_LG || (direction != NTT_FORWARD && direction != NTT_INVERSE) || (type != NTT_STANDARD && type != NTT_COSET))
+        return (int)cudaErrorInvalidValue;
+    NttPass passes[8];
+    int P = 0, rc = ntt_make_passes(lg, passes, &P);
+    if (rc) return rc;
+    if (p < 0 || p >= P || tile0 + ntiles > passes[p].tiles || (P > 1 && !d_B)) return (int)cudaErrorInvalidValue;
+    if (ntiles == 0) return 0;
     const Fr* tw = nullptr;
     int lgN = 0;
     CosetTables ct{nullptr, nullptr, nullptr};
     const bool inverse = direction == NTT_INVERSE, coset = type == NTT_COSET;
     static std::once_flag smem_once[64];
-
     if ((rc = get_twiddles((int)lg, &tw, &lgN)) != 0) return rc;
     if (inverse || coset) { if ((rc = get_coset_tables((int)lg, inverse ? 1 : 0, &ct)) != 0) return rc; }
     {
@@ -373,43 +398,36 @@ int ntt_device(void* d_inout, uint32_t lg, int direction, int type, void* d_scra
             cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << TILE_LG) * (int)sizeof(Fr) + (int)tw_smem_bytes(TILE_LG, true));
         });
     }
+    PassArgs a;
+    a.tw = tw; a.coset_lo = ct.lo; a.coset_hi = ct.hi; a.ninv = ct.ninv;
+    a.lg = (int)lg; a.lgN = lgN; a.t0 = passes[p].t0; a.S = passes[p].S; a.Q = passes[p].Q;
+    a.last = (p == P - 1) ? 1 : 0;
+    a.inverse = inverse ? 1 : 0;
+    a.pre = (p == 0 && coset && !inverse) ? 1 : 0;
+    a.post = (a.last && inverse) ? (coset ? 2 : 1) : 0;
+    a.in = (p == 0) ? (const Fr*)d_A : (const Fr*)d_B;
+    a.out = (P == 1 || a.last) ? (Fr*)d_A : (Fr*)d_B;
+    a.tile0 = (uint32_t)tile0;
+    const size_t smem = ((size_t)1 << (a.S + a.Q)) * sizeof(Fr) + tw_smem_bytes(a.S, a.last != 0);
     {
-        // split lg into P passes of near-equal stage counts
-        int P = lg <= (uint32_t)TILE_LG ? 1 : (int)((lg + MAX_STAGES - 1) / MAX_STAGES);
-        if (P > 1 && !B) {
-            CUDA_TRY(pool_alloc((void**)&B, ((size_t)1 << lg) * sizeof(Fr), stream));
-            own_scratch = true;
-        }
-        int t0 = 0;
-        for (int p = 0; p < P; p++) {
-            int remaining = (int)lg - t0;
-            int S = (remaining + (P - p) - 1) / (P - p);
-            PassArgs a;
-            a.tw = tw; a.coset_lo = ct.lo; a.coset_hi = ct.hi; a.ninv = ct.ninv;
-            a.lg = (int)lg; a.lgN = lgN; a.t0 = t0; a.S = S;
-            a.last = (p == P - 1) ? 1 : 0;
-            a.inverse = inverse ? 1 : 0;
-            a.pre = (p == 0 && coset && !inverse) ? 1 : 0;
-            a.post = (a.last && inverse) ? (coset ? 2 : 1) : 0;
-            int Q = TILE_LG - S;
-            if (Q > 3) Q = 3;
-            if (a.last) { if (Q > t0) Q = t0; }
-            else { int L = (int)lg - t0 - S; if (Q > L) Q = L; }
-            a.Q = Q;
-            a.in = (p == 0) ? A : B;
-            a.out = (P == 1) ? A : (a.last ? A : B);
-            size_t tiles = ((size_t)1 << lg) >> (S + Q);
-            size_t smem = ((size_t)1 << (S + Q)) * sizeof(Fr) + tw_smem_bytes(S, a.last != 0);
-            {
-                ProfScope pass_scope(PROF_NTT_PASS, stream);
-                k_ntt_pass<<<(unsigned)tiles, 256, smem, stream>>>(a);
-            }
-            count_launch();
-            t0 += S;
-        }
-        CUDA_TRY(cudaGetLastError());
+        ProfScope pass_scope(PROF_NTT_PASS, stream);
+        k_ntt_pass<<<(unsigned)ntiles, 256, smem, stream>>>(a);
     }
-done:
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int ntt_device(void* d_inout, uint32_t lg, int direction, int type, void* d_scratch, cudaStream_t stream) {
+    NttPass passes[8];
+    int P = 0, rc = ntt_make_passes(lg, passes, &P);
+    if (rc) return rc;
+    void* B = d_scratch;
+    bool own_scratch = false;
+    if (P > 1 && !B) {
+        if ((rc = (int)pool_alloc(&B, ((size_t)1 << lg) * sizeof(Fr), stream)) != 0) return rc;
+        own_scratch = true;
+    }
+    for (int p = 0; p < P && rc == 0; p++) rc = ntt_launch_pass(d_inout, B, lg, direction, type, p, 0, passes[p].tiles, stream);
     if (own_scratch) cudaFreeAsync(B, stream);
     return rc;
 }

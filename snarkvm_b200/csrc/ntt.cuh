@@ -26,6 +26,11 @@ enum NttType { NTT_STANDARD = 0, NTT_COSET = 1 };
 // is taken from the stream-ordered pool).  Returns cudaError_t as int.
 int ntt_device(void* d_inout, uint32_t lg, int direction, int type, void* d_scratch, cudaStream_t stream);
 
+// One transform = ntt_make_passes(lg) passes; pass p may be launched in tile ranges (see ntt.cu for the tile ↔ column-range map).
+struct NttPass { int t0, S, Q; size_t tiles; };
+int ntt_make_passes(uint32_t lg, NttPass* out /* ≥ 8 entries */, int* npasses);
+int ntt_launch_pass(void* d_A, void* d_B, uint32_t lg, int direction, int type, int pass, size_t tile0, size_t ntiles, cudaStream_t stream);
+
 // in-place bit-reversal permutation of 2^lg Fr elements (NR / RN / RR orders)
 int fr_bitrev_device(void* d_x, uint32_t lg, cudaStream_t stream);
 

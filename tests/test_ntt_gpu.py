@@ -33,6 +33,32 @@ def test_ntt_host_ffi_vs_oracle(oracle_cpu, lg):
         assert (got == want).all(), (lg, d, t)
 
 
+@pytest.mark.parametrize("lg", [20, 21, 22])
+def test_ntt_host_ffi_pipelined_vs_oracle(oracle_cpu, lg, monkeypatch):
+    """snarkvm_ntt from 2^20 elements: the host buffer is uploaded / downloaded by column ranges under the first and last pass
+    (ntt_host_pipelined) — pageable numpy memory (staged through the pinned ring row by row) and pinned memory (2-D DMA straight
+    from the caller's buffer), all four transforms; the plain path (switch off) must agree"""
+    import torch
+    from snarkvm_b200 import cuda
+    n = 1 << lg
+    x = random_fr_mont(n, seed=300 + lg)
+    pinned = torch.empty((n, 4), dtype=torch.int64).pin_memory()
+    for d, t in MODES:
+        want = oracle_cpu.ntt(x, d, t)
+        got = x.copy()
+        cuda.NTT(n, got, cuda.NTTInputOutputOrder.NN, cuda.NTTDirection(d), cuda.NTTType(t))
+        assert (got == want).all(), (lg, d, t, "pageable")
+        pinned.numpy()[:] = x.view(np.int64)
+        buf = pinned.numpy().view(np.uint64)
+        cuda.NTT(n, buf, cuda.NTTInputOutputOrder.NN, cuda.NTTDirection(d), cuda.NTTType(t))
+        assert (buf == want).all(), (lg, d, t, "pinned")
+    got = x.copy()                                                        # the other orders keep the plain path
+    cuda.NTT(n, got, cuda.NTTInputOutputOrder.NR, cuda.NTTDirection(0), cuda.NTTType(0))
+    back = got.copy()
+    cuda.NTT(n, back, cuda.NTTInputOutputOrder.RN, cuda.NTTDirection(1), cuda.NTTType(0))
+    assert (back == x).all()
+
+
 @pytest.mark.parametrize("lg", [1, 5, 11, 12, 13, 16, 17, 20, 21])
 def test_ntt_device_api_vs_oracle(oracle_cpu, lg):
     from snarkvm_b200.algorithms import EvaluationDomain
