@@ -25,7 +25,7 @@ def _host_u64(t):
     return t.cpu().numpy().view(np.uint64)
 
 
-@pytest.mark.parametrize("lg", [0, 1, 2, 3, 6, 9])
+@pytest.mark.parametrize("lg", [0, 1, 2, 3, 6, 7, 8, 9, 12])
 def test_g1_ifft_vs_oracle(oracle_cpu, lg):
     from snarkvm_b200 import device
     n = 1 << lg
@@ -47,7 +47,7 @@ def test_lagrange_basis_real_srs_and_commit_lagrange(oracle_cpu):
     """lagrange_basis of the real powers-of-beta (kzg10/data_structures.rs:68-72); then commit_lagrange(evals) == commit(ifft(evals)):
     the two commitment keys commit to the same polynomial (kzg10/mod.rs:98-206)."""
     from snarkvm_b200.algorithms import KZG10, EvaluationDomain, UniversalParams
-    n = 256
+    n = 512                                                    # every point of the committed excerpt of the mainnet file
     blob = open(os.path.join(HERE, "golden", "powers_of_beta_15_first512.usrs"), "rb").read()
     powers = affine_array(py.parse_usrs_points(blob, n))
     dpowers = _dev(powers)
