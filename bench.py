@@ -230,6 +230,12 @@ def run_reference(args, rank, world):
     chk = Checker()
     cpu = chk.cpu
     lg = args.ref_lg
+    if lg <= 0:
+        # the workload's own size when the whole run stays within a few minutes (≈ 0.75 µs per point on 64 cores), else the
+        # largest smaller power of two that does: 2^24 for ≤ 12 timed steps, 2^23 for ≤ 24, 2^22 beyond
+        lg = args.lg
+        while lg > 16 and args.steps * (1 << lg) * 0.75e-6 > 150.0:
+            lg -= 1
     bases = cpu_bases(1 << lg)
     threads = cpu.num_threads()
     scal = random_scalars(1 << lg, 777)
@@ -651,9 +657,9 @@ def main():
     ap.add_argument("--total-lg", type=int, default=26, help="BASELINE config 5a: total points of the strong-scaling sharded MSM (0 = skip)")
     ap.add_argument("--ntt-lg", type=int, default=24)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-lg", type=int, default=22, help="cpu_baseline sample size (bounded)")
+    ap.add_argument("--cpu-lg", type=int, default=24, help="cpu_baseline sample size (bounded: 2^24 points ≈ 12 s on 64 cores)")
     ap.add_argument("--cpu-ntt-lg", type=int, default=22)
-    ap.add_argument("--ref-lg", type=int, default=22, help="--impl reference: points per step (bounded sample)")
+    ap.add_argument("--ref-lg", type=int, default=0, help="--impl reference: log2 points per step (0 = the workload's size if the run stays within a few minutes, else the largest bounded sample that does)")
     ap.add_argument("--ref-ntt-lg", type=int, default=22)
     ap.add_argument("--kzg-lg", type=int, default=22)
     ap.add_argument("--varuna-lg", type=int, default=18, help="log2 constraints of the Varuna prover-rounds extra (0 = skip)")

@@ -151,6 +151,9 @@ static int get_coset_tables(int lg, int inverse, CosetTables* out) {
 #ifndef NTT_SWIZZLE
 #define NTT_SWIZZLE 0
 #endif
+#ifndef NTT_TW_PREFETCH
+#define NTT_TW_PREFETCH 0      // measured: 4.06 → 4.37 ms at 2^24 (profiles/r2o_ntt_prefetch.log): the duplicated index arithmetic costs more issue slots than the hidden twiddle latency returns
+#endif
 struct PassArgs {
     const Fr* in;
     Fr* out;
@@ -247,6 +250,37 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs a) {
         // NTT_UNROLL butterflies per thread per trip with all operands requested up front.  Measured on B200 at
         // 2^24: unroll 1 → 4.15 ms, 2 → 4.95 ms, 4 → 7.36 ms (the extra registers cost more occupancy than the
         // overlapped latency gains), so the default is 1.
+#if NTT_TW_PREFETCH
+        // (variant, off) The twiddle of the thread's NEXT butterfly is requested before the current one is multiplied: the first two passes read
+        // theirs from HBM / L2 (long_scoreboard 2.6 and 1.9 stall cycles per issue in profiles/r2_ntt_metrics.csv against 0.7 in
+        // the last pass, whose ≤ 128 twiddles sit in L1), and with shared memory capping the SM at 3 CTAs the 8 extra registers
+        // cost no occupancy (≤ 85 registers per thread).
+        auto tw_ptr = [&](uint32_t b) -> const Fr* {             // address of butterfly b's twiddle, or null when it is 1
+            const uint32_t c = b & (cols - 1), j = b >> Q, r_lo = j & ((1u << hb) - 1u);
+            const size_t r = a.last ? (size_t)r_lo : (((size_t)r_lo << L) | low_base | c);
+            const size_t ex = r << t;
+            return ex ? a.tw + ((a.inverse ? (((size_t)1 << (lg - 1)) - ex) : ex) << tw_shift) : nullptr;
+        };
+        const Fr* wp = tid < nbf ? tw_ptr(tid) : nullptr;
+        Fr wn = Fr::one();
+        if (wp) wn = Fr::load(wp);
+        for (uint32_t b = tid; b < nbf; b += nthr) {
+            const Fr w = wn;
+            const bool has = wp != nullptr;
+            const uint32_t nb = b + nthr;
+            wp = nb < nbf ? tw_ptr(nb) : nullptr;
+            if (wp) wn = Fr::load(wp);
+            const uint32_t c = b & (cols - 1), j = b >> Q, r_lo = j & ((1u << hb) - 1u);
+            const uint32_t d_lo = ((j >> hb) << (hb + 1)) | r_lo;
+            const uint32_t il = (d_lo << Q) | c, ih = il + ((1u << hb) << Q);
+            const Fr x = sm.get(il), y = sm.get(ih);
+            Fr dif = x - y;
+            if (has) { dif = dif * w; if (a.inverse) dif = dif.neg(); }
+            sm.put(il, x + y); sm.put(ih, dif);
+        }
+        __syncthreads();
+        continue;
+#endif
         for (uint32_t b0 = tid; b0 < nbf; b0 += nthr * NTT_UNROLL) {
             Fr x[NTT_UNROLL], y[NTT_UNROLL], w[NTT_UNROLL];
             uint32_t il[NTT_UNROLL], ih[NTT_UNROLL];
