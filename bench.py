@@ -555,6 +555,13 @@ def run_product(args, rank, world, local_rank):
             kzg["precomputed_tables"] = {"value": nk * world / (pre_ms * 1e-3), "unit": "coefficients/s", "ms_per_commit": pre_ms,
                                          "window_bits": pre.c, "windows": pre.nwin, "table_bytes": pre.table_bytes,
                                          "one_time_precompute_s": pre_s, "note": "plain (non-hiding) commitment over the tables"}
+            if nb <= nk:
+                gotp = pre.kzg_commit_batch(polys)
+                checks["kzg_batch_tables_vs_single"] = bool((gotp[0] == want0).all() and (gotp[7] == device.kzg_commit(powers, polys[7])).all())
+                assert checks["kzg_batch_tables_vs_single"]
+                pb_ms, _ = timed(lambda: pre.kzg_commit_batch(polys), 5)
+                kzg["precomputed_tables"]["round_batch"] = {"value": 8 * nb * world / (pb_ms * 1e-3), "unit": "coefficients/s", "ms_per_round": pb_ms,
+                                                            "workload": "8 polynomials × 2^20 coefficients, one pass over the tables"}
             pre.free()
         # UniversalParams::lagrange_basis: iFFT over G1 points (data_structures.rs:68-72)
         ng = 1 << args.g1_ntt_lg

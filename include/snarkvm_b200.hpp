@@ -31,6 +31,9 @@ struct BigInteger256 { uint64_t l[4]; };           // canonical scalar (utilitie
 struct Fq { uint64_t l[6]; };                      // Fp384<FqParameters>, Montgomery form (fields/src/fp_384.rs:52)
 struct G1Affine { Fq x, y; bool infinity; uint8_t pad[7]; };   // affine.rs:41-46 — 104 bytes
 struct G1Projective { Fq x, y, z; };               // projective.rs:36-41 — 144 bytes, infinity ⇔ z == 0
+struct Fq2 { Fq c0, c1; };                         // Fp2<Fq2Parameters> (curves/src/bls12_377/fq2.rs:29)
+struct G2Affine { Fq2 x, y; bool infinity; uint8_t pad[7]; };  // the same Affine template over Fq2 — 200 bytes
+struct G2Projective { Fq2 x, y, z; };              // 288 bytes
 static_assert(sizeof(G1Affine) == 104 && sizeof(G1Projective) == 144 && sizeof(Fr) == 32, "reference layouts");
 
 struct CudaError {                                  // cuda::Error (lib.rs:19)
@@ -91,6 +94,13 @@ inline Result<G1Projective> msm(const G1Affine* points, size_t npoints_available
     r.err = detail::take(snarkvm_msm(&r.value, points, nscalars, scalars, sizeof(G1Affine)));
     return r;
 }
+// the same call for Affine<G2> (the reference routes every curve but BLS12-377 G1 to standard::msm, mod.rs:44-47)
+inline Result<G2Projective> msm_g2(const G2Affine* points, size_t npoints_available, const BigInteger256* scalars, size_t nscalars) {
+    if (nscalars > npoints_available) throw std::invalid_argument("length mismatch: fewer points than scalars");
+    Result<G2Projective> r;
+    r.err = detail::take(snarkvm_b200_msm_g2(&r.value, points, nscalars, scalars, sizeof(G2Affine)));
+    return r;
+}
 }  // namespace cuda
 
 // algorithms/src/msm/variable_base/mod.rs:27-49.  The reference uses the GPU only for len > 1024 and otherwise (or on Err)
@@ -98,6 +108,10 @@ inline Result<G1Projective> msm(const G1Affine* points, size_t npoints_available
 struct VariableBase {
     static Result<G1Projective> msm(const std::vector<G1Affine>& bases, const std::vector<BigInteger256>& scalars) {
         return cuda::msm(bases.data(), bases.size(), scalars.data(), scalars.size());
+    }
+    // the generic arm of the TypeId dispatch (mod.rs:44-47)
+    static Result<G2Projective> msm(const std::vector<G2Affine>& bases, const std::vector<BigInteger256>& scalars) {
+        return cuda::msm_g2(bases.data(), bases.size(), scalars.data(), scalars.size());
     }
 };
 

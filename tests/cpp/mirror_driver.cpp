@@ -39,6 +39,16 @@ int main(int argc, char** argv) {
     check(r, "VariableBase::msm");
     write_all(d + "msm.out", &r.value, 1);
 
+    {   // the generic arm of VariableBase::msm: Affine<G2> bases (optional input file)
+        std::ifstream probe(d + "g2_bases.bin", std::ios::binary);
+        if (probe.good()) {
+            auto g2b = read_all<G2Affine>(d + "g2_bases.bin");
+            auto g2s = read_all<BigInteger256>(d + "g2_scalars.bin");
+            auto r2 = VariableBase::msm(g2b, g2s);
+            check(r2, "VariableBase::msm (G2)");
+            write_all(d + "msm_g2.out", &r2.value, 1);
+        }
+    }
     auto x = read_all<Fr>(d + "fr.bin");
     auto dom = EvaluationDomain::new_(x.size());
     if (!dom) return 2;

@@ -44,8 +44,18 @@ def test_cpp_mirror_compiles_and_reports_errors_without_gpu(tmp_path, oracle_cpu
 def test_cpp_mirror_matches_oracle(tmp_path, oracle_cpu):
     exe = _build(tmp_path)
     bases, scal, x, p1, p2 = _write_inputs(tmp_path, oracle_cpu)
+    # G2 inputs: 40 multiples of the generator (big-int oracle) and random scalars
+    from oracle import g2
+    from helpers import random_canonical_fr
+    g2_pts = [g2.g2_mul(g2.G2_GEN, 1000 + 7 * i) for i in range(40)]
+    g2_scal = random_canonical_fr(40, seed=66)
+    np.frombuffer(b"".join(g2.g2_affine_bytes(q) for q in g2_pts), dtype=np.uint8).tofile(tmp_path / "g2_bases.bin")
+    g2_scal.tofile(tmp_path / "g2_scalars.bin")
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    got2 = np.fromfile(tmp_path / "msm_g2.out", dtype=np.uint64)
+    ints = [sum(int(v) << (64 * i) for i, v in enumerate(row)) for row in g2_scal]
+    assert (got2 == np.frombuffer(g2.g2_projective_bytes_normalised(g2.standard_msm(g2_pts, ints)), dtype=np.uint64)).all()
     got = np.fromfile(tmp_path / "msm.out", dtype=np.uint64)
     assert (got == oracle_cpu.msm(bases, scal, 0)).all()
     for name, d, t in (("fft", 0, 0), ("ifft", 1, 0), ("coset_fft", 0, 1), ("coset_ifft", 1, 1)):
