@@ -14,6 +14,7 @@
 #define FF_CALL_MUL 1
 #include "ec.cuh"
 #include "cta_inverse.cuh"
+#include "quad.cuh"
 
 namespace b200 {
 
@@ -166,10 +167,14 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
     }
 }
 
-__global__ void k_items_per_bucket(const uint32_t* __restrict__ hist, uint32_t* __restrict__ items, uint32_t total_buckets, uint32_t cap) {
+__global__ void k_items_per_bucket(const uint32_t* __restrict__ hist, uint32_t* __restrict__ items, uint32_t total_buckets, uint32_t cap,
+                                   uint32_t* __restrict__ hot /* may be null; hot[0] = count, hot[1 …] = buckets with more than 32 items */, uint32_t hot_max) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < total_buckets) items[i] = (hist[i] + cap - 1u) / cap;
-    else if (i == total_buckets) items[i] = 0;
+    if (i < total_buckets) {
+        const uint32_t it = (hist[i] + cap - 1u) / cap;
+        items[i] = it;
+        if (hot != nullptr && it > 32u) { const uint32_t pos = atomicAdd(hot, 1u); if (pos < hot_max) hot[1u + pos] = i; }
+    } else if (i == total_buckets) items[i] = 0;
 }
 
 // Dense points are 96 B (x, y Montgomery); infinity is encoded as (0, 0), which is not on y² = x³ + 1.
@@ -924,6 +929,202 @@ __global__ void __launch_bounds__(32) k_window_combine_warp(const uint32_t* __re
     if (lane == 0) total.store(out + (size_t)set * XYZZ_WORDS);
 }
 
+// =================================================================================================
+// The same tail with FOUR LANES PER POINT (quad.cuh): an XYZZ addition costs 4 dependent multiplications instead of 14.
+//   * k_bucket_accumulate_q8 — one WARP per work item: quad s adds every 8th entry (mixed additions), 3-step butterfly
+//                              over the eight quads (sizes where the whole problem is a few thousand items);
+//   * k_bucket_reduce_quad   — one warp per 8 buckets: 3-step suffix scan + 3-step sum give (Σ (l+1)·S_l, Σ S_l);
+//   * k_window_combine_quad  — one CTA per bucket set folds the (acc, run) entries 8 at a time, level after level in
+//                              shared memory: acc' = Σ acc_s + w·Σ s·run_s, run' = Σ run_s for entries spanning w buckets.
+// =================================================================================================
+FF_DEV XYZZ load_xyzz_plain(const uint32_t* p) {              // global or shared memory, 16-byte aligned
+    XYZZ r; const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint32_t w[XYZZ_WORDS];
+#pragma unroll
+    for (int i = 0; i < XYZZ_WORDS / 4; i++) { const uint4 t = q[i]; w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w; }
+#pragma unroll
+    for (int j = 0; j < 12; j++) { r.X.v[j] = w[j]; r.Y.v[j] = w[12 + j]; r.ZZ.v[j] = w[24 + j]; r.ZZZ.v[j] = w[36 + j]; }
+    return r;
+}
+FF_DEV void store_xyzz_plain(uint32_t* p, const XYZZ& a) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    uint32_t w[XYZZ_WORDS];
+#pragma unroll
+    for (int j = 0; j < 12; j++) { w[j] = a.X.v[j]; w[12 + j] = a.Y.v[j]; w[24 + j] = a.ZZ.v[j]; w[36 + j] = a.ZZZ.v[j]; }
+#pragma unroll
+    for (int i = 0; i < XYZZ_WORDS / 4; i++) q[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+
+__global__ void __launch_bounds__(128, 2) k_bucket_accumulate_q8(const uint32_t* __restrict__ records, const uint32_t* __restrict__ sorted,
+                                                                 const uint32_t* __restrict__ bucket_start, const uint32_t* __restrict__ item_start,
+                                                                 uint32_t total_buckets, uint32_t cap, uint32_t* __restrict__ partial) {
+    const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (item >= item_start[total_buckets]) return;               // whole warps
+    const Quad Q = Quad::here();
+    uint32_t lo = 0, hi = total_buckets;                         // item_start[lo] <= item < item_start[hi]
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (item_start[mid] <= item) lo = mid; else hi = mid; }
+    const uint32_t seg = item - item_start[lo];
+    const uint32_t b0 = bucket_start[lo], b1 = bucket_start[lo + 1];
+    const uint32_t s0 = b0 + seg * cap, s1 = s0 + cap < b1 ? s0 + cap : b1;
+    XYZZ acc = XYZZ::infinity();
+    {
+        // lockstep over the item (see k_bucket_reduce_quad): every quad makes every trip, ∞ beyond the item's end
+        AffinePoint p; p.x = Fq::zero(); p.y = Fq::zero(); p.inf = true;
+        uint32_t e = 0;
+        uint32_t k = s0 + (uint32_t)Q.slot;
+        if (k < s1) { e = sorted[k]; p = load_record(records, e & 0x7fffffffu); }
+#pragma unroll 1
+        for (uint32_t base = s0; base < s1; base += 8, k += 8) {
+            __syncwarp();
+            const uint32_t e_cur = e;
+            const AffinePoint p_cur = p;
+            p.inf = true;
+            if (k + 8 < s1) { e = sorted[k + 8]; p = load_record(records, e & 0x7fffffffu); }
+            acc = quad_add_affine(acc, p_cur, (e_cur >> 31) != 0u, Q);
+        }
+    }
+    acc = slot_sum(acc, Q);
+    if ((threadIdx.x & 31u) == 0u) acc.store(partial + (size_t)item * XYZZ_WORDS);
+}
+
+// Hot buckets without scans.  Some buckets are hot by construction: the top window of a 253-bit scalar has a handful of digit
+// values (c = 8: 16 buckets share all n points) or is the carry alone (c = 11: one bucket with ≈ 0.14·n points), equal scalars
+// add more.  A bucket's item partials stay at partial[item_start[b] …]; a round replaces every 32 consecutive ones by their sum at
+// the SAME base offset of the other buffer (count → ⌈count / 32⌉) while the count exceeds 32, so no offsets are recomputed and
+// each bucket knows from its own count how many rounds it took part in and which buffer holds its partials.  k_items_per_bucket
+// lists the buckets with more than 32 items; warp w works on hot bucket w / 32 and takes every 32nd group of it, quad s of the
+// warp adds entries s, s + 8, … of the group.  Rounds launched for the worst case find nothing to do and return.
+FF_DEV uint32_t fold_rounds_of(uint32_t cnt, uint32_t& final_cnt) {
+    uint32_t r = 0;
+    while (cnt > 32u) { cnt = (cnt + 31u) >> 5; r++; }
+    final_cnt = cnt;
+    return r;
+}
+__global__ void __launch_bounds__(128) k_fold_hot_quad(const uint32_t* __restrict__ in, const uint32_t* __restrict__ item_start,
+                                                       const uint32_t* __restrict__ hot, uint32_t hot_max, uint32_t round, uint32_t* __restrict__ out) {
+    uint32_t nhot = hot[0];
+    if (nhot > hot_max) nhot = hot_max;
+    const Quad Q = Quad::here();
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5, w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (uint32_t h = w0 >> 5; h < nhot; h += nwarps >> 5) {             // whole warps; nwarps is a multiple of 32
+        const uint32_t b = hot[1u + h];
+        const uint32_t i0 = item_start[b];
+        uint32_t cnt = item_start[b + 1] - i0;
+        bool live = true;
+        for (uint32_t r = 0; r < round; r++) { if (cnt <= 32u) live = false; cnt = (cnt + 31u) >> 5; }
+        if (!live || cnt <= 32u) continue;                              // this bucket finished in an earlier round
+        const uint32_t groups = (cnt + 31u) >> 5;
+        for (uint32_t g = w0 & 31u; g < groups; g += 32u) {
+            const uint32_t k = g << 5, end = k + 32u < cnt ? k + 32u : cnt;
+            XYZZ s = XYZZ::infinity();
+#pragma unroll 1
+            for (uint32_t i = k; i < end; i += 8u) {                    // lockstep: every quad makes every trip
+                __syncwarp();
+                XYZZ v = XYZZ::infinity();
+                if (i + (uint32_t)Q.slot < end) v = XYZZ::load(in + (size_t)(i0 + i + (uint32_t)Q.slot) * XYZZ_WORDS);
+                s = quad_add(s, v, Q);
+            }
+            s = slot_sum(s, Q);
+            if ((threadIdx.x & 31u) == 0u) s.store(out + (size_t)(i0 + g) * XYZZ_WORDS);
+        }
+    }
+}
+
+// out[(set·chunks + chunk)·2] = Σ_l (l + 1)·S_{8·chunk + l},  out[… + 1] = Σ_l S_{8·chunk + l}
+// The item partials of bucket b start at item_start[b] in partial_a, or, after an odd number of folds (fold_rounds_of its
+// item count), in partial_b.  `folds` = 0: no fold kernel ran (every bucket has one partial or the caller folded already).
+__global__ void __launch_bounds__(128) k_bucket_reduce_quad(const uint32_t* __restrict__ partial_a, const uint32_t* __restrict__ partial_b,
+                                                            const uint32_t* __restrict__ item_start, int folds,
+                                                            uint32_t nbuckets, uint32_t chunks, uint32_t nsets, uint32_t* __restrict__ out) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= nsets * chunks) return;                                 // whole warps only
+    const Quad Q = Quad::here();
+    const uint32_t set = warp / chunks, ch = warp % chunks, b = ch * 8u + (uint32_t)Q.slot;
+    XYZZ s = XYZZ::infinity();
+    {
+        // The eight quads walk their buckets in LOCKSTEP (trip count = the largest item count of the warp, ∞ operands beyond a
+        // quad's own count, a __syncwarp per trip): quads that leave a loop at different trips are scheduled one after the other
+        // from then on, which made each addition cost 8× (36 µs instead of 4.5, profiles/r2u_cap.log).
+        uint32_t i0 = 0, cnt = 0;
+        const uint32_t* partial = partial_a;
+        if (b < nbuckets) {
+            const uint32_t wb = set * nbuckets + b;
+            i0 = item_start[wb];
+            cnt = item_start[wb + 1] - i0;
+            if (folds) { if (fold_rounds_of(cnt, cnt) & 1u) partial = partial_b; }
+        }
+        const uint32_t trips = __reduce_max_sync(0xffffffffu, cnt);
+#pragma unroll 1
+        for (uint32_t i = 0; i < trips; i++) {
+            __syncwarp();
+            XYZZ t = XYZZ::infinity();
+            if (i < cnt) t = XYZZ::load(partial + (size_t)(i0 + i) * XYZZ_WORDS);
+            s = quad_add(s, t, Q);
+        }
+    }
+    const XYZZ run = slot_suffix_scan(s, Q);
+    const XYZZ acc = slot_sum(run, Q);
+    if ((threadIdx.x & 31u) == 0u) {
+        acc.store(out + (size_t)warp * 2 * XYZZ_WORDS);
+        run.store(out + ((size_t)warp * 2 + 1) * XYZZ_WORDS);
+    }
+}
+
+// One 8:1 fold of (acc, run) entries that span 2^lgw buckets each: acc' = Σ_s acc_s + 2^lgw·Σ_s s·run_s, run' = Σ_s run_s.
+// Called by one warp with slot s holding entry 8·group + s (∞ beyond the end); every lane returns acc', `run_out` = run'.
+FF_DEV XYZZ combine_fold_quad(const XYZZ& a, const XYZZ& r, int lgw, const Quad& Q, XYZZ& run_out) {
+    XYZZ A = slot_sum(a, Q);
+    const XYZZ suf = slot_suffix_scan(r, Q);                            // Σ_{s' ≥ s} run_s'
+    XYZZ W = slot_sum(Q.slot == 0 ? XYZZ::infinity() : suf, Q);         // Σ_{s ≥ 1} suffix_s = Σ_s s·run_s
+#pragma unroll 1
+    for (int k = 0; k < lgw; k++) W = quad_dbl(W, Q);
+    run_out = suf;                                                      // slot 0 holds the total
+    return quad_add(A, W, Q);
+}
+// one level for sets with more than 64 entries: m entries per set → ceil(m / 8), one warp per output entry
+__global__ void __launch_bounds__(128) k_combine_level_quad(const uint32_t* __restrict__ in, uint32_t m, uint32_t nsets, int lgw, uint32_t* __restrict__ out) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, groups = (m + 7u) / 8u;
+    if (warp >= nsets * groups) return;
+    const Quad Q = Quad::here();
+    const uint32_t set = warp / groups, g = warp % groups, j = g * 8u + (uint32_t)Q.slot;
+    XYZZ a = XYZZ::infinity(), r = XYZZ::infinity();
+    if (j < m) { a = load_xyzz_plain(in + ((size_t)set * m + j) * 2 * XYZZ_WORDS); r = load_xyzz_plain(in + (((size_t)set * m + j) * 2 + 1) * XYZZ_WORDS); }
+    XYZZ run;
+    const XYZZ A = combine_fold_quad(a, r, lgw, Q, run);
+    if ((threadIdx.x & 31u) == 0u) {
+        store_xyzz_plain(out + (size_t)warp * 2 * XYZZ_WORDS, A);
+        store_xyzz_plain(out + ((size_t)warp * 2 + 1) * XYZZ_WORDS, run);
+    }
+}
+// window sum of a set from its m0 ≤ 64 entries (each spanning 2^lgw0 buckets): one CTA per set, 8:1 per level through
+// shared memory
+static constexpr int COMBINE_QUAD_MAX_WARPS = 8;
+__global__ void __launch_bounds__(32 * COMBINE_QUAD_MAX_WARPS) k_window_combine_quad(const uint32_t* __restrict__ in, uint32_t m0, int lgw0, uint32_t* __restrict__ out) {
+    __shared__ __align__(16) uint32_t sm[COMBINE_QUAD_MAX_WARPS][2][XYZZ_WORDS];
+    const uint32_t set = blockIdx.x, warp = threadIdx.x >> 5;
+    const Quad Q = Quad::here();
+    const uint32_t* src = in + (size_t)set * m0 * 2 * XYZZ_WORDS;
+    uint32_t m = m0;
+    int lgw = lgw0;
+    for (;;) {                                                          // m ≤ 64 → ≤ 8 → 1
+        const uint32_t groups = (m + 7u) / 8u;
+        XYZZ A, run;
+        if (warp < groups) {
+            const uint32_t j = warp * 8u + (uint32_t)Q.slot;
+            XYZZ a = XYZZ::infinity(), r = XYZZ::infinity();
+            if (j < m) { a = load_xyzz_plain(src + (size_t)j * 2 * XYZZ_WORDS); r = load_xyzz_plain(src + ((size_t)j * 2 + 1) * XYZZ_WORDS); }
+            A = combine_fold_quad(a, r, lgw, Q, run);
+            if (groups == 1u && (threadIdx.x & 31u) == 0u) A.store(out + (size_t)set * XYZZ_WORDS);
+        }
+        if (groups == 1u) break;
+        __syncthreads();                                                // the previous level's entries have been read
+        if (warp < groups && (threadIdx.x & 31u) == 0u) { store_xyzz_plain(&sm[warp][0][0], A); store_xyzz_plain(&sm[warp][1][0], run); }
+        __syncthreads();
+        src = &sm[0][0][0];
+        m = groups; lgw += 3;
+    }
+}
+
 __global__ void k_xyzz_sum_ranks(const uint32_t* __restrict__ in, int nranks, int count, uint32_t* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -1146,7 +1347,19 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
     // item win only while the whole problem is a few CTAs — 2^10: 0.20 → 0.10 ms, 2^12 equal, 2^14 and up lose to the butterfly's
     // extra additions)
     bool acc_g8 = levels == 0 && max_entries <= 100000;
-    if (const char* e = getenv("SNARKVM_B200_MSM_WARP_PATH")) { if (atoi(e) == 0) { warp_reduce = false; acc_g8 = false; } }
+    // round 2 (quad.cuh): four lanes per point operation.  One warp per work item (k_bucket_accumulate_q8) while the whole
+    // problem is a few thousand buckets — every lane of the warp executes every multiplication, so it costs 3× the
+    // multiplier time of the one-thread kernel and only pays while the GPU is mostly idle; the item holds up to 1/16 of a
+    // bucket set, so a bucket has ≤ 17 item partials, k_bucket_reduce_quad adds them itself and the 32:1 folds are skipped.
+    int quad_path = 1;
+    if (const char* e = getenv("SNARKVM_B200_MSM_QUAD")) quad_path = atoi(e);
+    // (measured, profiles/r2s_phases_*.log: the warp-per-item kernel wins at 2^8 points — 0.10 → 0.06 ms — and loses from 2^10,
+    // 0.105 → 0.134 ms, where the 1400 items no longer fit one wave of 255-register warps)
+    bool acc_q8 = quad_path != 0 && warp_reduce && levels == 0 && (size_t)TB + max_entries / 32 <= 1100;
+    // scan-free 32:1 folds of hot buckets, skipped on the device when no bucket has more than 32 item partials
+    const bool quad_fold = quad_path != 0 && warp_reduce && levels == 0;
+    if (const char* e = getenv("SNARKVM_B200_MSM_WARP_PATH")) { if (atoi(e) == 0) { warp_reduce = false; acc_g8 = false; acc_q8 = false; } }
+    if (acc_q8) acc_g8 = false;
     uint32_t item_cap = plan.cap;                                  // points per work item of the XYZZ accumulation
     if (acc_g8) {                                                  // eight lanes per item: 8 × (4 … 16) points
         size_t per_lane = max_entries / 300000 + 1;
@@ -1155,7 +1368,19 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
         item_cap = (uint32_t)per_lane * 8u;
         if (const char* e = getenv("SNARKVM_B200_MSM_CAP")) { long v = atol(e); if (v >= 1) item_cap = (uint32_t)v; }
     }
+    if (acc_q8) {
+        size_t cap16 = ((set_cap + 15) / 16 + 7) & ~(size_t)7;
+        item_cap = (uint32_t)(cap16 < 32 ? 32 : cap16);
+    } else if (quad_fold && !acc_g8 && max_entries <= 900000) {
+        // latency-bound sizes (2^12 … 2^15 points): 4 … 8 dependent mixed additions per thread instead of 16; the extra item
+        // partials of a bucket cost the quad reduction 4 multiplication steps each (profiles/r2u_cap.log: 2^12 0.78 → 0.66 ms
+        // with 4, 2^13 0.95 → 0.85 and 2^15 1.26 → 1.19 with 8)
+        item_cap = max_entries <= 150000 ? 4 : 8;
+        if (const char* e = getenv("SNARKVM_B200_MSM_CAP")) { long v = atol(e); if (v >= 1) item_cap = (uint32_t)v; }
+    }
+    const bool small_cap = quad_fold && !acc_g8 && !acc_q8 && item_cap != plan.cap;
     const size_t max_items = (size_t)TBg + entries_g / (item_cap < plan.cap ? item_cap : plan.cap) + 1;
+    const size_t hot_max = max_items / 32 + 1;                        // buckets with more than 32 item partials
     const size_t dense_cap_a = entries_g / 2 + TBg + 1, dense_cap_b = entries_g / 4 + 2 * (size_t)TBg + 1;
 
     size_t pair_waves = 0;                       // 0 = fewest whole waves with T ≤ 1024 outputs per lane
@@ -1190,7 +1415,7 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
     // ---- one scratch block, carved up ----
     uint32_t *hist, *bucket_start, *cursors, *items, *item_start, *items2, *sorted, *partial, *partial2, *red_a, *red_b;
     uint32_t *off_a = nullptr, *off_b = nullptr, *dense_a = nullptr, *dense_b = nullptr, *prefix = nullptr, *dense_bases = nullptr, *sm_slots = nullptr;
-    uint32_t *dense0 = nullptr, *cnt_tmp = nullptr;
+    uint32_t *dense0 = nullptr, *cnt_tmp = nullptr, *hot_dev = nullptr;
     uint2* desc = nullptr;
     uint8_t* cub_tmp;
     Arena ar;
@@ -1204,9 +1429,10 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
         sorted = records ? nullptr : a.take<uint32_t>(max_entries);
         cnt_tmp = a.take<uint32_t>((size_t)TBg + 1);
         partial = a.take<uint32_t>(max_items * XYZZ_WORDS);
-        partial2 = a.take<uint32_t>(((size_t)TBg + max_items / 32 + 2) * XYZZ_WORDS);
-        red_a = a.take<uint32_t>((size_t)gw * (chunks_per_set > 2 * ((plan.nbuckets + 31u) / 32u) ? chunks_per_set : 2 * ((plan.nbuckets + 31u) / 32u)) * XYZZ_WORDS);
-        red_b = a.take<uint32_t>((size_t)gw * (chunks_per_set / tree + 1) * XYZZ_WORDS);
+        partial2 = a.take<uint32_t>((quad_fold ? max_items : (size_t)TBg + max_items / 32 + 2) * XYZZ_WORDS);      // quad folds keep the item layout
+        hot_dev = a.take<uint32_t>(hot_max + 2);
+        red_a = a.take<uint32_t>((size_t)gw * (chunks_per_set > 2 * ((plan.nbuckets + 7u) / 8u) ? chunks_per_set : 2 * ((plan.nbuckets + 7u) / 8u)) * XYZZ_WORDS);
+        red_b = a.take<uint32_t>((size_t)gw * (chunks_per_set / tree + 1 > 2 * ((plan.nbuckets + 63u) / 64u) ? chunks_per_set / tree + 1 : 2 * ((plan.nbuckets + 63u) / 64u)) * XYZZ_WORDS);
         cub_tmp = a.take<uint8_t>(cub_bytes);
         if (!flat && !records) dense_bases = a.take<uint32_t>(total_bases * (size_t)BASE_WORDS);
         if (records) dense0 = a.take<uint32_t>(entries_g * (size_t)DENSE_WORDS);
@@ -1230,6 +1456,7 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
 
     CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)(TB + 1) * 4, stream));
     if (sm_slots) CUDA_TRY(cudaMemsetAsync(sm_slots, 0, 256 * 4, stream));
+    if (quad_fold) CUDA_TRY(cudaMemsetAsync(hot_dev, 0, 4, stream));
     {
         // ---- bucket sort of all jobs and windows: histogram → offsets → scatter ----
         {
@@ -1281,19 +1508,22 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
             const uint32_t* final_partial = nullptr;
             const uint32_t* final_start = nullptr;
             if (levels == 0) {
-                const uint32_t cap = acc_g8 ? item_cap : plan.cap;
-                k_items_per_bucket<<<(tb + 256) / 256, 256, 0, stream>>>(hist + (size_t)w0 * plan.nbuckets, items, tb, cap);
+                const uint32_t cap = (acc_g8 || acc_q8 || small_cap) ? item_cap : plan.cap;
+                k_items_per_bucket<<<(tb + 256) / 256, 256, 0, stream>>>(hist + (size_t)w0 * plan.nbuckets, items, tb, cap, quad_fold ? hot_dev : nullptr, (uint32_t)hot_max);
                 CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(tb + 1), stream));
                 count_launch(2);
                 const size_t group_items = (size_t)tb + entries / cap + 1;
                 items_bound = set_cap / cap + 1;
                 items_launched = group_items;
                 ProfScope acc_scope(PROF_MSM_ACCUMULATE, stream);
-                if (acc_g8)
+                if (acc_q8) {
+                    k_bucket_accumulate_q8<<<(unsigned)((group_items * 32 + 127) / 128), 128, 0, stream>>>(gather_src, sorted, bs, item_start, tb, cap, partial);
+                    items_bound = 1;                           // ≤ 17 partials per bucket: summed by k_bucket_reduce_quad, no folds
+                } else if (acc_g8)
                     k_bucket_accumulate_g8<<<(unsigned)((group_items * ACC_G + 127) / 128), 128, 0, stream>>>(gather_src, sorted, bs, item_start, tb, cap, partial);
                 else
                     k_bucket_accumulate<<<(unsigned)((group_items + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
-                        gather_src, sorted, bs, item_start, tb, plan.cap, partial);
+                        gather_src, sorted, bs, item_start, tb, cap, partial);
                 count_launch();
             } else {
                 if (records) {
@@ -1381,7 +1611,21 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
                 count_launch(3);
             }
             ProfScope red_scope(PROF_MSM_REDUCE, stream);
-            {
+            int quad_rounds = 0;
+            if (quad_fold) {
+                // the quad reduction adds up to 32 partials per bucket itself; buckets with more are folded 32:1 per round from the
+                // device's hot list, as many rounds as the worst case needs
+                size_t worst = acc_q8 ? 1 : items_bound;
+                const uint32_t* p_in = partial; uint32_t* p_out = partial2;
+                while (worst > 32) {
+                    k_fold_hot_quad<<<(unsigned)sm_count * 8, 128, 0, stream>>>(p_in, item_start, hot_dev, (uint32_t)hot_max, (uint32_t)quad_rounds, p_out);
+                    count_launch();
+                    worst = (worst + 31) / 32;
+                    quad_rounds++;
+                    const uint32_t* t1 = p_in; p_in = p_out; p_out = (uint32_t*)t1;
+                }
+                final_partial = partial; final_start = item_start;
+            } else {
                 // fold item partials 32:1 until no bucket can hold more than one (worst case: all entries in one bucket).
                 // `worst` (≥ the item count of any single bucket) only decides when to stop; the launch covers
                 // Σ_b ceil(items_b / 32) ≤ #buckets + total/32 outputs, where `total_bound` bounds the items of ALL buckets
@@ -1404,6 +1648,23 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
                 final_partial = p_in; final_start = st_in;
             }
             uint32_t* group_sums = d_window_sums + (size_t)w0 * XYZZ_WORDS;
+            if (warp_reduce && quad_path != 0) {
+                const uint32_t qchunks = (plan.nbuckets + 7u) / 8u;                     // ≤ 128
+                k_bucket_reduce_quad<<<(wn * qchunks * 32u + 127u) / 128u, 128, 0, stream>>>(final_partial, quad_fold ? partial2 : final_partial, final_start,
+                                                                                              quad_rounds, plan.nbuckets, qchunks, wn, red_a);
+                const uint32_t* ent = red_a;
+                uint32_t m = qchunks;
+                int lgw = 3;
+                if (m > 64u) {                                                          // c = 11: 128 entries → 16
+                    const uint32_t groups = (m + 7u) / 8u;
+                    k_combine_level_quad<<<(wn * groups * 32u + 127u) / 128u, 128, 0, stream>>>(ent, m, wn, lgw, red_b);
+                    count_launch();
+                    ent = red_b; m = groups; lgw += 3;
+                }
+                k_window_combine_quad<<<wn, 32u * ((m + 7u) / 8u), 0, stream>>>(ent, m, lgw, group_sums);
+                count_launch(2);
+                continue;
+            }
             if (warp_reduce) {
                 const uint32_t wchunks = (plan.nbuckets + 31u) / 32u;
                 k_bucket_reduce_warp<<<(wn * wchunks * 32u + 127u) / 128u, 128, 0, stream>>>(final_partial, final_start, plan.nbuckets, wchunks, wn, red_a);
@@ -1464,7 +1725,7 @@ int msm_sort_indices(const MsmPlan& plan, const void* d_scalars, size_t n, int m
     return (int)cudaGetLastError();
 }
 int msm_items_per_bucket(const uint32_t* hist, uint32_t* items, uint32_t total_buckets, uint32_t cap, cudaStream_t stream) {
-    k_items_per_bucket<<<(total_buckets + 256) / 256, 256, 0, stream>>>(hist, items, total_buckets, cap);
+    k_items_per_bucket<<<(total_buckets + 256) / 256, 256, 0, stream>>>(hist, items, total_buckets, cap, nullptr, 0u);
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -622,3 +622,29 @@ def test_warp_cooperative_field_arithmetic_selftest():
     with torch.cuda.device(0):
         _lib.check(_lib.lib().snarkvm_b200_selftest_coop(20000, 0xC0FFEE, ctypes.byref(bad), torch.cuda.current_stream().cuda_stream))
     assert bad.value == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [64, 1000, 4096, 1 << 13, 1 << 15])
+def test_msm_quad_latency_path_edge_cases(oracle_cpu, bases64k, n):
+    """the four-lanes-per-point tail (csrc/quad.cuh: k_bucket_accumulate_q8 up to 2^12 points, k_bucket_reduce_quad /
+    k_window_combine_quad up to 1024 buckets per window) on the inputs that reach its special cases: every scalar equal (one
+    bucket per window holds all points: 17 item partials per bucket, no folds), one point repeated with one scalar (doubling
+    inside quad_add_affine and quad_add), P and −P with one scalar (cancellation), ∞ points and zero scalars (∞ operands)."""
+    from snarkvm_b200.algorithms import VariableBase
+    scal = random_canonical_fr(n, seed=100 + n)
+    same = np.tile(scal[:1], (n, 1))
+    assert (VariableBase.msm(bases64k[:n], same) == oracle_cpu.msm(bases64k[:n], same, 1)).all()
+    rep = np.tile(bases64k[7:8], (n, 1))
+    assert (VariableBase.msm(rep, same) == oracle_cpu.msm(rep, same, 1)).all()                 # n copies of (P, s)
+    assert (VariableBase.msm(rep, scal) == oracle_cpu.msm(rep, scal, 1)).all()                 # one point, random scalars
+    mixed = bases64k[:n].copy(); ms = scal.copy()
+    half = n // 2
+    neg = affine_array([py.g1_neg(py.affine_from_bytes(bases64k[i].tobytes())) for i in range(min(half, 32))])
+    mixed[half:half + len(neg)] = neg; ms[half:half + len(neg)] = ms[:len(neg)]               # P_i and −P_i, equal scalars
+    mixed[1::5, 96] = 1                                                                         # ∞ points
+    ms[2::7] = 0
+    ms[3::11] = ms[3]                                                                           # a hot bucket over a background
+    got = VariableBase.msm(mixed, ms)
+    assert (got == oracle_cpu.msm(mixed, ms, 0)).all()
+    assert (got == oracle_cpu.msm(mixed, ms, 1)).all()
