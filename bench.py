@@ -597,6 +597,30 @@ def run_product(args, rank, world, local_rank):
                    "checked": True, "workload": f"2^{args.g2_lg}-point VariableBase::msm over Affine<G2> (Fq2 coordinates, 200-byte images), resident"}
         del g2b, g2sd
 
+    # ---- the same MSM at the sizes a prover calls it with (Varuna commits 2^12 … 2^21 coefficients): resident inputs, whole call
+    #      (sort, accumulate, quad-lane reduction tail, D2H of the window sums, host Horner), each checked by the closed form ----
+    sizes_line = None
+    if world == 1 and not args.skip_sizes:
+        sizes_line = {}
+        for lg_s in (12, 14, 16, 18, 20, 22):
+            if lg_s >= args.lg:
+                continue
+            ns = 1 << lg_s
+            bs, ss = bases[:ns], scalars[:ns]
+            got_s = device.msm(bs, ss)
+            ok_s = bool((got_s == chk.point(chk.dot(scal_np[:ns], seed))).all())
+            checks[f"msm_2^{lg_s}"] = ok_s
+            assert ok_s, f"2^{lg_s}-point MSM differs from the closed form"
+            reps_s = 20 if lg_s <= 18 else 5
+            for _ in range(3):
+                device.msm(bs, ss)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps_s):
+                device.msm(bs, ss)
+            ms_s = (time.perf_counter() - t0) / reps_s * 1e3
+            sizes_line[f"2^{lg_s}"] = {"ms_per_msm": ms_s, "points_per_s": ns / (ms_s * 1e-3)}
+
     if rank != 0:
         return
 
@@ -650,6 +674,7 @@ def run_product(args, rank, world, local_rank):
         "kzg_commit": kzg,
         "varuna": varuna_line,
         "g2_msm": g2_line,
+        "msm_sizes": sizes_line,
     }
     print(json.dumps(line), flush=True)
 
@@ -673,6 +698,7 @@ def main():
     ap.add_argument("--g2-lg", type=int, default=16, help="log2 points of the G2 MSM extra (0 = skip)")
     ap.add_argument("--g1-ntt-lg", type=int, default=16, help="size of the G1 iFFT (lagrange_basis) timed inside the KZG extra")
     ap.add_argument("--skip-kzg", action="store_true")
+    ap.add_argument("--skip-sizes", action="store_true")
     ap.add_argument("--skip-ntt", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-strong", action="store_true")

@@ -161,6 +161,16 @@ SNARKVM_API int snarkvm_b200_kzg_commit_batch_hiding_device(void* out144s, const
 SNARKVM_API int snarkvm_b200_kzg_commit_batch_precomputed_device(void* out144s, const void* handle, const void* const* d_coeffs_mont,
                                                                  const size_t* ncoeffs, size_t count, void* stream);
 
+/* SonicKZG10::commit for all polynomials of a round (polycommit/sonic_pc/mod.rs:177-257) in one pass: polynomial i is committed
+ * against d_bases[i] — the powers (ck.powers()), the powers advanced by max_degree - degree_bound points
+ * (ck.shifted_powers_of_beta_g(degree_bound), sonic_pc/data_structures.rs:310-331) or a Lagrange basis (mod.rs:215-227) — plus, when
+ * nblinding[i] > 0, sum_j blinding_i[j] * d_gamma_bases[i][j] (hiding_bound = Some(_), kzg10/mod.rs:129-150).  Base slices may
+ * overlap (they are merged); all arrays share `stride`.  d_gamma_bases / d_blinding_mont / nblinding may be NULL (no hiding). */
+SNARKVM_API int snarkvm_b200_sonic_commit_batch_device(void* out144s, size_t stride, const void* const* d_bases,
+                                                       const void* const* d_coeffs_mont, const size_t* ncoeffs,
+                                                       const void* const* d_gamma_bases, const void* const* d_blinding_mont,
+                                                       const size_t* nblinding, size_t count, void* stream);
+
 /* MSM scratch budget of the current device (bytes): the limit concurrent calls share (half the device unless
  * SNARKVM_B200_SCRATCH_LIMIT_GB is set; callers that do not fit wait instead of failing), what is in flight, and the high-water mark. */
 SNARKVM_API int snarkvm_b200_msm_scratch_stats(size_t* limit_bytes, size_t* in_use_bytes, size_t* peak_bytes);
@@ -239,6 +249,9 @@ SNARKVM_API int snarkvm_b200_msm_g2_device(void* out288, const void* d_points, s
 SNARKVM_API int snarkvm_b200_generate_bases_g2_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, void* stream);
 
 SNARKVM_API int snarkvm_b200_generate_bases_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, void* stream);
+/* P_i = s_i * G for npoints canonical scalars (32 B each) in HBM, written in the reference Affine layout: s_i = beta^i gives the
+ * powers_of_beta_g of a universal setup with a KNOWN trapdoor (kzg10/data_structures.rs UniversalParams) for tests and benches. */
+SNARKVM_API int snarkvm_b200_generator_mul_device(void* d_points, size_t stride, const void* d_scalars, size_t npoints, void* stream);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,7 @@
 // cudaError_t code; leave outputs untouched on failure so the Rust caller can fall back.
 #include "../../include/snarkvm_b200.h"
 
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdlib>
@@ -935,6 +936,77 @@ int snarkvm_b200_kzg_commit_batch_hiding_device(void* out144s, const void* d_pow
     return msm_batch_impl(out144s, d_powers, stride, d_coeffs_mont, ncoeffs, count, 1, d_gamma_powers, d_blinding_mont, nblinding, (cudaStream_t)stream);
 }
 
+// SonicKZG10::commit for all polynomials of a round (sonic_pc/mod.rs:177-257) in ONE msm_core pass.  Polynomial i is committed
+// against the base array the reference would pick for it — ck.powers() (d_bases[i] = the powers), ck.shifted_powers_of_beta_g(bound)
+// (the powers advanced by max_degree − bound points, mod.rs:229-233, data_structures.rs:310-331) or a Lagrange basis
+// (mod.rs:215-227) — plus, when hiding, Σ_j blinding_i[j]·gamma_i[j] (kzg10/mod.rs:129-150).  The slices may overlap (shifted powers
+// are suffixes of one SRS): they are merged into disjoint arrays and every scalar vector becomes a segment with its offset.
+int snarkvm_b200_sonic_commit_batch_device(void* out144s, size_t stride, const void* const* d_bases, const void* const* d_coeffs_mont,
+                                           const size_t* ncoeffs, const void* const* d_gamma_bases, const void* const* d_blinding_mont,
+                                           const size_t* nblinding, size_t count, void* stream_v) {
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (count == 0) return 0;
+    if (!out144s || !d_bases || !d_coeffs_mont || !ncoeffs || stride < 104 || (stride & 7)) return (int)cudaErrorInvalidValue;
+    struct Use { const uint8_t* p; size_t n; const void* scal; uint32_t job; };
+    std::vector<Use> uses;
+    std::vector<size_t> job_of(count, (size_t)-1), job_n;
+    uint32_t njobs = 0;
+    size_t total_n = 0;
+    for (size_t i = 0; i < count; i++) {
+        const size_t n1 = ncoeffs[i], n2 = (d_blinding_mont && nblinding) ? nblinding[i] : 0;
+        if (n1 == 0 && n2 == 0) { write_infinity((uint8_t*)out144s + i * 144); continue; }
+        if ((n1 && (!d_bases[i] || !d_coeffs_mont[i])) || (n2 && (!d_gamma_bases || !d_gamma_bases[i] || !d_blinding_mont[i]))) return (int)cudaErrorInvalidValue;
+        job_of[i] = njobs;
+        if (n1) uses.push_back(Use{(const uint8_t*)d_bases[i], n1, d_coeffs_mont[i], njobs});
+        if (n2) uses.push_back(Use{(const uint8_t*)d_gamma_bases[i], n2, d_blinding_mont[i], njobs});
+        job_n.push_back(n1 + n2);
+        total_n += n1 + n2;
+        njobs++;
+    }
+    if (njobs == 0) return 0;
+    // merge the base slices into disjoint arrays: sort by address, join a slice that starts inside (or right at the end of) the
+    // running array on the same stride grid
+    std::vector<size_t> order(uses.size());
+    for (size_t k = 0; k < order.size(); k++) order[k] = k;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return uses[a].p < uses[b].p; });
+    std::vector<MsmBases> arrays;
+    std::vector<size_t> array_first;                       // index of the array's first point in the concatenation
+    std::vector<uint32_t> base0(uses.size(), 0);
+    size_t concat = 0;
+    for (size_t k : order) {
+        const Use& u = uses[k];
+        bool joined = false;
+        if (!arrays.empty()) {
+            MsmBases& a = arrays.back();
+            const uint8_t* a0 = (const uint8_t*)a.d_points;
+            const size_t off = (size_t)(u.p - a0);
+            if (off <= a.n * stride && off % stride == 0) {
+                const size_t first = off / stride;
+                if (first + u.n > a.n) { concat += first + u.n - a.n; a.n = first + u.n; }
+                base0[k] = (uint32_t)(array_first.back() + first);
+                joined = true;
+            } else if (off < a.n * stride) return (int)cudaErrorInvalidValue;      // overlapping arrays on different grids
+        }
+        if (!joined) {
+            array_first.push_back(concat);
+            arrays.push_back(MsmBases{u.p, stride, u.n});
+            base0[k] = (uint32_t)concat;
+            concat += u.n;
+        }
+        if (concat >= (1ull << 31)) return (int)cudaErrorInvalidValue;
+    }
+    std::vector<MsmSegment> segs;
+    for (size_t k = 0; k < uses.size(); k++) segs.push_back(MsmSegment{uses[k].scal, uses[k].n, base0[k], uses[k].job, 1});
+    size_t job_max = 1;
+    for (size_t v : job_n) if (v > job_max) job_max = v;
+    MsmPlan plan = msm_make_plan_batch(job_max, total_n);
+    std::vector<uint8_t> outs((size_t)njobs * 144);
+    int rc = msm_jobs_impl(outs.data(), plan, arrays.data(), (int)arrays.size(), nullptr, 0, segs.data(), (int)segs.size(), (int)njobs, stream);
+    if (rc != 0) return rc;
+    for (size_t i = 0; i < count; i++) if (job_of[i] != (size_t)-1) memcpy((uint8_t*)out144s + i * 144, outs.data() + job_of[i] * 144, 144);
+    return 0;
+}
+
 // VariableBase::msm for G2 (Affine<G2> images: x.c0 x.c1 y.c0 y.c1 infinity, stride ≥ 200; canonical scalars) — the curves the
 // reference routes to standard::msm (msm/variable_base/mod.rs:44-47).  out288: HOST memory, the normalised projective image
 // (x, y, 1) or (0, 1, 0) over Fq2.
@@ -1098,6 +1170,12 @@ int snarkvm_b200_profile_collect(int kind, double* total_ms, uint64_t* count) { 
 
 int snarkvm_b200_generate_bases_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, void* stream) {
     return msm_generate_bases_device(d_points, npoints, stride, seed, (cudaStream_t)stream);
+}
+
+// P_i = s_i·G for n canonical scalars (32 B each) in HBM → the reference Affine layout; test/bench set-up of an SRS with a known trapdoor
+int snarkvm_b200_generator_mul_device(void* d_points, size_t stride, const void* d_scalars, size_t npoints, void* stream) {
+    if (npoints && (!d_points || !d_scalars)) return (int)cudaErrorInvalidValue;
+    return msm_generator_mul_device(d_points, npoints, stride, d_scalars, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1927,6 +1927,41 @@ int selftest_coop_device(uint32_t nwarps, uint64_t seed, uint32_t* d_mismatches,
     return (int)cudaGetLastError();
 }
 
+// P_i = s_i·G for canonical 253-bit scalars s_i in HBM (a universal setup with a KNOWN trapdoor for tests and benches:
+// s_i = β^i gives powers_of_beta_g, s_i = γβ^i powers_of_beta_times_gamma_g; kzg10/data_structures.rs UniversalParams)
+__global__ void __launch_bounds__(128) k_generator_mul(uint8_t* points, size_t n, size_t stride, const uint32_t* __restrict__ scalars) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = scalars[8 * i + j];
+    AffinePoint g;
+#pragma unroll
+    for (int j = 0; j < 12; j++) { g.x.v[j] = G1_GEN_X[j]; g.y.v[j] = G1_GEN_Y[j]; }
+    g.inf = false;
+    XYZZ acc = XYZZ::infinity();
+    bool started = false;
+#pragma unroll 1
+    for (int w = 7; w >= 0; w--) {
+        uint32_t kw = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (j == w) kw = k[j];
+#pragma unroll 1
+        for (int b = 31; b >= 0; b--) {
+            if (started) acc.dbl();
+            if ((kw >> b) & 1u) { acc.add_affine(g, false); started = true; }
+        }
+    }
+    store_affine(points, stride, i, acc.to_affine());
+}
+int msm_generator_mul_device(void* d_points, size_t npoints, size_t stride, const void* d_scalars, cudaStream_t stream) {
+    if (stride < 104 || (stride & 7)) return (int)cudaErrorInvalidValue;
+    if (npoints == 0) return 0;
+    k_generator_mul<<<(unsigned)((npoints + 127) / 128), 128, 0, stream>>>((uint8_t*)d_points, npoints, stride, (const uint32_t*)d_scalars);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 int msm_generate_bases_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, cudaStream_t stream) {
     if (stride < 104 || (stride & 7)) return (int)cudaErrorInvalidValue;
     if (npoints == 0) return 0;

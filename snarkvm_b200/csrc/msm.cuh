@@ -86,6 +86,7 @@ int msm_generate_bases_g2_device(void* d_points, size_t npoints, size_t stride, 
 // (every point is in the prime-order subgroup because G is).  Writes the reference
 // affine layout with the given stride.
 int msm_generate_bases_device(void* d_points, size_t npoints, size_t stride, uint64_t seed, cudaStream_t stream);
+int msm_generator_mul_device(void* d_points, size_t npoints, size_t stride, const void* d_scalars, cudaStream_t stream);
 
 // `.usrs` uncompressed points (96 B canonical each) → reference Affine images in HBM; *d_invalid counts points that are
 // off the curve, out of range or badly flagged.

@@ -247,6 +247,66 @@ def kzg_commit_batch(powers: torch.Tensor, polys_mont: list, stride: int = AFFIN
     return out
 
 
+def generator_mul(scalars: torch.Tensor, stride: int = AFFINE_STRIDE) -> torch.Tensor:
+    """P_i = s_i·G for canonical scalars [n, 4] in HBM → affine points [n, stride] (set-up helper, not a hot path)"""
+    n = _nbytes(scalars) // 32
+    out = torch.empty((n, stride), dtype=torch.uint8, device=scalars.device)
+    with torch.cuda.device(scalars.device):
+        _lib.check(_lib.lib().snarkvm_b200_generator_mul_device(out.data_ptr(), stride, _check(scalars, "scalars") if n else None, n, _stream()))
+    return out
+
+
+def generate_powers(n: int, beta: int, scale: int = 1, device="cuda", stride: int = AFFINE_STRIDE) -> torch.Tensor:
+    """scale·β^i·G for i < n: powers_of_beta_g (scale = 1) or powers_of_beta_times_gamma_g (scale = γ) of a universal setup whose
+    trapdoor the caller knows.  The scalars are built by doubling (v[m:2m] = β^m·v[0:m]), then one fixed-base pass."""
+    from .algorithms import _fr_int_to_mont, _R_MOD
+    s = torch.zeros((n, 4), dtype=torch.int64, device=device)
+    if n == 0:
+        return torch.empty((0, stride), dtype=torch.uint8, device=device)
+    s[0] = torch.from_numpy(_fr_int_to_mont(scale % _R_MOD).view(np.int64)).to(s.device)
+    m = 1
+    while m < n:
+        k = min(m, n - m)
+        fr_vec_op(s[:k], _fr_int_to_mont(pow(beta, m, _R_MOD)), FR_MUL, out=s[m:m + k])
+        m *= 2
+    return generator_mul(fr_from_mont(s), stride)
+
+
+def sonic_commit_batch(bases: list, polys_mont: list, gamma_bases: list | None = None, blindings_mont: list | None = None,
+                       stride: int = AFFINE_STRIDE) -> np.ndarray:
+    """SonicKZG10::commit of a round in ONE pass (sonic_pc/mod.rs:177-257) → [count, 18] u64.  `bases[i]` is the CUDA tensor (or a
+    row slice of one: shifted powers are suffixes of the SRS) polynomial i is committed against; `gamma_bases[i]` / `blindings_mont[i]`
+    (or None) its hiding terms (kzg10/mod.rs:129-150)."""
+    count = len(polys_mont)
+    out = np.zeros((count, 18), dtype=np.uint64)
+    if count == 0:
+        return out
+    if len(bases) != count:
+        raise ValueError("one base array per polynomial")
+    lens = [_nbytes(p) // 32 for p in polys_mont]
+    for b, n in zip(bases, lens):
+        if n > _nbytes(b) // stride:
+            raise ValueError("polynomial degree exceeds the number of powers")             # check_degree_is_too_large, kzg10/mod.rs:105
+    bptr = (ctypes.c_void_p * count)(*[(_check(b, "bases") if n else None) for b, n in zip(bases, lens)])
+    cptr = (ctypes.c_void_p * count)(*[(_check(p, "poly") if n else None) for p, n in zip(polys_mont, lens)])
+    szs = (ctypes.c_size_t * count)(*lens)
+    gptr = rptr = rszs = None
+    if blindings_mont is not None:
+        if gamma_bases is None or len(blindings_mont) != count or len(gamma_bases) != count:
+            raise ValueError("one (gamma powers, blinding polynomial) pair (or None) per polynomial")
+        blens = [0 if r is None else _nbytes(r) // 32 for r in blindings_mont]
+        for g, n in zip(gamma_bases, blens):
+            if n and (g is None or n > _nbytes(g) // stride):
+                raise ValueError("hiding bound exceeds powers_of_beta_times_gamma_g")      # check_hiding_bound, kzg10/mod.rs:134-137
+        gptr = (ctypes.c_void_p * count)(*[(_check(g, "gamma") if n else None) for g, n in zip(gamma_bases, blens)])
+        rptr = (ctypes.c_void_p * count)(*[(_check(r, "blinding") if n else None) for r, n in zip(blindings_mont, blens)])
+        rszs = (ctypes.c_size_t * count)(*blens)
+    dev = next(b.device for b in bases if b is not None)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().snarkvm_b200_sonic_commit_batch_device(out.ctypes.data, stride, bptr, cptr, szs, gptr, rptr, rszs, count, _stream()))
+    return out
+
+
 def g1_ntt(points: torch.Tensor, inverse: bool, stride: int = AFFINE_STRIDE) -> torch.Tensor:
     """FFT / iFFT over 2^k G1 points (EvaluationDomain with T = G1Projective, fft/domain.rs:169-221) → affine points, same stride."""
     n = _nbytes(points) // stride
