@@ -368,8 +368,89 @@ class Prover:
                 h_i, xg_i = apply_randomized_selector(z_m, combiner, V, V, True)
                 h_1, xg_1 = poly_add(h_1, h_i), poly_add(xg_1, xg_i)
             sums.append(inst_sums)
+        if self.mask_poly is not None:                                  # third.rs:207-213 (hiding mode)
+            h_mask, xg_mask = divide_by_vanishing_poly(self.mask_poly, V)
+            h_1, xg_1 = poly_add(h_1, h_mask), poly_add(xg_1, xg_mask)
         self.h_1, self.g_1, self.third_sums = h_1, trim(xg_1[1:]), sums
         return self.g_1, self.h_1
+
+    # ---- AHPForR1CS::construct_linear_combinations (ahp/ahp.rs:172-389) + verifier_query_set, one circuit ----
+    def polynomials(self):
+        """label → coefficients of every polynomial prove_batch hands to open_combinations (varuna.rs:509-517)"""
+        out = {f"w_{j}": w for j, w in enumerate(self.w_polys)}
+        if self.mask_poly is not None:
+            out["mask_poly"] = trim(self.mask_poly)
+        out.update({"h_0": self.h_0, "g_1": self.g_1, "h_1": self.h_1, "h_2": self.h_2})
+        for m, g, a, b in zip("abc", self.gs, self.a_polys, self.b_polys):
+            out[f"g_{m}"], out[f"a_poly_{m}"], out[f"b_poly_{m}"] = g, a, b
+        return out
+
+    def linear_combinations(self, alpha, eta_b, eta_c, beta, deltas, gamma, circuit_combiner=1, instance_combiners=None):
+        """→ (lcs, query_set): lcs = [(label, [(coefficient, polynomial label or None for LCTerm::One)])] in the reference's BTreeMap
+        order, query_set = [(lc label, (point name, point))].  The three checks evaluate to ZERO at their points (the reference's
+        debug_asserts, ahp.rs:258, 340, 384) — tests/test_varuna_golden.py verifies exactly that."""
+        c = self.circuit
+        Rd, V, I = c.constraint_domain, c.variable_domain, c.input_domain
+        K = c.max_non_zero_domain
+        polys = self.polynomials()
+        instance_combiners = instance_combiners or [1] * self.batch
+        lcs = {}
+        # rowcheck_zerocheck at α (ahp.rs:230-256); the selector of the circuit's own (= max) constraint domain is 1
+        const = 0
+        for comb, sums in zip(instance_combiners, self.third_sums):
+            const = (const + comb * (sums[0] * sums[1] - sums[2])) % R
+        lcs["rowcheck_zerocheck"] = [(circuit_combiner * const % R, None), ((-Rd.evaluate_vanishing_polynomial(alpha)) % R, "h_0")]
+        # g_1 and lineval_sumcheck at β (ahp.rs:262-343)
+        lcs["g_1"] = [(1, "g_1")]
+        v_c_beta, v_x_beta = V.evaluate_vanishing_polynomial(beta), I.evaluate_vanishing_polynomial(beta)
+        g_1_at_beta = poly_eval(self.g_1, beta)
+        sums4 = [s * d.size % R for s, d in zip(self.fourth_sums, c.non_zero_domains)]
+        weight = (sums4[0] + sums4[1] * eta_b + sums4[2] * eta_c) % R
+        lineval = [(1, "mask_poly")] if self.mask_poly is not None else []
+        for j, comb in enumerate(instance_combiners):
+            x_at_beta = poly_eval(self.x_polys[j], beta)
+            k = circuit_combiner * comb % R
+            lineval.append((k * weight % R * x_at_beta % R, None))
+            lineval.append((k * weight % R * v_x_beta % R, f"w_{j}"))
+        batch_lineval_sum = circuit_combiner * sum(comb * (s[0] + eta_b * s[1] + eta_c * s[2]) for comb, s in zip(instance_combiners, self.third_sums)) % R * V.size_inv % R
+        lineval += [((-v_c_beta) % R, "h_1"), ((-beta * g_1_at_beta) % R, None), ((-batch_lineval_sum) % R, None)]
+        lcs["lineval_sumcheck"] = lineval
+        # g_a, g_b, g_c and matrix_sumcheck at γ (ahp.rs:345-386)
+        v_k_gamma = K.evaluate_vanishing_polynomial(gamma)
+        matrix = []
+        for m, g, s, delta, dom in zip("abc", self.gs, self.fourth_sums, deltas, c.non_zero_domains):
+            lcs[f"g_{m}"] = [(1, f"g_{m}")]
+            selector = v_k_gamma * dom.size % R * pow(dom.evaluate_vanishing_polynomial(gamma) * K.size % R, -1, R) % R
+            b_term = (gamma * poly_eval(g, gamma) + s) % R
+            matrix.append((delta * selector % R, f"a_poly_{m}"))
+            matrix.append(((-delta * selector % R * b_term) % R, f"b_poly_{m}"))
+        matrix.append(((-v_k_gamma) % R, "h_2"))
+        lcs["matrix_sumcheck"] = matrix
+        points = {"rowcheck_zerocheck": ("alpha", alpha), "g_1": ("beta", beta), "lineval_sumcheck": ("beta", beta),
+                  "g_a": ("gamma", gamma), "g_b": ("gamma", gamma), "g_c": ("gamma", gamma), "matrix_sumcheck": ("gamma", gamma)}
+        order = sorted(lcs)
+        return [(k, lcs[k]) for k in order], [(k, points[k]) for k in order]
+
+    def evaluate_lc(self, terms, point):
+        polys = self.polynomials()
+        return sum(coeff * (1 if label is None else poly_eval(polys[label], point)) for coeff, label in terms) % R
+
+    mask_poly = None
+
+    def set_mask_poly(self, h_1_mask_rand, g_1_mask_rand):
+        """calculate_mask_poly (first.rs:102-127): h_1_mask = rand(degree 3)·v_H on the (max) variable domain, g_1_mask = rand(degree 5)
+        with its constant coefficient zeroed; the two random polynomials are arguments (DensePolynomial::rand draws them)."""
+        assert len(h_1_mask_rand) == 4 and len(g_1_mask_rand) == 6
+        n = self.circuit.variable_domain.size
+        mask = [0] * (n + 4)
+        for i, c in enumerate(h_1_mask_rand):
+            mask[n + i] = (mask[n + i] + c) % R
+            mask[i] = (mask[i] - c) % R
+        for i, c in enumerate(g_1_mask_rand):
+            if i:
+                mask[i] = (mask[i] + c) % R
+        self.mask_poly = mask
+        return mask
 
     # ---- round 4 (fourth.rs:151-245) ----
     def fourth_round(self, alpha, beta):

@@ -277,8 +277,90 @@ class Prover:
                 h_i, xg_i = apply_randomized_selector(z_m, combiner, V, V, True)
                 h_1, xg_1 = _add(h_1, h_i), _add(xg_1, xg_i)
             sums.append(inst_sums)
+        if self.mask_poly is not None:                                  # third.rs:207-213 (hiding mode)
+            h_mask, xg_mask = divide_by_vanishing(self.mask_poly, V)
+            h_1, xg_1 = _add(h_1, h_mask), _add(xg_1, xg_mask)
         self.h_1, self.g_1, self.third_sums = h_1, xg_1[1:].contiguous(), sums
         return self.g_1, self.h_1
+
+    # ---- AHPForR1CS::construct_linear_combinations (ahp/ahp.rs:172-389) + verifier_query_set, one circuit ----
+    def polynomials(self) -> dict:
+        """label → device polynomial, everything prove_batch hands to open_combinations (varuna.rs:509-517)"""
+        out = {f"w_{j}": w for j, w in enumerate(self.w_polys)}
+        if self.mask_poly is not None:
+            out["mask_poly"] = self.mask_poly
+        out.update({"h_0": self.h_0, "g_1": self.g_1, "h_1": self.h_1, "h_2": self.h_2})
+        for m, g, a, b in zip("abc", self.gs, self.a_polys, self.b_polys):
+            out[f"g_{m}"], out[f"a_poly_{m}"], out[f"b_poly_{m}"] = g, a, b
+        return out
+
+    @staticmethod
+    def _eval(poly: torch.Tensor, point: int) -> int:
+        return _fr_mont_to_int(device.poly_evaluate(poly.contiguous(), _mont(point))) if poly.shape[0] else 0
+
+    def linear_combinations(self, alpha, eta_b, eta_c, beta, deltas, gamma, circuit_combiner: int = 1, instance_combiners=None):
+        """→ (lcs, query_set) exactly as oracle/varuna.py Prover.linear_combinations: the coefficients are host integers (a few dozen
+        field operations), the three evaluations they need — g_1(β), g_M(γ), x_j(β) — are device Horner passes."""
+        c = self.circuit
+        Rd, V, I, K = c.constraint_domain, c.variable_domain, c.input_domain, c.max_non_zero_domain
+        vanish = lambda d, x: (pow(x, d.size, R_MOD) - 1) % R_MOD       # noqa: E731
+        instance_combiners = instance_combiners or [1] * self.batch
+        lcs = {}
+        const = 0
+        for comb, sums in zip(instance_combiners, self.third_sums):
+            const = (const + comb * (sums[0] * sums[1] - sums[2])) % R_MOD
+        lcs["rowcheck_zerocheck"] = [(circuit_combiner * const % R_MOD, None), ((-vanish(Rd, alpha)) % R_MOD, "h_0")]
+        lcs["g_1"] = [(1, "g_1")]
+        v_c_beta, v_x_beta = vanish(V, beta), vanish(I, beta)
+        g_1_at_beta = self._eval(self.g_1, beta)
+        doms = [a.domain for a in c.ariths]
+        sums4 = [s * d.size % R_MOD for s, d in zip(self.fourth_sums, doms)]
+        weight = (sums4[0] + sums4[1] * eta_b + sums4[2] * eta_c) % R_MOD
+        lineval = [(1, "mask_poly")] if self.mask_poly is not None else []
+        for j, comb in enumerate(instance_combiners):
+            x_at_beta = self._eval(self.x_polys[j], beta)
+            k = circuit_combiner * comb % R_MOD
+            lineval.append((k * weight % R_MOD * x_at_beta % R_MOD, None))
+            lineval.append((k * weight % R_MOD * v_x_beta % R_MOD, f"w_{j}"))
+        batch_lineval_sum = circuit_combiner * sum(comb * (s[0] + eta_b * s[1] + eta_c * s[2]) for comb, s in zip(instance_combiners, self.third_sums)) % R_MOD \
+            * pow(V.size, -1, R_MOD) % R_MOD
+        lineval += [((-v_c_beta) % R_MOD, "h_1"), ((-beta * g_1_at_beta) % R_MOD, None), ((-batch_lineval_sum) % R_MOD, None)]
+        lcs["lineval_sumcheck"] = lineval
+        v_k_gamma = vanish(K, gamma)
+        matrix = []
+        for m, g, s, delta, dom in zip("abc", self.gs, self.fourth_sums, deltas, doms):
+            lcs[f"g_{m}"] = [(1, f"g_{m}")]
+            selector = v_k_gamma * dom.size % R_MOD * pow(vanish(dom, gamma) * K.size % R_MOD, -1, R_MOD) % R_MOD
+            b_term = (gamma * self._eval(g, gamma) + s) % R_MOD
+            matrix.append((delta * selector % R_MOD, f"a_poly_{m}"))
+            matrix.append(((-delta * selector % R_MOD * b_term) % R_MOD, f"b_poly_{m}"))
+        matrix.append(((-v_k_gamma) % R_MOD, "h_2"))
+        lcs["matrix_sumcheck"] = matrix
+        points = {"rowcheck_zerocheck": ("alpha", alpha), "g_1": ("beta", beta), "lineval_sumcheck": ("beta", beta),
+                  "g_a": ("gamma", gamma), "g_b": ("gamma", gamma), "g_c": ("gamma", gamma), "matrix_sumcheck": ("gamma", gamma)}
+        order = sorted(lcs)
+        return [(k, lcs[k]) for k in order], [(k, points[k]) for k in order]
+
+    mask_poly = None
+
+    def set_mask_poly(self, h_1_mask_rand, g_1_mask_rand):
+        """calculate_mask_poly (first.rs:102-127) for the hiding mode: rand(degree 3)·v_H on the variable domain plus rand(degree 5)
+        with a zero constant term; the random coefficients (ints) are arguments.  The mask is a first-round oracle (committed without a
+        degree or hiding bound, first.rs:54-56) and enters h_1 / g_1 in the third round."""
+        assert len(h_1_mask_rand) == 4 and len(g_1_mask_rand) == 6
+        n = self.circuit.variable_domain.size
+        mask = [0] * (n + 4)
+        for i, c in enumerate(h_1_mask_rand):
+            mask[n + i] = (mask[n + i] + c) % R_MOD
+            mask[i] = (mask[i] - c) % R_MOD
+        for i, c in enumerate(g_1_mask_rand):
+            if i:
+                mask[i] = (mask[i] + c) % R_MOD
+        host = np.zeros((n + 4, 4), dtype=np.uint64)
+        for i in list(range(6)) + list(range(n, n + 4)):
+            host[i] = _mont(mask[i])
+        self.mask_poly = torch.from_numpy(host.view(np.int64)).to(self.z[0].device)
+        return self.mask_poly
 
     # ---- round 4: matrix sumchecks (fourth.rs:151-245) ----
     def fourth_round(self, alpha: int, beta: int):
@@ -315,7 +397,8 @@ class Prover:
 
     def oracles(self) -> dict:
         """every polynomial the prover commits to, by round (varuna.rs:387-506)"""
-        return {1: list(self.w_polys), 2: [self.h_0], 3: [self.g_1, self.h_1], 4: list(self.gs), 5: [self.h_2]}
+        first = list(self.w_polys) + ([self.mask_poly] if self.mask_poly is not None else [])
+        return {1: first, 2: [self.h_0], 3: [self.g_1, self.h_1], 4: list(self.gs), 5: [self.h_2]}
 
 
 def test_circuit_csr(a: int, b: int, mul_depth: int, num_constraints: int, num_variables: int, dev):

@@ -80,3 +80,58 @@ def test_matrix_sumcheck_identities(kat, proved):
         h = ov.poly_sub(a_poly, ov.poly_mul(b_poly, f))
         q, r = ov.divide_by_vanishing_poly(h, arith.domain)
         assert r == [] and q == lhs_k
+
+
+def test_mask_polynomial_of_the_hiding_mode():
+    """calculate_mask_poly (first.rs:102-127): the mask sums to zero over the variable domain (the reference's debug_assert), and the
+    third round with a mask differs from the one without by exactly the mask's quotient and remainder (third.rs:207-213)"""
+    import random
+    from oracle import varuna as ov
+    rng = random.Random(9)
+    a, b = rng.randrange(2, ov.R), rng.randrange(2, ov.R)
+    circuit = ov.Circuit(ov.test_circuit(a, b, 2, 20, 14))
+    ch = [rng.randrange(2, ov.R) for _ in range(3)]
+    def third(mask):
+        p = ov.Prover(circuit, [ov.test_circuit(a, b, 2, 20, 14)])
+        if mask:
+            p.set_mask_poly(*mask)
+        p.first_round(); p.assignments(); p.second_round()
+        p.third_round(*ch)
+        return p
+    mask = ([rng.randrange(ov.R) for _ in range(4)], [rng.randrange(ov.R) for _ in range(6)])
+    pm, p0 = third(mask), third(None)
+    V = circuit.variable_domain
+    m = pm.mask_poly
+    assert len(m) == V.size + 4 and sum(ov.poly_eval(m, e) for e in V.elements()) % ov.R == 0
+    hq, xg = ov.divide_by_vanishing_poly(m, V)
+    assert hq == ov.trim(mask[0]) and xg[0] == 0 and xg[1:] == mask[1][1:]
+    assert pm.h_1 == ov.poly_add(p0.h_1, hq)
+    assert pm.g_1 == ov.trim(ov.poly_add([0] + p0.g_1, xg)[1:])
+
+
+def test_linear_combinations_vanish_at_their_points():
+    """AHPForR1CS::construct_linear_combinations restated (ahp/ahp.rs:172-389): the rowcheck, lineval and matrix sumcheck
+    combinations evaluate to zero at α, β, γ — the reference's own debug_asserts (:258, :340, :384), i.e. the verifier's equations —
+    for a batch of two instances, with and without the hiding mode's mask polynomial."""
+    import random
+    from oracle import varuna as ov
+    for seed, masked in ((1, False), (2, True)):
+        rng = random.Random(seed)
+        wit = [(rng.randrange(2, ov.R), rng.randrange(2, ov.R)) for _ in range(2)]
+        circuit = ov.Circuit(ov.test_circuit(wit[0][0], wit[0][1], 3, 30, 21))
+        p = ov.Prover(circuit, [ov.test_circuit(a, b, 3, 30, 21) for a, b in wit])
+        if masked:
+            p.set_mask_poly([rng.randrange(ov.R) for _ in range(4)], [rng.randrange(ov.R) for _ in range(6)])
+        r = lambda: rng.randrange(2, ov.R)      # noqa: E731
+        alpha, eta_b, eta_c, beta, gamma, deltas, combs = r(), r(), r(), r(), r(), [r(), r(), r()], [1, r()]
+        p.first_round(); p.assignments(); p.second_round(1, combs)
+        p.third_round(alpha, eta_b, eta_c, 1, combs)
+        p.fourth_round(alpha, beta)
+        p.fifth_round(deltas)
+        lcs, qs = p.linear_combinations(alpha, eta_b, eta_c, beta, deltas, gamma, 1, combs)
+        assert [k for k, _ in lcs] == ["g_1", "g_a", "g_b", "g_c", "lineval_sumcheck", "matrix_sumcheck", "rowcheck_zerocheck"]
+        point = {k: pt for k, (_, pt) in qs}
+        for label, terms in lcs:
+            if label in ("rowcheck_zerocheck", "lineval_sumcheck", "matrix_sumcheck"):
+                assert p.evaluate_lc(terms, point[label]) == 0, (label, masked)
+        assert ("mask_poly" in [l for _, l in dict(lcs)["lineval_sumcheck"]]) == masked

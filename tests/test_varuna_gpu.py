@@ -13,10 +13,12 @@ pytestmark = pytest.mark.gpu
 ROUND_NAMES = ("w", "z", "h_0", "g_1", "h_1", "g_a", "g_b", "g_c", "h_2")
 
 
-def _device_run(circuit, zs, ch):
+def _device_run(circuit, zs, ch, mask=None):
     from snarkvm_b200 import varuna as dv
     alpha, eta_b, eta_c, beta, deltas = ch
     p = dv.Prover(circuit, zs)
+    if mask is not None:
+        p.set_mask_poly(*mask)
     p.first_round(); p.assignments(); p.second_round()
     p.third_round(alpha, eta_b, eta_c)
     p.fourth_round(alpha, beta)
@@ -27,9 +29,11 @@ def _device_run(circuit, zs, ch):
     return out
 
 
-def _oracle_run(circuit, instances, ch):
+def _oracle_run(circuit, instances, ch, mask=None):
     alpha, eta_b, eta_c, beta, deltas = ch
     p = ov.Prover(circuit, instances)
+    if mask is not None:
+        p.set_mask_poly(*mask)
     p.first_round(); p.assignments(); p.second_round()
     p.third_round(alpha, eta_b, eta_c)
     p.fourth_round(alpha, beta)
@@ -114,3 +118,87 @@ def test_random_sparse_r1cs_vs_oracle():
     got, want = _device_run(circuit, [z], ch), _oracle_run(o_circuit, [cs], ch)
     for k in want:
         assert got[k] == want[k], k
+
+
+def test_hiding_mode_mask_polynomial_vs_oracle():
+    """VarunaHidingMode's mask polynomial (first.rs:102-127) enters h_1 and g_1 in the third round (third.rs:207-213)"""
+    from snarkvm_b200 import varuna as dv
+    rng = random.Random(5)
+    a, b = rng.randrange(2, ov.R), rng.randrange(2, ov.R)
+    o_circuit = ov.Circuit(ov.test_circuit(a, b, 2, 200, 180))
+    circuit, z = dv.test_circuit_csr(a, b, 2, 200, 180, "cuda")
+    mask = ([rng.randrange(ov.R) for _ in range(4)], [rng.randrange(ov.R) for _ in range(6)])
+    ch = _challenges(rng)
+    got, want = _device_run(circuit, [z], ch, mask), _oracle_run(o_circuit, [ov.test_circuit(a, b, 2, 200, 180)], ch, mask)
+    for k in want:
+        assert got[k] == want[k], k
+    plain = _oracle_run(o_circuit, [ov.test_circuit(a, b, 2, 200, 180)], ch)
+    assert want["h_1"] != plain["h_1"] and want["g_1"] != plain["g_1"] and want["h_0"] == plain["h_0"]
+
+
+def test_linear_combinations_and_openings_vs_oracle(oracle_cpu):
+    """the last step of prove_batch (varuna.rs:509-594): construct_linear_combinations on the device prover equals the oracle's
+    (whose three checks vanish at α, β, γ: tests/test_varuna_golden.py), and SonicKZG10 commits every oracle with the reference's
+    bounds (hiding mode: w, g_1, g_M hide; g_1, g_M are degree-bounded) and opens the combinations — against oracle/sonic.py."""
+    import torch
+    from oracle import sonic as osonic
+    from snarkvm_b200 import varuna as dv
+    from snarkvm_b200.sonic_pc import CommitterKey, LabeledPolynomial, SonicKZG10, synthetic_srs
+    rng = random.Random(21)
+    wit = [(rng.randrange(2, ov.R), rng.randrange(2, ov.R)) for _ in range(2)]
+    shape = (3, 300, 200)
+    o_circuit = ov.Circuit(ov.test_circuit(wit[0][0], wit[0][1], *shape))
+    op = ov.Prover(o_circuit, [ov.test_circuit(a, b, *shape) for a, b in wit])
+    zs, circuit = [], None
+    for a, b in wit:
+        circuit, z = dv.test_circuit_csr(a, b, *shape, "cuda")
+        zs.append(z)
+    dp = dv.Prover(circuit, zs)
+    mask = ([rng.randrange(ov.R) for _ in range(4)], [rng.randrange(ov.R) for _ in range(6)])
+    r = lambda: rng.randrange(2, ov.R)          # noqa: E731
+    alpha, eta_b, eta_c, beta, gamma, deltas, combs = r(), r(), r(), r(), r(), [r(), r(), r()], [1, r()]
+    for p in (op, dp):
+        p.set_mask_poly(*mask)
+        p.first_round(); p.assignments(); p.second_round(1, combs)
+        p.third_round(alpha, eta_b, eta_c, 1, combs)
+        p.fourth_round(alpha, beta)
+        p.fifth_round(deltas)
+    want_lcs, want_qs = op.linear_combinations(alpha, eta_b, eta_c, beta, deltas, gamma, 1, combs)
+    got_lcs, got_qs = dp.linear_combinations(alpha, eta_b, eta_c, beta, deltas, gamma, 1, combs)
+    assert got_lcs == want_lcs and got_qs == want_qs
+    opolys, dpolys = op.polynomials(), dp.polynomials()
+    assert sorted(opolys) == sorted(dpolys)
+    for k in opolys:
+        assert dv.trimmed(dpolys[k]) == opolys[k], k
+    # commitments and openings over an SRS with a known trapdoor
+    D = 2047
+    BETA, GAMMA = 0x1234567890ABCDEF % ov.R, 0xFEDCBA09 % ov.R
+    powers, gpowers = synthetic_srs(D, BETA, GAMMA)
+    V, K = o_circuit.variable_domain, o_circuit.max_non_zero_domain
+    bound_g1, bound_gm = V.size - 2, K.size - 2                                  # third.rs / fourth.rs polynomial infos
+    bounds = {"g_1": bound_g1, "g_a": o_circuit.non_zero_domains[0].size - 2, "g_b": o_circuit.non_zero_domains[1].size - 2,
+              "g_c": o_circuit.non_zero_domains[2].size - 2}
+    hiding = {"w_0", "w_1", "g_1", "g_a", "g_b", "g_c"}
+    ck = CommitterKey.trim(powers, gpowers, supported_degree=D, supported_hiding_bound=1, enforced_degree_bounds=sorted(set(bounds.values())))
+    ock = osonic.CommitterKey(powers.cpu().numpy(), gpowers.cpu().numpy(), D, (), 1, sorted(set(bounds.values())))
+    labels = sorted(opolys)
+    blind = {k: ([rng.randrange(ov.R) for _ in range(3)] if k in hiding else None) for k in labels}
+    to_dev = lambda v: torch.from_numpy(np.array([dv._mont(x) for x in v], dtype=np.uint64).reshape(-1, 4).view(np.int64)).cuda()   # noqa: E731
+    def fit(k):                                                                  # device polynomials may carry trailing zeros: cut to the bound
+        t = dpolys[k]
+        return t[: bounds[k] + 1].contiguous() if k in bounds and t.shape[0] > bounds[k] + 1 else t.contiguous()
+    labeled = [LabeledPolynomial(k, fit(k), bounds.get(k), 1 if k in hiding else None) for k in labels]
+    comms, rands = SonicKZG10.commit(ck, labeled, [None if blind[k] is None else to_dev(blind[k]) for k in labels])
+    want_comms, _ = osonic.commit(ock, [(k, opolys[k], bounds.get(k), 1 if k in hiding else None, False) for k in labels], [blind[k] for k in labels])
+    for i, k in enumerate(labels):
+        assert (comms[i] == want_comms[i]).all(), k
+    chal = [rng.randrange(1 << 128) for _ in range(len(got_lcs) + 3)]
+    got = SonicKZG10.open_combinations(ck, got_lcs, labeled, rands, got_qs, iter(chal))
+    want = osonic.open_combinations(ock, want_lcs, {k: (opolys[k], blind[k], bounds.get(k)) for k in labels}, want_qs, iter(chal))
+    assert len(got) == len(want) == 3
+    for (gw, gv), (ww, wv) in zip(got, want):
+        assert (gw == ww).all()
+        assert (gv is None) == (wv is None)
+        if gv is not None:
+            from oracle import bls12_377 as py
+            assert py.fr_from_mont(py.from_limbs(np.asarray(gv, dtype=np.uint64))) == wv
