@@ -578,6 +578,8 @@ def run_product(args, rank, world, local_rank):
         bv = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(bv)
         varuna_line = bv.run(args.varuna_lg, reps=2)
+        # the whole prove_batch-shaped pipeline: hiding mode, SonicKZG10 commits with degree / hiding bounds, linear combinations, openings
+        varuna_line["prove"] = bv.run_prove(args.varuna_lg, reps=1)
 
     # ---- G2 (north_star "G1/G2"): VariableBase::msm over Affine<G2>, standard::msm semantics, closed-form check ----
     g2_line = None
