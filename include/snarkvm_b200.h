@@ -236,6 +236,8 @@ SNARKVM_API int snarkvm_b200_profile_collect(int kind, double* total_ms, uint64_
 /* Device self-test of the warp-cooperative Fq multiplication / inversion used by the CTA-shared inversions: nwarps pseudo-random cases
  * (plus 0, 1, q - 1 and a long-carry value) checked against the per-thread multiplier; *mismatches (HOST) = failing cases. */
 SNARKVM_API int snarkvm_b200_selftest_coop(uint32_t nwarps, uint64_t seed, uint32_t* mismatches, void* stream);
+/* host-only self-test of the pageable-memory staging copies (copy-thread pool, non-temporal stores); needs no GPU */
+SNARKVM_API int snarkvm_b200_selftest_host_copy(size_t max_bytes, uint64_t seed, uint32_t* mismatches);
 
 /* Deterministic synthetic bases P_i = h(seed, i) * G written in the reference affine layout. */
 /* ---- G2 (points over Fq2) ----------------------------------------------------------------------------------------------

@@ -30,7 +30,7 @@ SYMBOLS = (
     "snarkvm_b200_register_bases_precomputed",
     "snarkvm_b200_msm_batch_device", "snarkvm_b200_msm_window_sums_plan_device", "snarkvm_b200_kzg_commit_batch_hiding_device",
     "snarkvm_b200_kzg_commit_batch_precomputed_device", "snarkvm_b200_msm_scratch_stats", "snarkvm_b200_msm_set_scratch_limit", "snarkvm_b200_msm_window_sums_host", "snarkvm_b200_selftest_coop", "snarkvm_b200_msm_plan_levels", "snarkvm_b200_msm_g2", "snarkvm_b200_msm_g2_device", "snarkvm_b200_generate_bases_g2_device",
-    "snarkvm_b200_sonic_commit_batch_device", "snarkvm_b200_generator_mul_device",
+    "snarkvm_b200_sonic_commit_batch_device", "snarkvm_b200_generator_mul_device", "snarkvm_b200_selftest_host_copy",
 )
 
 
@@ -118,6 +118,7 @@ def lib():
     L.snarkvm_b200_msm_scratch_stats.argtypes = [ctypes.POINTER(sz), ctypes.POINTER(sz), ctypes.POINTER(sz)]
     L.snarkvm_b200_msm_set_scratch_limit.argtypes = [sz]
     L.snarkvm_b200_selftest_coop.argtypes = [u32, u64, ctypes.POINTER(u32), vp]
+    L.snarkvm_b200_selftest_host_copy.argtypes = [sz, u64, ctypes.POINTER(u32)]
     L.snarkvm_b200_msm_window_sums_host.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp]
     for s in SYMBOLS[5:]:
         getattr(L, s).restype = i32

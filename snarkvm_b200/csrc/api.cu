@@ -24,6 +24,7 @@
 #include "ntt.cuh"
 #include "poly.cuh"
 
+namespace b200 { void host_stream_copy(void* dst, const void* src, size_t n); }      // hostcopy.cpp: memcpy with non-temporal stores
 using namespace b200;
 
 namespace {
@@ -184,7 +185,7 @@ public:
     // memcpy(dst, src, bytes) split over the pool and the caller; returns when all of it is done
     void parallel_memcpy(void* dst, const void* src, size_t bytes) {
         const size_t piece = (size_t)2 << 20;
-        if (bytes <= piece || nthreads_ == 0) { memcpy(dst, src, bytes); return; }
+        if (bytes <= piece || nthreads_ == 0) { host_stream_copy(dst, src, bytes); return; }
         Batch batch;
         batch.dst = (uint8_t*)dst; batch.src = (const uint8_t*)src; batch.bytes = bytes; batch.piece = piece;
         batch.npieces = (bytes + piece - 1) / piece;
@@ -235,9 +236,9 @@ private:
         for (;;) {
             size_t k = b.next.fetch_add(1);
             if (k >= b.npieces) return;
-            if (b.rows) { memcpy(b.dst + k * b.dpitch, b.src + k * b.spitch, b.piece); continue; }
+            if (b.rows) { host_stream_copy(b.dst + k * b.dpitch, b.src + k * b.spitch, b.piece); continue; }
             size_t off = k * b.piece, len = b.bytes - off < b.piece ? b.bytes - off : b.piece;
-            memcpy(b.dst + off, b.src + off, len);
+            host_stream_copy(b.dst + off, b.src + off, len);
         }
     }
     void loop() {
@@ -1153,6 +1154,39 @@ int snarkvm_b200_register_bases_precomputed(const void* host_points, size_t npoi
 }
 
 // device self-test of the warp-cooperative field arithmetic: returns 0 and *mismatches = number of failing warps
+// Host-only self-test of the staging copies (copy pool + non-temporal stores, hostcopy.cpp): contiguous copies and column-range
+// copies of random sizes and alignments against memcpy.  Needs no GPU; *mismatches receives the number of differing cases.
+int snarkvm_b200_selftest_host_copy(size_t max_bytes, uint64_t seed, uint32_t* mismatches) {
+    if (!mismatches || max_bytes < 4096) return (int)cudaErrorInvalidValue;
+    std::vector<uint8_t> src(max_bytes + 256), dst(max_bytes + 256), ref(max_bytes + 256);
+    uint64_t x = seed | 1;
+    auto rnd = [&x]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    for (size_t i = 0; i < src.size(); i++) src[i] = (uint8_t)rnd();
+    uint32_t bad = 0;
+    const size_t sizes[] = {0, 1, 31, 32, 33, 4095, 4096, 4097, 65537, ((size_t)2 << 20) - 1, ((size_t)2 << 20) + 5, max_bytes};
+    for (size_t n : sizes) {
+        if (n > max_bytes) continue;
+        for (int rep = 0; rep < 3; rep++) {
+            const size_t so = rnd() % 64, doff = rnd() % 64;
+            memset(dst.data(), 0xA5, dst.size()); memset(ref.data(), 0xA5, ref.size());
+            memcpy(ref.data() + doff, src.data() + so, n);
+            CopyPool::get().parallel_memcpy(dst.data() + doff, src.data() + so, n);
+            if (memcmp(dst.data(), ref.data(), dst.size()) != 0) bad++;
+        }
+    }
+    for (int rep = 0; rep < 6; rep++) {                             // rows: a column range of a row-major matrix
+        const size_t width = 32 * (1 + rnd() % 700) + (rep & 1 ? 8 : 0), rows = 1 + rnd() % 97;
+        const size_t spitch = width + 32 * (rnd() % 9), dpitch = width + 8 * (rnd() % 5);
+        if (rows * spitch > max_bytes || rows * dpitch > max_bytes) continue;
+        memset(dst.data(), 0x5A, dst.size()); memset(ref.data(), 0x5A, ref.size());
+        for (size_t r = 0; r < rows; r++) memcpy(ref.data() + r * dpitch, src.data() + r * spitch, width);
+        CopyPool::get().parallel_rows(dst.data(), dpitch, src.data(), spitch, width, rows);
+        if (memcmp(dst.data(), ref.data(), dst.size()) != 0) bad++;
+    }
+    *mismatches = bad;
+    return 0;
+}
+
 int snarkvm_b200_selftest_coop(uint32_t nwarps, uint64_t seed, uint32_t* mismatches, void* stream_v) {
     if (!mismatches || nwarps == 0) return (int)cudaErrorInvalidValue;
     cudaStream_t stream = (cudaStream_t)stream_v;

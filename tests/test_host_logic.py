@@ -123,3 +123,13 @@ def test_kzg_argument_checks_need_no_gpu():
         KZG10.open_lagrange(basis, domain, evals[:5], alg._fr_int_to_mont(5), alg._fr_int_to_mont(0))
     with pytest.raises(ValueError, match="Lagrange basis size"):
         KZG10.commit_lagrange(basis, evals[:3])                 # next_power_of_two(3) = 4 ≠ 8
+
+
+def test_staging_copies_match_memcpy():
+    """the pageable → pinned staging path of snarkvm_msm / snarkvm_ntt (copy-thread pool + non-temporal stores, csrc/hostcopy.cpp):
+    contiguous and column-range copies of awkward sizes and alignments equal memcpy.  Host code only."""
+    import ctypes
+    from snarkvm_b200 import _lib
+    bad = ctypes.c_uint32(99)
+    _lib.check(_lib.lib().snarkvm_b200_selftest_host_copy(9 << 20, 0xC0DE, ctypes.byref(bad)))
+    assert bad.value == 0
