@@ -196,7 +196,8 @@ class SonicKZG10:
         for label, (point_name, point) in query_set:
             entry = by_point.setdefault(point_name, (point, set()))
             entry[1].add(label)
-        proofs = []
+        powers, gamma = ck.powers()
+        witnesses, hiding_witnesses, random_vs = [], [], []
         for point_name in sorted(by_point):
             point, labels = by_point[point_name]
             qp, qr = [], []
@@ -206,12 +207,17 @@ class SonicKZG10:
                 qp.append(poly_rand[label][0]); qr.append(poly_rand[label][1])
             polynomial, rand = SonicKZG10.combine_for_open(ck, qp, qr, challenges)
             next(challenges)                                                   # `_randomizer`
-            powers, gamma = ck.powers()
             z = _fr_int_to_mont(int(point) % _R_MOD)
             if polynomial.shape[0] > powers.shape[0]:
                 raise ValueError("check_degree_is_too_large")
-            proofs.append(KZG10.open(powers, polynomial, z, gamma, rand.blinding_polynomial if rand.is_hiding() else None))
-        return proofs
+            # kzg10::open (mod.rs:303-321): the witness polynomials now, their commitments below — all points in ONE device pass
+            w, rw = KZG10.compute_witness_polynomial(polynomial, z, rand.blinding_polynomial if rand.is_hiding() else None)
+            witnesses.append(w); hiding_witnesses.append(rw)
+            random_vs.append(device.poly_evaluate(rand.blinding_polynomial, z) if rand.is_hiding() else None)
+        k = len(witnesses)
+        any_hiding = any(h is not None for h in hiding_witnesses)
+        ws = device.sonic_commit_batch([powers] * k, witnesses, [gamma] * k if any_hiding else None, hiding_witnesses if any_hiding else None)
+        return [(ws[i], random_vs[i]) for i in range(k)]
 
     @staticmethod
     def open_combinations(ck: CommitterKey, linear_combinations: list, polynomials: list, rands: list, query_set: list, challenges):
