@@ -62,10 +62,18 @@ int prof_collect(int kind, double* total_ms, uint64_t* count) {
     } while (0)
 
 static int ceil_log2(size_t x) { int l = 0; size_t v = x > 1 ? x - 1 : 0; while (v) { l++; v >>= 1; } return l; }
+// log2 rounded to the NEAREST integer (in the log domain): the plans below were swept at powers of two, and a size just above one
+// — a 2^20-coefficient polynomial plus four blinding terms — belongs to that power's plan, not to the next one's
+// (round 1 of the Varuna prover committed w with the 2^21 plan: 15.5 ms instead of 9.8).
+static int plan_log2(size_t x) {
+    int l = ceil_log2(x < 2 ? 2 : x);
+    if (l > 1 && (double)x < 0.70710678118 * (double)((size_t)1 << l)) l--;
+    return l;
+}
 
 MsmPlan msm_make_plan(size_t npoints) {
     MsmPlan p;
-    int lg = ceil_log2(npoints < 2 ? 2 : npoints);
+    int lg = plan_log2(npoints);
     // Window bits from a sweep on B200 (tools/tune_msm.py, profiles/tune_msm_r1.log): wider windows mean fewer
     // bucket additions (n·W) but more buckets to reduce and shorter, more divergent bucket runs.
     int c = lg <= 8 ? 4 : lg <= 12 ? lg - 4 : lg <= 18 ? 11 : lg == 19 ? 13 : lg == 20 ? 15 : lg <= 22 ? 16 : 17;
@@ -97,7 +105,7 @@ MsmPlan msm_make_plan(size_t npoints) {
 MsmPlan msm_make_plan_batch(size_t max_n, size_t total_n) {
     MsmPlan p = msm_make_plan(max_n);
     if (total_n > max_n) {
-        int lgt = ceil_log2(total_n < 2 ? 2 : total_n);
+        int lgt = plan_log2(total_n);
         int levels = lgt >= 23 ? 5 : lgt >= 21 ? 4 : lgt == 20 ? 3 : lgt == 19 ? 2 : 0;
         while (levels > 0 && ((max_n >> (p.c - 1)) >> levels) < 2) levels--;
         if (const char* e = getenv("SNARKVM_B200_MSM_LEVELS")) { int v = atoi(e); if (v >= 0 && v <= 16) levels = v; }
