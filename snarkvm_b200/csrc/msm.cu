@@ -1364,9 +1364,9 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
     // (measured, profiles/r2s_phases_*.log: the warp-per-item kernel wins at 2^8 points — 0.10 → 0.06 ms — and loses from 2^10,
     // 0.105 → 0.134 ms, where the 1400 items no longer fit one wave of 255-register warps)
     bool acc_q8 = quad_path != 0 && warp_reduce && levels == 0 && (size_t)TB + max_entries / 32 <= 1100;
-    // scan-free 32:1 folds of hot buckets, skipped on the device when no bucket has more than 32 item partials
-    const bool quad_fold = quad_path != 0 && warp_reduce && levels == 0;
     if (const char* e = getenv("SNARKVM_B200_MSM_WARP_PATH")) { if (atoi(e) == 0) { warp_reduce = false; acc_g8 = false; acc_q8 = false; } }
+    // scan-free 32:1 folds of the hot buckets (a device-side list of those with more than 32 item partials)
+    const bool quad_fold = quad_path != 0 && warp_reduce && levels == 0;
     if (acc_q8) acc_g8 = false;
     uint32_t item_cap = plan.cap;                                  // points per work item of the XYZZ accumulation
     if (acc_g8) {                                                  // eight lanes per item: 8 × (4 … 16) points

@@ -14,3 +14,24 @@ print('ntt', d['ntt']['ms_per_transform'], d['ntt']['e2e']['ms_per_step'])
 print('varuna', d['varuna']['s_per_proof'], d['varuna'].get('prove', {}).get('s_per_proof'))
 print('checks', d['checks'])
 PY
+python - <<'PY'
+import os, sys, time
+sys.path.insert(0, os.getcwd())
+import numpy as np
+from snarkvm_b200 import device
+rng = np.random.default_rng(1)
+from oracle import cpu, bls12_377 as py
+# host tail alone: Horner over 32 window sums of c = 8 (what a 2^12-point call does after its D2H)
+g = np.frombuffer(py.affine_bytes(py.G1_GENERATOR), dtype=np.uint8)
+pts = []
+for k in range(32):
+    proj = cpu.g1_mul(g, np.array([k + 3, 0, 0, 0], dtype=np.uint64))
+    x, y = proj[:6], proj[6:12]
+    one = proj[12:18]
+    pts.append(np.concatenate([x, y, one, one]))          # XYZZ with ZZ = ZZZ = 1
+sums = np.stack(pts).astype(np.uint64)
+device.msm_finish(sums, 8)
+t0 = time.perf_counter()
+for _ in range(200): device.msm_finish(sums, 8)
+print(f"host Horner (32 windows, c = 8) incl. ctypes: {(time.perf_counter() - t0) / 200 * 1e6:.1f} us")
+PY
