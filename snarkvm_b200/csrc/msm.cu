@@ -176,12 +176,13 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
 }
 
 __global__ void k_items_per_bucket(const uint32_t* __restrict__ hist, uint32_t* __restrict__ items, uint32_t total_buckets, uint32_t cap,
-                                   uint32_t* __restrict__ hot /* may be null; hot[0] = count, hot[1 …] = buckets with more than 32 items */, uint32_t hot_max) {
+                                   uint32_t* __restrict__ hot /* may be null; hot[0] = count, hot[1 …] = buckets with more than `keep` items */, uint32_t hot_max,
+                                   uint32_t keep) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < total_buckets) {
         const uint32_t it = (hist[i] + cap - 1u) / cap;
         items[i] = it;
-        if (hot != nullptr && it > 32u) { const uint32_t pos = atomicAdd(hot, 1u); if (pos < hot_max) hot[1u + pos] = i; }
+        if (hot != nullptr && it > keep) { const uint32_t pos = atomicAdd(hot, 1u); if (pos < hot_max) hot[1u + pos] = i; }
     } else if (i == total_buckets) items[i] = 0;
 }
 
@@ -737,10 +738,14 @@ __global__ void k_halve_counts(const uint32_t* __restrict__ off_in, uint32_t* __
     if (i < total_buckets) cnt_out[i] = (off_in[i + 1] - off_in[i] + 1u) >> 1;
     else if (i == total_buckets) cnt_out[i] = 0;
 }
-__global__ void k_items_from_offsets(const uint32_t* __restrict__ off, uint32_t* __restrict__ items, uint32_t total_buckets, uint32_t cap) {
+__global__ void k_items_from_offsets(const uint32_t* __restrict__ off, uint32_t* __restrict__ items, uint32_t total_buckets, uint32_t cap,
+                                     uint32_t* __restrict__ hot, uint32_t hot_max, uint32_t keep) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < total_buckets) items[i] = (off[i + 1] - off[i] + cap - 1u) / cap;
-    else if (i == total_buckets) items[i] = 0;
+    if (i < total_buckets) {
+        const uint32_t it = (off[i + 1] - off[i] + cap - 1u) / cap;
+        items[i] = it;
+        if (hot != nullptr && it > keep) { const uint32_t pos = atomicAdd(hot, 1u); if (pos < hot_max) hot[1u + pos] = i; }
+    } else if (i == total_buckets) items[i] = 0;
 }
 
 // XYZZ accumulation of what the pair levels left: contiguous dense points, no gather, no signs.
@@ -788,6 +793,14 @@ __global__ void __launch_bounds__(128) k_partial_group_sum(const uint32_t* __res
     s.store(partial_out + (size_t)t * XYZZ_WORDS);
 }
 
+// rounds of 32:1 folds a bucket with `cnt` item partials takes until at most `keep` are left
+FF_DEV uint32_t fold_rounds_of(uint32_t cnt, uint32_t& final_cnt, uint32_t keep = 32u) {
+    uint32_t r = 0;
+    while (cnt > keep) { cnt = (cnt + 31u) >> 5; r++; }
+    final_cnt = cnt;
+    return r;
+}
+
 // Σ of a bucket's item partials
 FF_DEV XYZZ bucket_sum(const uint32_t* __restrict__ partial, const uint32_t* __restrict__ item_start, uint32_t wb) {
     uint32_t i0 = item_start[wb], i1 = item_start[wb + 1];
@@ -802,18 +815,37 @@ FF_DEV XYZZ bucket_sum(const uint32_t* __restrict__ partial, const uint32_t* __r
 // Thread j of window w owns bucket values [lo, hi] = [j·K + 1, (j+1)·K]:
 //   running = Σ S_b ; acc = Σ (b − lo + 1)·S_b   (top-down running sum, batched.rs:356-361)
 //   out = acc + (lo − 1)·running = Σ b·S_b over the chunk.
+// PAIRS: the chunk's entry for the quad-lane combine levels instead — out[2t] = Σ (b − lo + 1)·S_b, out[2t + 1] = Σ S_b — which
+// apply the chunk's offset as 8:1 weighted folds (k_combine_level_quad).  The (lo − 1)·running product costs this thread ≈ 24
+// more dependent point operations (16 doublings + the additions of lo's bits) on top of its 32: 43 % of the kernel at 2^24 points.
+// folds > 0 (PAIRS only): hot buckets were folded down to ONE partial by k_fold_hot_quad (keep = 1); that partial sits at the bucket's
+// offset in `partial` or, after an odd number of rounds, in `partial_b`.
+template <bool PAIRS>
 __global__ void __launch_bounds__(128) k_bucket_reduce(const uint32_t* __restrict__ partial, const uint32_t* __restrict__ item_start,
                                                         uint32_t nbuckets, uint32_t chunk, uint32_t chunks_per_window,
-                                                        uint32_t nwin, uint32_t* __restrict__ out) {
+                                                        uint32_t nwin, uint32_t* __restrict__ out,
+                                                        const uint32_t* __restrict__ partial_b = nullptr, int folds = 0) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= chunks_per_window * nwin) return;
     uint32_t w = t / chunks_per_window, j = t % chunks_per_window;
     uint32_t lo = j * chunk, hi = lo + chunk;                 // 0-based bucket indices [lo, hi)
     XYZZ running = XYZZ::infinity(), acc = XYZZ::infinity();
     for (uint32_t b = hi; b-- > lo;) {
-        XYZZ s = bucket_sum(partial, item_start, w * nbuckets + b);
+        XYZZ s;
+        if (PAIRS && folds > 0) {
+            const uint32_t wb = w * nbuckets + b, i0 = item_start[wb];
+            uint32_t cnt = item_start[wb + 1] - i0;
+            const uint32_t r = fold_rounds_of(cnt, cnt, 1u);
+            s = cnt ? XYZZ::load(((r & 1u) ? partial_b : partial) + (size_t)i0 * XYZZ_WORDS) : XYZZ::infinity();
+        } else
+            s = bucket_sum(partial, item_start, w * nbuckets + b);
         running.add(s);
         acc.add(running);
+    }
+    if (PAIRS) {
+        acc.store(out + (size_t)t * 2 * XYZZ_WORDS);
+        running.store(out + ((size_t)t * 2 + 1) * XYZZ_WORDS);
+        return;
     }
     if (lo != 0u) acc.add(running.mul_u32(lo));               // bucket value of index lo is lo+1 ⇒ (lo+1−1)·running
     acc.store(out + (size_t)t * XYZZ_WORDS);
@@ -1002,14 +1034,9 @@ __global__ void __launch_bounds__(128, 2) k_bucket_accumulate_q8(const uint32_t*
 // each bucket knows from its own count how many rounds it took part in and which buffer holds its partials.  k_items_per_bucket
 // lists the buckets with more than 32 items; warp w works on hot bucket w / 32 and takes every 32nd group of it, quad s of the
 // warp adds entries s, s + 8, … of the group.  Rounds launched for the worst case find nothing to do and return.
-FF_DEV uint32_t fold_rounds_of(uint32_t cnt, uint32_t& final_cnt) {
-    uint32_t r = 0;
-    while (cnt > 32u) { cnt = (cnt + 31u) >> 5; r++; }
-    final_cnt = cnt;
-    return r;
-}
 __global__ void __launch_bounds__(128) k_fold_hot_quad(const uint32_t* __restrict__ in, const uint32_t* __restrict__ item_start,
-                                                       const uint32_t* __restrict__ hot, uint32_t hot_max, uint32_t round, uint32_t* __restrict__ out) {
+                                                       const uint32_t* __restrict__ hot, uint32_t hot_max, uint32_t round, uint32_t keep,
+                                                       uint32_t* __restrict__ out) {
     uint32_t nhot = hot[0];
     if (nhot > hot_max) nhot = hot_max;
     const Quad Q = Quad::here();
@@ -1019,8 +1046,8 @@ __global__ void __launch_bounds__(128) k_fold_hot_quad(const uint32_t* __restric
         const uint32_t i0 = item_start[b];
         uint32_t cnt = item_start[b + 1] - i0;
         bool live = true;
-        for (uint32_t r = 0; r < round; r++) { if (cnt <= 32u) live = false; cnt = (cnt + 31u) >> 5; }
-        if (!live || cnt <= 32u) continue;                              // this bucket finished in an earlier round
+        for (uint32_t r = 0; r < round; r++) { if (cnt <= keep) live = false; cnt = (cnt + 31u) >> 5; }
+        if (!live || cnt <= keep) continue;                             // this bucket finished in an earlier round
         const uint32_t groups = (cnt + 31u) >> 5;
         for (uint32_t g = w0 & 31u; g < groups; g += 32u) {
             const uint32_t k = g << 5, end = k + 32u < cnt ? k + 32u : cnt;
@@ -1102,6 +1129,32 @@ __global__ void __launch_bounds__(128) k_combine_level_quad(const uint32_t* __re
     if ((threadIdx.x & 31u) == 0u) {
         store_xyzz_plain(out + (size_t)warp * 2 * XYZZ_WORDS, A);
         store_xyzz_plain(out + ((size_t)warp * 2 + 1) * XYZZ_WORDS, run);
+    }
+}
+// The same fold with ONE QUAD per group, its 8 entries walked from the top with running sums (Σ s·run_s = Σ_{s ≥ 1} running after
+// entry s): 23 additions per group instead of 9 scan / sum steps that all eight quads of a warp execute — 4× fewer warp
+// instructions.  For levels with thousands of groups (4096 → 512 entries per window at 2^24 points: 0.69 → 0.2 ms), where the
+// multiplier's throughput matters more than the depth of one group's chain.
+__global__ void __launch_bounds__(128) k_combine_level_quadseq(const uint32_t* __restrict__ in, uint32_t m, uint32_t nsets, int lgw, uint32_t* __restrict__ out) {
+    const uint32_t quad = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, groups = (m + 7u) / 8u;
+    if (quad >= nsets * groups) return;                                 // whole quads; no warp-wide exchange below
+    const Quad Q = Quad::here();
+    const uint32_t set = quad / groups, g = quad % groups, first = g * 8u;
+    const uint32_t cnt = m - first < 8u ? m - first : 8u;
+    XYZZ A = XYZZ::infinity(), running = XYZZ::infinity(), W = XYZZ::infinity();
+#pragma unroll 1
+    for (uint32_t s = cnt; s-- > 0u;) {
+        const size_t e = ((size_t)set * m + first + s) * 2;
+        A = quad_add(A, load_xyzz_plain(in + e * XYZZ_WORDS), Q);
+        running = quad_add(running, load_xyzz_plain(in + (e + 1) * XYZZ_WORDS), Q);
+        if (s >= 1u) W = quad_add(W, running, Q);
+    }
+#pragma unroll 1
+    for (int k = 0; k < lgw; k++) W = quad_dbl(W, Q);
+    A = quad_add(A, W, Q);
+    if (Q.q == 0) {
+        store_xyzz_plain(out + (size_t)quad * 2 * XYZZ_WORDS, A);
+        store_xyzz_plain(out + ((size_t)quad * 2 + 1) * XYZZ_WORDS, running);
     }
 }
 // window sum of a set from its m0 ≤ 64 entries (each spanning 2^lgw0 buckets): one CTA per set, 8:1 per level through
@@ -1365,8 +1418,17 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
     // 0.105 → 0.134 ms, where the 1400 items no longer fit one wave of 255-register warps)
     bool acc_q8 = quad_path != 0 && warp_reduce && levels == 0 && (size_t)TB + max_entries / 32 <= 1100;
     if (const char* e = getenv("SNARKVM_B200_MSM_WARP_PATH")) { if (atoi(e) == 0) { warp_reduce = false; acc_g8 = false; acc_q8 = false; } }
+    bool quad_tail_large = true;                                  // quad-lane combine levels after the per-chunk reduction of large bucket sets
+    // (measured, profiles/r2ae_phases.log: total 2^24 90.75 → 89.59 ms, 2^22 28.02 → 27.29, 2^20 9.82 → 9.41; at 2^19 — 4096 buckets per
+    // window, 256 chunks — the shorter old chain wins, 7.28 vs 7.43 ms)
+    if (plan.nbuckets < 16384u) quad_tail_large = false;
+    if (const char* e = getenv("SNARKVM_B200_MSM_QUAD_TAIL")) quad_tail_large = atoi(e) != 0;
     // scan-free 32:1 folds of the hot buckets (a device-side list of those with more than 32 item partials)
     const bool quad_fold = quad_path != 0 && warp_reduce && levels == 0;
+    // large bucket sets: the same list-driven folds, down to ONE partial per bucket (a lone thread adds what is left of a bucket in
+    // k_bucket_reduce, so nothing may be left), instead of two scan + copy passes over every bucket
+    const bool large_hot = quad_path != 0 && quad_tail_large && !warp_reduce;
+    const uint32_t hot_keep = large_hot ? 1u : 32u;
     if (acc_q8) acc_g8 = false;
     uint32_t item_cap = plan.cap;                                  // points per work item of the XYZZ accumulation
     if (acc_g8) {                                                  // eight lanes per item: 8 × (4 … 16) points
@@ -1388,7 +1450,7 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
     }
     const bool small_cap = quad_fold && !acc_g8 && !acc_q8 && item_cap != plan.cap;
     const size_t max_items = (size_t)TBg + entries_g / (item_cap < plan.cap ? item_cap : plan.cap) + 1;
-    const size_t hot_max = max_items / 32 + 1;                        // buckets with more than 32 item partials
+    const size_t hot_max = max_items / 2 + 1;                         // buckets with more than `hot_keep` (1 or 32) item partials
     const size_t dense_cap_a = entries_g / 2 + TBg + 1, dense_cap_b = entries_g / 4 + 2 * (size_t)TBg + 1;
 
     size_t pair_waves = 0;                       // 0 = fewest whole waves with T ≤ 1024 outputs per lane
@@ -1437,10 +1499,10 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
         sorted = records ? nullptr : a.take<uint32_t>(max_entries);
         cnt_tmp = a.take<uint32_t>((size_t)TBg + 1);
         partial = a.take<uint32_t>(max_items * XYZZ_WORDS);
-        partial2 = a.take<uint32_t>((quad_fold ? max_items : (size_t)TBg + max_items / 32 + 2) * XYZZ_WORDS);      // quad folds keep the item layout
+        partial2 = a.take<uint32_t>(((quad_fold || large_hot) ? max_items : (size_t)TBg + max_items / 32 + 2) * XYZZ_WORDS);      // quad folds keep the item layout
         hot_dev = a.take<uint32_t>(hot_max + 2);
-        red_a = a.take<uint32_t>((size_t)gw * (chunks_per_set > 2 * ((plan.nbuckets + 7u) / 8u) ? chunks_per_set : 2 * ((plan.nbuckets + 7u) / 8u)) * XYZZ_WORDS);
-        red_b = a.take<uint32_t>((size_t)gw * (chunks_per_set / tree + 1 > 2 * ((plan.nbuckets + 63u) / 64u) ? chunks_per_set / tree + 1 : 2 * ((plan.nbuckets + 63u) / 64u)) * XYZZ_WORDS);
+        red_a = a.take<uint32_t>((size_t)gw * (2 * chunks_per_set > 2 * ((plan.nbuckets + 7u) / 8u) ? 2 * chunks_per_set : 2 * ((plan.nbuckets + 7u) / 8u)) * XYZZ_WORDS);
+        red_b = a.take<uint32_t>((size_t)gw * (chunks_per_set / tree + 1 > 2 * ((plan.nbuckets + 63u) / 64u) + 2 ? chunks_per_set / tree + 1 : 2 * ((plan.nbuckets + 63u) / 64u) + 2) * XYZZ_WORDS);
         cub_tmp = a.take<uint8_t>(cub_bytes);
         if (!flat && !records) dense_bases = a.take<uint32_t>(total_bases * (size_t)BASE_WORDS);
         if (records) dense0 = a.take<uint32_t>(entries_g * (size_t)DENSE_WORDS);
@@ -1464,7 +1526,7 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
 
     CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)(TB + 1) * 4, stream));
     if (sm_slots) CUDA_TRY(cudaMemsetAsync(sm_slots, 0, 256 * 4, stream));
-    if (quad_fold) CUDA_TRY(cudaMemsetAsync(hot_dev, 0, 4, stream));
+    if (quad_fold) CUDA_TRY(cudaMemsetAsync(hot_dev, 0, 4, stream));     // (large_hot: reset per window group below)
     {
         // ---- bucket sort of all jobs and windows: histogram → offsets → scatter ----
         {
@@ -1511,13 +1573,14 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
             const uint32_t* bs = bucket_start + (size_t)w0 * plan.nbuckets;                       // tb + 1 absolute offsets into `sorted`
             size_t entries = set_cap * (size_t)wn;                                                // bound on the group's entries
             if (entries > max_entries) entries = max_entries;
+            if (large_hot) CUDA_TRY(cudaMemsetAsync(hot_dev, 0, 4, stream));
             size_t items_bound = 1;                                                                // ≥ item count of any single bucket
             size_t items_launched = 1;                                                             // ≥ total item count of the group
             const uint32_t* final_partial = nullptr;
             const uint32_t* final_start = nullptr;
             if (levels == 0) {
                 const uint32_t cap = (acc_g8 || acc_q8 || small_cap) ? item_cap : plan.cap;
-                k_items_per_bucket<<<(tb + 256) / 256, 256, 0, stream>>>(hist + (size_t)w0 * plan.nbuckets, items, tb, cap, quad_fold ? hot_dev : nullptr, (uint32_t)hot_max);
+                k_items_per_bucket<<<(tb + 256) / 256, 256, 0, stream>>>(hist + (size_t)w0 * plan.nbuckets, items, tb, cap, (quad_fold || large_hot) ? hot_dev : nullptr, (uint32_t)hot_max, hot_keep);
                 CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(tb + 1), stream));
                 count_launch(2);
                 const size_t group_items = (size_t)tb + entries / cap + 1;
@@ -1609,7 +1672,7 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
                     off_in = off_out;
                     dense_in = dense_out;
                 }
-                k_items_from_offsets<<<(tb + 256) / 256, 256, 0, stream>>>(off_in, items, tb, plan.cap);
+                k_items_from_offsets<<<(tb + 256) / 256, 256, 0, stream>>>(off_in, items, tb, plan.cap, large_hot ? hot_dev : nullptr, (uint32_t)hot_max, hot_keep);
                 CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, items, item_start, (int)(tb + 1), stream));
                 const size_t group_items = (size_t)tb + bound / plan.cap + 1;
                 items_bound = ((set_cap >> levels) + 1) / plan.cap + 1;
@@ -1626,7 +1689,19 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
                 size_t worst = acc_q8 ? 1 : items_bound;
                 const uint32_t* p_in = partial; uint32_t* p_out = partial2;
                 while (worst > 32) {
-                    k_fold_hot_quad<<<(unsigned)sm_count * 8, 128, 0, stream>>>(p_in, item_start, hot_dev, (uint32_t)hot_max, (uint32_t)quad_rounds, p_out);
+                    k_fold_hot_quad<<<(unsigned)sm_count * 8, 128, 0, stream>>>(p_in, item_start, hot_dev, (uint32_t)hot_max, (uint32_t)quad_rounds, 32u, p_out);
+                    count_launch();
+                    worst = (worst + 31) / 32;
+                    quad_rounds++;
+                    const uint32_t* t1 = p_in; p_in = p_out; p_out = (uint32_t*)t1;
+                }
+                final_partial = partial; final_start = item_start;
+            } else if (large_hot) {
+                // buckets with more than one item partial (the hot ones: few) are folded to one by the list-driven quad kernel
+                size_t worst = items_bound;
+                const uint32_t* p_in = partial; uint32_t* p_out = partial2;
+                while (worst > 1) {
+                    k_fold_hot_quad<<<(unsigned)sm_count * 8, 128, 0, stream>>>(p_in, item_start, hot_dev, (uint32_t)hot_max, (uint32_t)quad_rounds, 1u, p_out);
                     count_launch();
                     worst = (worst + 31) / 32;
                     quad_rounds++;
@@ -1681,7 +1756,32 @@ int msm_core(uint32_t* d_window_sums, uint32_t* d_flags, const MsmPlan& plan, co
                 continue;
             }
             const uint32_t nthreads = chunks_per_set * wn;
-            k_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, stream>>>(final_partial, final_start, plan.nbuckets, chunk, chunks_per_set, wn, red_a);
+            if (quad_path != 0 && quad_tail_large) {
+                // one thread per 16-bucket chunk leaves its (weighted sum, sum) pair; the chunk offsets are applied by 8:1 quad-lane
+                // folds (span 16 → 128 → 1024 → …), the last ≤ 64 entries of a set inside one CTA
+                k_bucket_reduce<true><<<(nthreads + 127) / 128, 128, 0, stream>>>(final_partial, final_start, plan.nbuckets, chunk, chunks_per_set, wn, red_a,
+                                                                                    partial2, large_hot ? quad_rounds : 0);
+                count_launch(1);
+                const uint32_t* ent = red_a;
+                uint32_t* other = red_b;
+                uint32_t m = chunks_per_set;
+                int lgw = 0;
+                while ((1u << lgw) < chunk) lgw++;
+                while (m > 64u) {
+                    const uint32_t groups = (m + 7u) / 8u;
+                    if ((size_t)wn * groups >= 2048)                    // many groups: one quad each, sequential
+                        k_combine_level_quadseq<<<(unsigned)(((size_t)wn * groups * 4 + 127) / 128), 128, 0, stream>>>(ent, m, wn, lgw, other);
+                    else
+                        k_combine_level_quad<<<(wn * groups * 32u + 127u) / 128u, 128, 0, stream>>>(ent, m, wn, lgw, other);
+                    count_launch();
+                    uint32_t* done = other; other = (uint32_t*)ent; ent = done;
+                    m = groups; lgw += 3;
+                }
+                k_window_combine_quad<<<wn, 32u * ((m + 7u) / 8u), 0, stream>>>(ent, m, lgw, group_sums);
+                count_launch();
+                continue;
+            }
+            k_bucket_reduce<false><<<(nthreads + 127) / 128, 128, 0, stream>>>(final_partial, final_start, plan.nbuckets, chunk, chunks_per_set, wn, red_a);
             count_launch(1);
             // tree over the per-chunk sums: groups of `tree` until one point per bucket set remains
             uint32_t per_row = chunks_per_set;
@@ -1733,7 +1833,7 @@ int msm_sort_indices(const MsmPlan& plan, const void* d_scalars, size_t n, int m
     return (int)cudaGetLastError();
 }
 int msm_items_per_bucket(const uint32_t* hist, uint32_t* items, uint32_t total_buckets, uint32_t cap, cudaStream_t stream) {
-    k_items_per_bucket<<<(total_buckets + 256) / 256, 256, 0, stream>>>(hist, items, total_buckets, cap, nullptr, 0u);
+    k_items_per_bucket<<<(total_buckets + 256) / 256, 256, 0, stream>>>(hist, items, total_buckets, cap, nullptr, 0u, 32u);
     count_launch();
     return (int)cudaGetLastError();
 }
