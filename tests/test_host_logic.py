@@ -133,3 +133,18 @@ def test_staging_copies_match_memcpy():
     bad = ctypes.c_uint32(99)
     _lib.check(_lib.lib().snarkvm_b200_selftest_host_copy(9 << 20, 0xC0DE, ctypes.byref(bad)))
     assert bad.value == 0
+
+
+def test_msm_plan_rounds_the_size_to_the_nearest_power_of_two():
+    """msm_make_plan (csrc/msm.cu): the window plan of a size just above 2^k is the plan of 2^k (a 2^20-coefficient polynomial plus a
+    few blinding terms must not fall into the 2^21 plan), the switch happens at 2^(k + 1/2); batched.rs:390-393 picks c from
+    ceil_log2 instead — parity is unaffected, any window size gives the same group element."""
+    from snarkvm_b200 import device
+    for k in (12, 16, 20, 22, 24):
+        base = device.msm_plan(1 << k)
+        assert device.msm_plan((1 << k) + 4) == {**base, "cap": device.msm_plan((1 << k) + 4)["cap"]}
+        assert device.msm_plan(int(1.40 * (1 << k)))["c"] == base["c"]
+        assert device.msm_plan(int(1.42 * (1 << k)))["c"] == device.msm_plan(1 << (k + 1))["c"]
+    for n in (1, 2, 3, 7, 1000, (1 << 26)):
+        p = device.msm_plan(n)
+        assert p["nwin"] == 253 // p["c"] + 1 and p["c"] >= 2
