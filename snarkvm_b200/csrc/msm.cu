@@ -107,6 +107,9 @@ MsmPlan msm_make_plan_batch(size_t max_n, size_t total_n) {
     if (total_n > max_n) {
         int lgt = plan_log2(total_n);
         int levels = lgt >= 23 ? 5 : lgt >= 21 ? 4 : lgt == 20 ? 3 : lgt == 19 ? 2 : 0;
+        // (a level the total asks for beyond the largest job's own plan must leave ≥ 4 points per bucket: 8 × 2^20 coefficients with
+        // c = 15 hold 64 per bucket — 4 levels 57.7 ms, 5 levels 60.4 ms, profiles/r2ag_batch.log)
+        while (levels > p.levels && ((max_n >> (p.c - 1)) >> levels) < 4) levels--;
         while (levels > 0 && ((max_n >> (p.c - 1)) >> levels) < 2) levels--;
         if (const char* e = getenv("SNARKVM_B200_MSM_LEVELS")) { int v = atoi(e); if (v >= 0 && v <= 16) levels = v; }
         if (levels > p.levels) p.levels = levels;
