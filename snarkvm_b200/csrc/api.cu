@@ -197,7 +197,10 @@ int msm_device_impl(void* out144, const void* d_points, size_t npoints, const vo
 // inter-socket links twice: 4 ranks staged 51 GB/s in total (177 ms per 2^24-point step against 113 ms alone, r2ad_bench_n4).
 // The pool's threads and the pinned staging ring are therefore kept on the device's node (SNARKVM_B200_COPY_NUMA=0 disables).
 static bool device_local_cpus(cpu_set_t* out) {
+    // default: only under a one-process-per-GPU launch (torchrun exports LOCAL_WORLD_SIZE) — a single process that drives several
+    // GPUs shares one pool, and tying it to the first device's node would hurt the others; SNARKVM_B200_COPY_NUMA=1 / 0 forces it
     if (const char* e = getenv("SNARKVM_B200_COPY_NUMA")) { if (atoi(e) == 0) return false; }
+    else { const char* lws = getenv("LOCAL_WORLD_SIZE"); if (!lws || atoi(lws) <= 1) return false; }
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return false; }
     char bus[64] = {};
