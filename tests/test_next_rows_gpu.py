@@ -63,6 +63,26 @@ def test_lagrange_basis_real_srs_and_commit_lagrange(oracle_cpu):
         KZG10.commit_lagrange(basis, _dev(evals[:100]))       # next_power_of_two(100) != 256
 
 
+def test_lagrange_basis_of_the_whole_real_srs(oracle_cpu):
+    """UniversalParams::lagrange_basis (kzg10/data_structures.rs:68-72) of all 2^15 mainnet powers-of-beta (the reference's
+    parameters/src/mainnet/resources/powers-of-beta-15.usrs, copied by tests/golden/make_golden.py): decoded on the device, every
+    basis point equal to the oracle's group iFFT, and Σ_i L_i(β)·G = powers[0] = G."""
+    import torch
+    from snarkvm_b200 import device
+    blob = open(os.path.join(HERE, "golden", "powers_of_beta_15.usrs"), "rb").read()
+    n = int.from_bytes(blob[:8], "little")
+    assert n == 1 << 15 and len(blob) == 8 + n * 96
+    powers = affine_array(py.parse_usrs_points(blob, n))
+    raw = torch.from_numpy(np.frombuffer(blob[8:], dtype=np.uint8).copy()).cuda()
+    decoded, invalid = device.srs_decode(raw)
+    assert invalid == 0 and (decoded.cpu().numpy() == powers).all()
+    basis = device.lagrange_basis(decoded).cpu().numpy().reshape(n, 104)
+    assert (basis == oracle_cpu.g1_ifft(powers)).all()
+    ones = torch.from_numpy(np.tile(py.to_limbs(1, 4), (n, 1)).astype(np.uint64).view(np.int64)).cuda()
+    total = device.msm(torch.from_numpy(basis).cuda(), ones)
+    assert total.tobytes() == py.projective_bytes_normalised(py.G1_GENERATOR)
+
+
 def test_kzg_commit_hiding_and_batch(oracle_cpu):
     from snarkvm_b200.algorithms import KZG10
     from snarkvm_b200 import device
