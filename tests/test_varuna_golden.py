@@ -115,11 +115,12 @@ def test_linear_combinations_vanish_at_their_points():
     for a batch of two instances, with and without the hiding mode's mask polynomial."""
     import random
     from oracle import varuna as ov
-    for seed, masked in ((1, False), (2, True)):
+    # shapes with |R| > |C|, |R| < |C| and non-zero domains of different sizes (the selectors at γ differ from one)
+    for seed, masked, shape in ((1, False, (3, 30, 21)), (2, True, (3, 30, 21)), (3, True, (2, 50, 70)), (4, False, (4, 17, 9)), (5, True, (5, 9, 40))):
         rng = random.Random(seed)
         wit = [(rng.randrange(2, ov.R), rng.randrange(2, ov.R)) for _ in range(2)]
-        circuit = ov.Circuit(ov.test_circuit(wit[0][0], wit[0][1], 3, 30, 21))
-        p = ov.Prover(circuit, [ov.test_circuit(a, b, 3, 30, 21) for a, b in wit])
+        circuit = ov.Circuit(ov.test_circuit(wit[0][0], wit[0][1], *shape))
+        p = ov.Prover(circuit, [ov.test_circuit(a, b, *shape) for a, b in wit])
         if masked:
             p.set_mask_poly([rng.randrange(ov.R) for _ in range(4)], [rng.randrange(ov.R) for _ in range(6)])
         r = lambda: rng.randrange(2, ov.R)      # noqa: E731
