@@ -96,3 +96,44 @@ def test_quad_lane_formulas_match_the_group_law():
     for p in pts:
         want = py.g1_add(want, p)
     assert _affine(acc1) == _affine(quad_add(left, right)) == want
+
+
+def _fold_level(entries, lgw):
+    """k_combine_level_quad / _quadseq / one level of k_window_combine_quad: groups of 8 (acc, run) entries spanning 2^lgw buckets
+    each → acc' = Σ acc_s + 2^lgw·Σ s·run_s, run' = Σ run_s (the last group may be short)"""
+    out = []
+    for g in range(0, len(entries), 8):
+        grp = entries[g:g + 8]
+        acc = sum(a for a, _ in grp) + (1 << lgw) * sum(s * r for s, (_, r) in enumerate(grp))
+        out.append((acc, sum(r for _, r in grp)))
+    return out
+
+
+def _tail(buckets, chunk):
+    """the reduction tail as msm_core launches it: per-chunk (Σ (b − lo + 1)·S_b, Σ S_b) pairs (k_bucket_reduce_quad: chunk = 8,
+    k_bucket_reduce<PAIRS>: chunk = 16), 8:1 levels while more than 64 entries are left, then the in-CTA levels down to one"""
+    entries = []
+    for lo in range(0, len(buckets), chunk):
+        part = buckets[lo:lo + chunk]
+        entries.append((sum((i + 1) * s for i, s in enumerate(part)), sum(part)))
+    lgw = chunk.bit_length() - 1
+    launches = 0
+    while len(entries) > 64:
+        entries = _fold_level(entries, lgw); lgw += 3; launches += 1
+    while True:                                             # k_window_combine_quad: 64 → 8 → 1 through shared memory
+        entries = _fold_level(entries, lgw); lgw += 3
+        if len(entries) == 1:
+            break
+    return entries[0][0], launches
+
+
+def test_weighted_fold_levels_compute_the_bucket_sum():
+    """Σ_b (b + 1)·S_b (the running-sum reduction of batched.rs:356-361) through chunk pairs and 8:1 weighted folds, with integers
+    standing in for the bucket sums (the map S ↦ k·S is linear, so the identity carries over to group elements)"""
+    rng = random.Random(3)
+    for nb, chunk in ((8, 8), (16, 8), (128, 8), (1024, 8), (4, 8), (16384, 16), (65536, 16), (1 << 19, 16)):
+        buckets = [rng.randrange(1 << 40) for _ in range(nb)]
+        got, launches = _tail(buckets, chunk)
+        assert got == sum((b + 1) * s for b, s in enumerate(buckets)), (nb, chunk)
+        # the launch counts the host code relies on: 1024 buckets / 8 = 128 entries → one level kernel, 65536 / 16 = 4096 → two
+        assert launches == {8: 0, 16: 0, 128: 0, 1024: 1, 4: 0, 16384: 2, 65536: 2, 1 << 19: 3}[nb]
