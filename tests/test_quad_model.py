@@ -137,3 +137,46 @@ def test_weighted_fold_levels_compute_the_bucket_sum():
         assert got == sum((b + 1) * s for b, s in enumerate(buckets)), (nb, chunk)
         # the launch counts the host code relies on: 1024 buckets / 8 = 128 entries → one level kernel, 65536 / 16 = 4096 → two
         assert launches == {8: 0, 16: 0, 128: 0, 1024: 1, 4: 0, 16384: 2, 65536: 2, 1 << 19: 3}[nb]
+
+
+def _fold_rounds_of(cnt, keep):
+    r = 0
+    while cnt > keep:
+        cnt = (cnt + 31) // 32; r += 1
+    return r, cnt
+
+
+def test_hot_bucket_folds_keep_their_layout():
+    """k_fold_hot_quad + the readers (k_bucket_reduce_quad with keep = 32, k_bucket_reduce<PAIRS> with keep = 1): a bucket's item
+    partials stay at its own offset, every round writes the 32:1 sums of the buckets still above `keep` to the other buffer, and each
+    bucket finds its partials in buffer (rounds mod 2) with the count fold_rounds_of gives — whatever the other buckets did."""
+    rng = random.Random(8)
+    for keep in (1, 32):
+        counts = [rng.choice([0, 1, 2, 5, 31, 32, 33, 64, 65, 700, 1025, 40000]) for _ in range(40)]
+        start = [0]
+        for c in counts:
+            start.append(start[-1] + c)
+        a = [rng.randrange(1 << 30) for _ in range(start[-1])]
+        want = [sum(a[start[b]:start[b + 1]]) for b in range(len(counts))]
+        bufs = [list(a), [None] * len(a)]
+        worst = max(counts)
+        rounds = 0
+        while worst > keep:                                  # the host loop: rounds for the worst bucket
+            src, dst = bufs[rounds & 1], bufs[(rounds + 1) & 1]
+            for b, c0 in enumerate(counts):                  # the device: only buckets still above `keep` take part
+                cnt, live = c0, True
+                for _ in range(rounds):
+                    if cnt <= keep:
+                        live = False
+                    cnt = (cnt + 31) // 32
+                if not live or cnt <= keep:
+                    continue
+                for g in range((cnt + 31) // 32):
+                    dst[start[b] + g] = sum(src[start[b] + 32 * g: start[b] + min(32 * g + 32, cnt)])
+            worst = (worst + 31) // 32
+            rounds += 1
+        for b, c0 in enumerate(counts):
+            r, cnt = _fold_rounds_of(c0, keep)
+            assert r <= rounds and cnt <= keep
+            got = sum(bufs[r & 1][start[b]: start[b] + cnt])
+            assert got == want[b], (keep, b, c0)
